@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py -- co-occurrence updates/sec of the GloVe TRAIN step on B200 (metric of BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload wiki6b|text8|cc] [--adam-mode replay|lazy|dense]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...        # the reference path's CPU restatement on the box's host cores
+
+A "step" is one full TRAIN step (gather + loss + gradient + optimizer) over one batch of B_local*N synthetic
+co-occurrence triples.  Default workload = BASELINE.json configs[2] ("wiki6b": Zipf co-occurrence, V=400k, d=300,
+Adam, B=65,536 per GPU, data-parallel at 1/2/4/8 GPUs) -- the configuration the metric's "at 1/2/4/8 B200" is quoted
+on; it fits one GPU.  ``--workload text8`` is configs[1] (V=10,001, d=64, B=65,536), ``cc`` is configs[3]'s table
+shape (V=2.2M) on replicated tables.
+
+One JSON line is printed by rank 0 (see DESIGN.md "Measurement" for every key).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    #            V        d    B_local  nnz (per job)
+    "wiki6b": (400_000, 300, 65_536, 1 << 28),
+    "text8": (10_001, 64, 65_536, 873_186),
+    "cc": (2_200_000, 300, 65_536, 1 << 28),
+}
+ADAM_K = 6  # read + write of (x, m, v)
+T0 = 2048   # global_step the steady-state emulation resumes at
+
+
+def algorithmic_bytes(B, U_r, U_c, d, k_opt=ADAM_K):
+    """B*16 + (U_r + U_c) * (4d + 4) * k_opt."""
+    return B * 16 + (U_r + U_c) * (4 * d + 4) * k_opt
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# synthetic data (SURVEY §8d cfg3 generator): Zipf(s=1) ids by inverse CDF, reject i == j, Pareto counts
+# ------------------------------------------------------------------------------------------------------------------
+def zipf_cdf(V):
+    p = 1.0 / np.arange(1, V + 1, dtype=np.float64)
+    p /= p.sum()
+    return p, np.cumsum(p)
+
+
+def gen_coo_numpy(V, n, seed):
+    rng = np.random.default_rng(seed)
+    p, cdf = zipf_cdf(V)
+    row = np.minimum(np.searchsorted(cdf, rng.random(n)), V - 1).astype(np.int32)
+    col = np.minimum(np.searchsorted(cdf, rng.random(n)), V - 1).astype(np.int32)
+    col = np.where(col == row, (col + 1) % V, col).astype(np.int32)
+    count = 10 + np.floor(np.minimum(rng.pareto(1.0, n), 1e6))
+    value = count * rng.uniform(0.3, 0.6, n)
+    return {"row": row, "col": col, "target": np.log(value).astype(np.float32),
+            "weight": np.minimum(1.0, (count / 100.0) ** 0.75).astype(np.float32)}
+
+
+def gen_coo_device(V, n, seed, device):
+    import torch
+    gen = torch.Generator(device=device).manual_seed(seed)
+    _, cdf = zipf_cdf(V)
+    cdf_t = torch.from_numpy(cdf.astype(np.float32)).to(device)
+    row = torch.empty(n, dtype=torch.int32, device=device)
+    col = torch.empty(n, dtype=torch.int32, device=device)
+    tgt = torch.empty(n, dtype=torch.float32, device=device)
+    wgt = torch.empty(n, dtype=torch.float32, device=device)
+    chunk = 1 << 24
+    for s in range(0, n, chunk):
+        m = min(chunk, n - s)
+        r = torch.searchsorted(cdf_t, torch.rand(m, device=device, generator=gen)).clamp_(max=V - 1)
+        c = torch.searchsorted(cdf_t, torch.rand(m, device=device, generator=gen)).clamp_(max=V - 1)
+        c = torch.where(c == r, (c + 1) % V, c)
+        u = torch.rand(m, device=device, generator=gen).clamp_(min=1e-6)
+        count = 10 + torch.floor(torch.clamp(1.0 / u - 1.0, max=1e6))      # Pareto(alpha=1) by inverse CDF
+        value = count * (0.3 + 0.3 * torch.rand(m, device=device, generator=gen))
+        row[s:s + m] = r.to(torch.int32)
+        col[s:s + m] = c.to(torch.int32)
+        tgt[s:s + m] = torch.log(value)
+        wgt[s:s + m] = torch.clamp((count / 100.0) ** 0.75, max=1.0)
+    return row, col, tgt, wgt
+
+
+def steady_state(eng, V, B_global, seed):
+    """Emulate resuming a long run at step T0: per-row last_step drawn from the stationary gap distribution of a row
+    with Zipf touch probability, non-zero Adam slots on rows that have been touched.  Without this a short benchmark
+    would see only first-touch rows and skip the replay work that the reference-exact Adam schedule costs."""
+    import torch
+    dev = eng.device
+    gen = torch.Generator(device=dev).manual_seed(seed)
+    p, _ = zipf_cdf(V)
+    q = -np.expm1(B_global * np.log1p(-p))                      # P(row touched in a step)
+    q_t = torch.from_numpy(q.astype(np.float32)).to(dev).clamp_(1e-12, 1 - 1e-7)
+    for side in ("row", "col"):
+        u = torch.rand(V, device=dev, generator=gen).clamp_(min=1e-12)
+        gap = torch.floor(torch.log(u) / torch.log1p(-q_t))     # Geometric(q): idle steps since last touch
+        ls = torch.where(gap < T0, T0 - gap, torch.zeros_like(gap)).to(torch.int32)
+        touched = (ls > 0).to(torch.float32)
+        m = torch.randn(V, eng.d, device=dev, generator=gen) * 1e-6 * touched[:, None]
+        v = torch.rand(V, eng.d, device=dev, generator=gen) * 1e-12 * touched[:, None]
+        eng.set_plane(side, 1, m, torch.randn(V, device=dev, generator=gen) * 1e-6 * touched)
+        eng.set_plane(side, 2, v, torch.rand(V, device=dev, generator=gen) * 1e-12 * touched)
+        eng.set_last_step(side, ls)
+        del m, v
+    eng.set_step(T0)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        self.stop_flag = True
+        rows = [r for r in self.rows if len(r) >= 7 and r[0].isdigit()]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": float(np.median([float(r[0]) for r in rows])), "sm_max_mhz": float(rows[0][1]),
+                "reasons": reasons, "samples": len(rows)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_reference(V, d, B, steps, warmup, seed=0):
+    """Times the C port of the oracle (legacy-Keras dense Adam, OpenMP over host cores) on `steps` TRAIN steps of the
+    same workload shape.  Returns (updates/s, seconds, cores)."""
+    from oracle import c_oracle, glove_oracle as o
+    n = max(B * 4, 1 << 20)
+    coo = gen_coo_numpy(V, n, seed)
+    rng = np.random.default_rng(seed + 1)
+    st = o.init_state(V, d, seed + 2)
+    co = c_oracle.COracle(st.R, st.C, st.rb, st.cb, optimizer="Adam")
+    alpha = o.alpha_table(0.001, warmup + steps + 1)
+    if warmup:
+        co.train(coo, rng.integers(0, n, (warmup, B)), alpha=alpha)
+    idx = rng.integers(0, n, (steps, B))
+    t0 = time.perf_counter()
+    co.train(coo, idx, alpha=alpha)
+    dt = time.perf_counter() - t0
+    return steps * B / dt, dt, c_oracle.num_threads()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="wiki6b", choices=sorted(WORKLOADS))
+    ap.add_argument("--adam-mode", default="replay", choices=["replay", "lazy", "dense"])
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: workload's)")
+    ap.add_argument("--nnz", type=int, default=None)
+    ap.add_argument("--plan-steps", type=int, default=16)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cold-state", action="store_true", help="start from step 0 with empty Adam state")
+    args = ap.parse_args()
+
+    V, d, B_local, nnz = WORKLOADS[args.workload]
+    B_local = args.batch or B_local
+    nnz = args.nnz or nnz
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    config = {"workload": "%s: synthetic Zipf(s=1) co-occurrence, V=%d, d=%d, Adam lr 1e-3, l2 0.01, B=%d per GPU"
+                          % (args.workload, V, d, B_local), "nnz": nnz, "batch_per_gpu": B_local}
+
+    # ---- reference arm: CPU restatement of the reference TRAIN step on host cores -------------------------------
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps = max(1, min(args.steps, 8 if V >= 100_000 else 64))   # bounded sample: a few steps of the same shape
+        warm = 1 if args.warmup else 0
+        ups, dt, cores = cpu_reference(V, d, B_local, steps, warm)
+        line = {"metric": "co-occurrence updates/sec", "value": ups, "unit": "updates/s", "n_gpus": 0, "steps": steps,
+                "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference", "config": config,
+                "cpu_baseline": {"value": ups, "unit": "updates/s", "cores": cores, "kind": "port",
+                                 "sample": "%d TRAIN steps of B=%d (requested %d), C port of the oracle, OpenMP, "
+                                           "legacy-Keras dense Adam; restatement of the reference path, not TensorFlow"
+                                           % (steps, B_local, args.steps)},
+                "e2e": {"value": ups, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from glove_tensorflow_b200.engine import GloveEngine
+    from glove_tensorflow_b200 import _lib
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    N = max(world, 1)
+    B = B_local * N                                            # global batch (weak scaling)
+    K = args.plan_steps
+    steps = (args.steps + K - 1) // K * K if not args.no_e2e else args.steps
+    total_steps = args.warmup + args.steps + 3 * K + 64
+    eng = GloveEngine(V, d, optimizer="Adam", learning_rate=0.001, l2_reg=0.01, reg_scale=2.0, head="glove",
+                      adam_mode=args.adam_mode, batch_size=B, plan_steps=K, max_steps=T0 + 2 * total_steps + steps,
+                      device=dev, dp_rank=rank, dp_world=N)
+    eng.init_uniform(seed=1)                                   # same seed on every rank: replicas start identical
+    row, col, tgt, wgt = gen_coo_device(V, nnz, 1234, dev)     # replicated COO (weak scaling: B grows with N)
+    eng.set_coo(row, col, tgt, wgt, shuffle_key=0xC0FFEE)
+    if not args.cold_state:
+        steady_state(eng, V, B, seed=99)
+    torch.cuda.synchronize()
+
+    # ---- warm-up ---------------------------------------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        eng.step()
+    torch.cuda.synchronize()
+    # distinct ids per step for the roofline figure (outside the timed region)
+    first_timed = eng.host_step
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_prep0 = 0
+    e0.record()
+    for _ in range(args.steps):
+        eng.step()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.summary() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    sc = eng.read_scalars()
+    assert sc["error"] == 0 and sc["step"] == eng.host_step, sc
+    losses = eng.loss_out[(torch.arange(first_timed, eng.host_step, device=dev) % eng.loss_cap)].cpu().numpy()
+    assert np.all(np.isfinite(losses)), "non-finite loss in the timed region"
+    value = B * args.steps / (ms * 1e-3)
+
+    # ---- roofline: per-kernel durations (CUDA events on the launching stream) + algorithmic bytes -------------------
+    U = np.array([eng.batch_counts(s)[:2] for s in range(first_timed, first_timed + min(args.steps, 32))], np.float64)
+    U_r, U_c = U.mean(0)
+    bytes_alg = algorithmic_bytes(B, U_r, U_c, d)
+    roofline, kernels_ms = None, None
+    if N == 1:
+        prof = np.array([eng.step_profiled() for _ in range(32)])
+        kernels_ms = {"stage": float(prof[:, 0].mean()), "update": float(prof[:, 1].mean()), "fix_finish": float(prof[:, 2].mean())}
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        step_ms = ms / args.steps
+        achieved = bytes_alg / (step_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6650",
+                    "kernel": "whole step = stage_kernel + update_kernel + fix_kernel (algorithmic bytes are per step)",
+                    "algorithmic_bytes_per_step": bytes_alg, "U_row": U_r, "U_col": U_c,
+                    "rho": (U_r + U_c) / (2.0 * B), "frac_of_nominal_8000": achieved / 8000.0,
+                    "kernels_ms": kernels_ms,
+                    "update_kernel_share": kernels_ms["update"] / max(sum(kernels_ms.values()), 1e-9)}
+
+    # ---- e2e: HOST buffers through the C ABI (glove_train_steps_host): H2D of every batch + D2H of every loss --------
+    e2e = None
+    if not args.no_e2e and N == 1:
+        n_chunks = max(1, args.steps // K)
+        pool = 4
+        hr = [torch.empty(K * B, dtype=torch.int32).pin_memory() for _ in range(pool)]
+        hc = [torch.empty(K * B, dtype=torch.int32).pin_memory() for _ in range(pool)]
+        ha = [torch.empty(K * B, dtype=torch.float32).pin_memory() for _ in range(pool)]
+        hb = [torch.empty(K * B, dtype=torch.float32).pin_memory() for _ in range(pool)]
+        hl = torch.empty(K, dtype=torch.float32).pin_memory()
+        for i in range(pool):
+            s = (i * K * B) % max(1, nnz - K * B)
+            hr[i].copy_(row[s:s + K * B]); hc[i].copy_(col[s:s + K * B]); ha[i].copy_(tgt[s:s + K * B]); hb[i].copy_(wgt[s:s + K * B])
+        torch.cuda.synchronize()
+        eng.train_steps_host(hr[0], hc[0], ha[0], hb[0], hl)       # warm
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for c in range(n_chunks):
+            i = c % pool
+            eng.train_steps_host(hr[i], hc[i], ha[i], hb[i], hl)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        e2e = {"value": n_chunks * K * B / dt, "unit": "updates/s", "h2d_bytes_per_step": B * 16,
+               "d2h_bytes_per_step": 4 + 4.0 / K, "steps": n_chunks * K,
+               "path": "glove_train_steps_host: pinned host COO -> H2D -> plan -> K steps -> D2H losses, per call"}
+    elif N > 1:
+        e2e = {"value": None, "unit": "updates/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
+               "path": "not measured at N>1 this round"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cpu = None
+    if not args.no_cpu_baseline and N == 1:
+        csteps = 4 if V >= 100_000 else 32
+        ups, dt, cores = cpu_reference(V, d, B_local, csteps, 1)
+        cpu = {"value": ups, "unit": "updates/s", "cores": cores, "kind": "port",
+               "sample": "%d TRAIN steps of B=%d (%.1f s), C port of the oracle with OpenMP, legacy-Keras dense Adam"
+                         % (csteps, B_local, dt)}
+
+    n_prep = (args.steps + K - 1) // K
+    line = {"metric": "co-occurrence updates/sec", "value": value, "unit": "updates/s", "n_gpus": N,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": dict(config, global_batch=B, adam_mode=args.adam_mode, parallelism="dp%d" % N,
+                           l2_flush="inputs larger than L2 (tables+slots %.1f GB, COO %.1f GB)"
+                                    % (2 * V * eng.P * eng.S * 4 / 1e9, nnz * 16 / 1e9),
+                           state="cold" if args.cold_state else "steady-state emulation at step %d" % T0),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * 3 + n_prep * 14,
+            "roofline": roofline, "cpu_baseline": cpu, "final_loss": float(losses[-1])}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

