@@ -38,11 +38,11 @@ SIGNATURES = {
     "glove_abi_version": (c_i32, []),
     "glove_table_stride": (c_i32, [c_i32]),
     "glove_table_planes": (c_i32, [c_i32]),
-    "glove_table_init": (ctypes.c_int, [c_void, c_i64, c_i32, c_i32, c_void]),
-    "glove_pack_plane": (ctypes.c_int, [c_void, c_i64, c_i32, c_i32, c_i32, c_void, c_void, c_void]),
-    "glove_unpack_plane": (ctypes.c_int, [c_void, c_i64, c_i32, c_i32, c_i32, c_void, c_void, c_void]),
-    "glove_get_last_step": (ctypes.c_int, [c_void, c_i64, c_i32, c_i32, c_void, c_void]),
-    "glove_set_last_step": (ctypes.c_int, [c_void, c_i64, c_i32, c_i32, c_void, c_void]),
+    "glove_table_init": (ctypes.c_int, [c_void, c_i64, c_i32, c_i32, c_i32, c_void]),
+    "glove_pack_plane": (ctypes.c_int, [c_void, c_i64, c_i32, c_i32, c_i32, c_i32, c_void, c_void, c_void]),
+    "glove_unpack_plane": (ctypes.c_int, [c_void, c_i64, c_i32, c_i32, c_i32, c_i32, c_void, c_void, c_void]),
+    "glove_get_last_step": (ctypes.c_int, [c_void, c_i64, c_i32, c_i32, c_i32, c_void, c_void]),
+    "glove_set_last_step": (ctypes.c_int, [c_void, c_i64, c_i32, c_i32, c_i32, c_void, c_void]),
     "glove_shuffle_indices": (ctypes.c_int, [c_u32, c_i64, c_i64, c_i64, c_void, c_void]),
     "glove_plan_bytes": (c_size, [c_i32, c_i32]),
     "glove_prepare_workspace_bytes": (c_size, [c_i32, c_i32]),
@@ -54,7 +54,7 @@ SIGNATURES = {
     "glove_train_step_profiled": (ctypes.c_int, [ctypes.POINTER(StepArgs), c_void, ctypes.POINTER(c_f32)]),
     "glove_grad_step": (ctypes.c_int, [ctypes.POINTER(StepArgs), c_void, c_void, c_void, c_void]),
     "glove_apply_step": (ctypes.c_int, [ctypes.POINTER(StepArgs), c_void, c_void, c_void, c_void]),
-    "glove_flush_lazy_state": (ctypes.c_int, [c_void, c_i64, c_i32, c_i32, c_void, c_i32, c_i32, c_f32, c_f32, c_f32,
+    "glove_flush_lazy_state": (ctypes.c_int, [c_void, c_i64, c_i32, c_i32, c_i32, c_void, c_i32, c_i32, c_f32, c_f32, c_f32,
                                               c_void]),
     "glove_eval_workspace_bytes": (c_size, [c_i64, c_i32]),
     "glove_eval_loss": (ctypes.c_int, [c_void, c_void, c_void, c_i32, c_i32, c_void, c_void, c_void, c_void, c_i64,

@@ -43,7 +43,8 @@ __global__ void __launch_bounds__(256) eval_tiles_kernel(const float *__restrict
                         const int cc = 4 * f + c;
                         const float xv = f4v(x, c), yv = f4v(y, c);
                         if (cc < d) { dot += xv * yv; nr += xv * xv; nc += yv * yv; }
-                        else if (cc == d) { rb = xv; cb = yv; }
+                        else if (cc == d) rb = xv;          // row table: bias in column d
+                        else if (cc == d + 1) cb = yv;      // col table: bias in column d + 1
                     }
                 }
             }

@@ -166,10 +166,19 @@ __global__ void fill_kernel(int32_t N, int32_t B, PrepSide ps, const int32_t *__
                             const float *__restrict__ A, const float *__restrict__ Bv, PlanSide out) {
     for (int32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < N; q += gridDim.x * blockDim.x) {
         const uint32_t p = ps.vals_out[q];
-        out.oslot[q] = other_slot_of_p[p];
-        out.owner[q] = (int32_t)(p % (uint32_t)B);
-        out.a[q] = A[p];
-        out.b[q] = Bv[p];
+        out.rec[q] = make_int4(other_slot_of_p[p], __float_as_int(A[p]), __float_as_int(Bv[p]), (int32_t)(p % (uint32_t)B));
+    }
+}
+
+__global__ void itemrec_kernel(int32_t B, const int32_t *__restrict__ n_items, PlanSide out) {
+    const int32_t NI = *n_items;
+    for (int32_t it = blockIdx.x * blockDim.x + threadIdx.x; it < NI; it += gridDim.x * blockDim.x) {
+        const int32_t g = out.item_seg[it], start = out.item_start[it];
+        const int32_t k = start / B;
+        const int32_t seg_end = out.seg_start[g + 1], seg_len = seg_end - out.seg_start[g];
+        const int32_t n = min(start + kItemMax, seg_end) - start;
+        const int32_t part = seg_len > kItemMax ? out.item_part[it] - out.b_part[k] + 1 : 0;
+        out.item_rec[it] = make_int4(out.seg_id[g], g - out.b_seg[k], start, n | (part << 8));
     }
 }
 
@@ -252,6 +261,7 @@ int glove_prepare_batches(void *plan, void *workspace, size_t workspace_bytes, c
         GLOVE_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(w.cub_temp, tb, ps.f_part, ps.e_part, N, stream));
         items_kernel<<<blocks, threads, 0, stream>>>(N, B, K, ps, pv.side[s], pv.hdr, s);
         slots_kernel<<<blocks, threads, 0, stream>>>(N, B, ps, pv.side[s]);
+        itemrec_kernel<<<blocks, threads, 0, stream>>>(B, &pv.hdr->n_item[s], pv.side[s]);
         GLOVE_CHECK_LAUNCH();
     }
     for (int s = 0; s < 2; ++s)

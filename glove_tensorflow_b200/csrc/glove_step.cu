@@ -1,31 +1,39 @@
 // TRAIN step: model_fn(mode=TRAIN) of the reference [ref src/models/estimator.py:13-56] as three sm_100a kernels.
 //
 //   stage_kernel   one warp per distinct row / col id of the batch: (replay missed idle Adam steps,) publish the
-//                  pre-step row into a compact L2-resident snapshot cache[side][slot][S].
+//                  pre-step row into a compact L2-resident snapshot snap[side][slot][S].  A snapshot row is
+//                  [x_0..x_{d-1} | bias at column d+side | 1.0 at column d+1-side | 0..], so that
+//                  dot(snap_row[i], snap_col[j]) over all S columns = sum_k R_ik C_jk + rb_i + cb_j with no masking,
+//                  and sum_b e_b * snap_opposite lands the bias gradient sum_b e_b in the own bias column for free.
 //   update_kernel  one warp per work item (<= kItemMax triples of one id, both sides in one launch): gather the
-//                  opposite rows from the snapshot with 128-bit loads, warp-shuffle dot product, residual, loss,
-//                  gradient accumulation in registers, and -- when the item is the whole segment -- the fused sparse
-//                  optimizer update written in place to the packed table.  Because all forward reads come from the
-//                  snapshot, the row side and the col side never race (SURVEY §7 hard part 2).
-//   fix_kernel     segments longer than kItemMax: partial sums are combined in fixed order (one CTA per segment, one
-//                  thread per column) and updated; the last CTA to finish reduces the per-item loss terms in fixed
-//                  order, updates the scalar global bias, publishes the loss and increments the device step counter.
+//                  opposite rows from the snapshot with 128-bit loads (software-pipelined one triple ahead),
+//                  warp-shuffle dot product, residual, loss, gradient accumulation in registers, and -- when the item
+//                  is the whole segment -- the fused sparse optimizer update written in place to the packed table.
+//                  All forward reads come from the snapshot, so the row side and the col side never race
+//                  (SURVEY §7 hard part 2) and both sides run in one launch.
+//   fix_kernel     segments longer than kItemMax: partial sums are combined in a fixed order (one CTA per segment) and
+//                  updated; every CTA pre-reduces a slice of the per-item loss terms, and the last CTA to finish sums
+//                  those in CTA order, updates the scalar global bias, publishes the loss and increments the device
+//                  step counter.
 //
-// Everything is deterministic: no floating-point atomics, fixed summation order given (B, kItemMax).
+// Everything is deterministic: no floating-point atomics, fixed summation order given (B, kItemMax, grid size).
 #include "glove_common.cuh"
 
 namespace glove {
 
 enum { MODE_TRAIN = 0, MODE_GRAD = 1, MODE_APPLY = 2 };
+constexpr int kFixThreads = 256;
+constexpr int kFixBlocks = kNumSMs;
 
 struct StepParams {
     float *table[2];
     glove_scalars *sc;
     const PlanHeader *hdr;
     PlanSide side[2];
-    float *cache[2];
-    float *partial[2];
-    float4 *item_out[2];
+    float *snap[2];       // [B][S] pre-step snapshot rows
+    float *partial[2];    // [max parts][S] partial gradient sums of split segments
+    float4 *item_out[2];  // [max items] {data loss, sum e, reg term, 0}
+    double *cta_out;      // [kFixBlocks][3] per-CTA pre-reduced loss terms
     float *grad[2];       // MODE_GRAD / MODE_APPLY: dense per-slot gradient buffers
     float *grad_scalars;  // [4]
     const float *alpha;
@@ -39,9 +47,10 @@ struct StepParams {
 };
 
 struct StepWs {
-    float *cache[2];
+    float *snap[2];
     float *partial[2];
     float4 *item_out[2];
+    double *cta_out;
     size_t bytes;
 };
 static inline int64_t max_items_per_batch(int32_t B) { return (int64_t)B + B / kItemMax + 2; }
@@ -52,9 +61,10 @@ static StepWs step_ws_view(void *base, int32_t B, int32_t d) {
     size_t off = 0;
     auto take = [&](size_t bytes) { char *r = p ? p + off : nullptr; off += align_up(bytes); return r; };
     const int32_t S = table_stride(d);
-    for (int s = 0; s < 2; ++s) w.cache[s] = (float *)take(sizeof(float) * (size_t)B * S);
+    for (int s = 0; s < 2; ++s) w.snap[s] = (float *)take(sizeof(float) * (size_t)B * S);
     for (int s = 0; s < 2; ++s) w.partial[s] = (float *)take(sizeof(float) * (size_t)max_parts_per_batch(B) * S);
     for (int s = 0; s < 2; ++s) w.item_out[s] = (float4 *)take(sizeof(float4) * (size_t)max_items_per_batch(B));
+    w.cta_out = (double *)take(sizeof(double) * 3 * kFixBlocks);
     w.bytes = off;
     return w;
 }
@@ -69,6 +79,31 @@ __device__ __forceinline__ float row_col(const float4 (&x)[NV], int col, int lan
     for (int rr = 0; rr < NV; ++rr)
         if (rr == r) v = (c == 0 ? x[rr].x : c == 1 ? x[rr].y : c == 2 ? x[rr].z : x[rr].w);
     return __shfl_sync(0xffffffffu, v, src);
+}
+
+template <int NV>
+__device__ __forceinline__ void load_row(float4 (&x)[NV], const float *row, int lane, int S4) {
+#pragma unroll
+    for (int r = 0; r < NV; ++r) {
+        const int f = lane + 32 * r;
+        x[r] = (r < NV - 1 || f < S4) ? ld4(row + 4 * f) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+template <int NV>
+__device__ __forceinline__ void load_row_nc(float4 (&x)[NV], const float *row, int lane, int S4) {
+#pragma unroll
+    for (int r = 0; r < NV; ++r) {
+        const int f = lane + 32 * r;
+        x[r] = (r < NV - 1 || f < S4) ? ld4_nc(row + 4 * f) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+template <int NV>
+__device__ __forceinline__ void store_row(float *row, const float4 (&x)[NV], int lane, int S4) {
+#pragma unroll
+    for (int r = 0; r < NV; ++r) {
+        const int f = lane + 32 * r;
+        if (r < NV - 1 || f < S4) st4(row + 4 * f, x[r]);
+    }
 }
 
 __device__ __forceinline__ bool batch_index(const StepParams &p, int &k, int &step) {
@@ -89,8 +124,9 @@ __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf
 __device__ __forceinline__ void head_eval(int head, float z, float a, float b, float invB, float nf, float &e, float &l) {
     if (head == GLOVE_HEAD_GLOVE) {  // a = target, b = weight
         const float r = z - a;
-        l = b * r * r;
-        e = (2.0f * invB) * b * r;
+        const float br = b * r;
+        l = br * r;
+        e = (2.0f * invB) * br;
     } else {  // a = pos weight (value), b = neg weight
         const float sg = sigmoid_f(z);
         l = a * softplus_f(-z) + nf * (b * softplus_f(z));
@@ -99,7 +135,9 @@ __device__ __forceinline__ void head_eval(int head, float z, float a, float b, f
 }
 
 // ---- K1: stage -----------------------------------------------------------------------------------------------------
-template <int NV>
+// Flat mapping: one thread per (slot, float4) of the snapshot, a warp per 32 consecutive float4s.  Rows that need no
+// replay are a pure 128-bit copy; rows that do are replayed 4 columns per thread, so a long gap is spread over the
+// ~S/4 threads of the row instead of serialising on one warp, and the many small chunks balance across the SMs.
 __global__ void __launch_bounds__(256) stage_kernel(const StepParams p) {
     int k, step;
     if (!batch_index(p, k, step)) return;
@@ -109,278 +147,239 @@ __global__ void __launch_bounds__(256) stage_kernel(const StepParams p) {
     const int U0 = p.side[0].b_seg[k + 1] - seg0[0], U1 = p.side[1].b_seg[k + 1] - seg0[1];
     const int S4 = p.S >> 2;
     const bool replay = (p.opt == GLOVE_OPT_ADAM && p.adam_mode == GLOVE_ADAM_REPLAY);
-    for (int w = warp; w < U0 + U1; w += nwarps) {
+    const int total = (U0 + U1) * S4;
+    for (int base = warp * 32; base < total; base += nwarps * 32) {
+        const int idx = base + lane;
+        const bool active = idx < total;
+        const int w = active ? idx / S4 : 0, f = active ? idx - w * S4 : 0;
         const int s = w >= U0 ? 1 : 0;
         const int slot = s ? w - U0 : w;
         const int id = p.side[s].seg_id[seg0[s] + slot];
         const float *row = p.table[s] + (int64_t)id * p.P * p.S;
-        float4 x[NV];
-#pragma unroll
-        for (int r = 0; r < NV; ++r) {
-            const int f = lane + 32 * r;
-            x[r] = f < S4 ? ld4(row + 4 * f) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        const int lcol = ls_col(p.d, s);
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        int ls = 0;
+        if (active) { x = ld4(row + 4 * f); ls = __float_as_int(__ldg(row + lcol)); }
         if (replay) {
-            const int ls = __float_as_int(row_col<NV>(x, p.d + 1, lane));
-            if (ls > 0 && ls < step) {
-                // Padding columns (col > d, and lanes beyond the row) hold m = v = 0: a 0 / eps division sends the whole
-                // warp through the IEEE slow path on every step.  They get dummy operands (m = v = 1) in registers and
-                // are rebuilt when the row is stored.
-                float4 m[NV], v[NV];
-#pragma unroll
-                for (int r = 0; r < NV; ++r) {
-                    const int f = lane + 32 * r;
-                    m[r] = f < S4 ? ld4(row + p.S + 4 * f) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    v[r] = f < S4 ? ld4(row + 2 * p.S + 4 * f) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        if (4 * f + c > p.d) { f4c(m[r], c) = 1.0f; f4c(v[r], c) = 1.0f; }
-                }
-                for (int t = ls; t < step; ++t) {
-                    const float a = __ldg(p.alpha + t);
-                    bool changed = false;
-#pragma unroll
-                    for (int r = 0; r < NV; ++r) {
-                        const int f = lane + 32 * r;
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            const float old = f4c(x[r], c);
-                            adam_idle_step(f4c(x[r], c), f4c(m[r], c), f4c(v[r], c), a, p.b1, p.b2, p.eps);
-                            changed |= (4 * f + c <= p.d) && (f4c(x[r], c) != old);
-                        }
+            const bool need = active && ls > 0 && ls < step;
+            float4 m = make_float4(0.f, 0.f, 0.f, 0.f), v = m;
+            if (need) { m = ld4(row + p.S + 4 * f); v = ld4(row + 2 * p.S + 4 * f); }
+            float2 xa = make_float2(x.x, x.y), xb = make_float2(x.z, x.w);
+            float2 ma = make_float2(m.x, m.y), mb = make_float2(m.z, m.w);
+            float2 va = make_float2(v.x, v.y), vb = make_float2(v.z, v.w);
+            int t = need ? ls : step;
+            bool moving = need;
+            // |increment| shrinks monotonically (x0.9 per step from m, at most x1.012 from alpha and sqrt(v)): once an
+            // element stops moving it never moves again; from then on only the m, v decays remain (2 packed multiplies).
+            while (__any_sync(0xffffffffu, t < step)) {
+                if (t < step) {
+                    if (moving) {
+                        const float na = -__ldg(p.alpha + t);
+                        const float2 oa = xa, ob = xb;
+                        adam_idle_step2(xa, ma, va, na, p.b1, p.b2, p.eps);
+                        adam_idle_step2(xb, mb, vb, na, p.b1, p.b2, p.eps);
+                        moving = (xa.x != oa.x) | (xa.y != oa.y) | (xb.x != ob.x) | (xb.y != ob.y);
+                    } else {
+                        ma = __fmul2_rn(ma, f2(p.b1)); mb = __fmul2_rn(mb, f2(p.b1));
+                        va = __fmul2_rn(va, f2(p.b2)); vb = __fmul2_rn(vb, f2(p.b2));
                     }
-                    // |increment| shrinks monotonically (x0.9 per step from m, at most x1.012 from alpha and sqrt(v)):
-                    // once no element of the row moves, none ever will again -> the remaining steps are exact no-ops on x
-                    if (!__any_sync(0xffffffffu, changed)) break;
-                }
-#pragma unroll
-                for (int r = 0; r < NV; ++r) {
-                    const int f = lane + 32 * r;
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const int col = 4 * f + c;
-                        if (col == p.d + 1) f4c(x[r], c) = __int_as_float(ls);
-                        else if (col > p.d + 1) f4c(x[r], c) = 0.0f;
-                    }
+                    ++t;
                 }
             }
+            if (need) {
+                // the row is current through step-1 now: publish the decayed moments so that the update kernel reads
+                // them as-is (the x plane of the table is rewritten by the update in this same step)
+                x = make_float4(xa.x, xa.y, xb.x, xb.y);
+                st4(const_cast<float *>(row) + p.S + 4 * f, make_float4(ma.x, ma.y, mb.x, mb.y));
+                st4(const_cast<float *>(row) + 2 * p.S + 4 * f, make_float4(va.x, va.y, vb.x, vb.y));
+            }
         }
-        float *dst = p.cache[s] + (int64_t)slot * p.S;
-#pragma unroll
-        for (int r = 0; r < NV; ++r) {
-            const int f = lane + 32 * r;
-            if (f < S4) st4(dst + 4 * f, x[r]);
+        if (active) {
+            // snapshot: 1.0 in the other side's bias column (= this side's last_step column)
+            if ((lcol >> 2) == f) f4c(x, lcol & 3) = 1.0f;
+            st4(p.snap[s] + (int64_t)slot * p.S + 4 * f, x);
         }
     }
 }
 
 // ---- optimizer epilogue on a row held in registers ---------------------------------------------------------------
+// x = pre-step snapshot row (1.0 in the last_step column), G = de-duplicated gradient (0 outside columns 0..d-1 and
+// the bias column).  Padding columns carry x = G = m = v = 0 and stay 0 through every formula below.  In replay mode the
+// stage kernel has already decayed m, v through step-1, so the moments are read as-is.
 template <int NV>
 __device__ __forceinline__ void apply_row(const StepParams &p, float *row, float4 (&x)[NV], const float4 (&G)[NV],
-                                          int ls, int step, int lane) {
+                                          int s, int step, int lane) {
     const int S4 = p.S >> 2;
-    // Padding columns (col > d) carry G = m = v = 0; 0 / eps would drag the warp through the IEEE-division slow path,
-    // so they run on dummy operands (1) and are written back as zeros.
     if (p.opt == GLOVE_OPT_ADAM) {
         float4 m[NV], v[NV];
+        load_row<NV>(m, row + p.S, lane, S4);
+        load_row<NV>(v, row + 2 * p.S, lane, S4);
+        const float na = -__ldg(p.alpha + step);
 #pragma unroll
         for (int r = 0; r < NV; ++r) {
-            const int f = lane + 32 * r;
-            m[r] = f < S4 ? ld4(row + p.S + 4 * f) : make_float4(0.f, 0.f, 0.f, 0.f);
-            v[r] = f < S4 ? ld4(row + 2 * p.S + 4 * f) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float2 xa = make_float2(x[r].x, x[r].y), xb = make_float2(x[r].z, x[r].w);
+            float2 ma = make_float2(m[r].x, m[r].y), mb = make_float2(m[r].z, m[r].w);
+            float2 va = make_float2(v[r].x, v[r].y), vb = make_float2(v[r].z, v[r].w);
+            adam_update2(xa, ma, va, make_float2(G[r].x, G[r].y), na, p.b1, p.b2, p.eps);
+            adam_update2(xb, mb, vb, make_float2(G[r].z, G[r].w), na, p.b1, p.b2, p.eps);
+            x[r] = make_float4(xa.x, xa.y, xb.x, xb.y);
+            m[r] = make_float4(ma.x, ma.y, mb.x, mb.y);
+            v[r] = make_float4(va.x, va.y, vb.x, vb.y);
         }
-        if (p.adam_mode == GLOVE_ADAM_REPLAY && ls > 0) {
-            for (int t = ls; t < step; ++t) {
-#pragma unroll
-                for (int r = 0; r < NV; ++r) {
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        f4c(m[r], c) = __fmul_rn(f4c(m[r], c), p.b1);
-                        f4c(v[r], c) = __fmul_rn(f4c(v[r], c), p.b2);
-                    }
-                }
-            }
-        }
-        const float a = __ldg(p.alpha + step);
-#pragma unroll
-        for (int r = 0; r < NV; ++r) {
-            const int f = lane + 32 * r;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const bool pad = 4 * f + c > p.d;
-                float mm = pad ? 1.0f : f4c(m[r], c), vv = pad ? 1.0f : f4c(v[r], c);
-                adam_update(f4c(x[r], c), mm, vv, pad ? 1.0f : f4v(G[r], c), a, p.b1, p.b2, p.eps);
-                f4c(m[r], c) = pad ? 0.0f : mm;
-                f4c(v[r], c) = pad ? 0.0f : vv;
-            }
-            if (f < S4) { st4(row + p.S + 4 * f, m[r]); st4(row + 2 * p.S + 4 * f, v[r]); }
-        }
+        store_row<NV>(row + p.S, m, lane, S4);
+        store_row<NV>(row + 2 * p.S, v, lane, S4);
     } else if (p.opt == GLOVE_OPT_ADAGRAD) {
+        float4 acc[NV];
+        load_row<NV>(acc, row + p.S, lane, S4);
 #pragma unroll
         for (int r = 0; r < NV; ++r) {
-            const int f = lane + 32 * r;
-            float4 acc = f < S4 ? ld4(row + p.S + 4 * f) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const bool pad = 4 * f + c > p.d;
-                float aa = pad ? 1.0f : f4c(acc, c);
-                adagrad_update(f4c(x[r], c), aa, pad ? 1.0f : f4v(G[r], c), p.lr, p.eps);
-                f4c(acc, c) = pad ? 0.0f : aa;
-            }
-            if (f < S4) st4(row + p.S + 4 * f, acc);
+            float2 xa = make_float2(x[r].x, x[r].y), xb = make_float2(x[r].z, x[r].w);
+            float2 aa = make_float2(acc[r].x, acc[r].y), ab = make_float2(acc[r].z, acc[r].w);
+            adagrad_update2(xa, aa, make_float2(G[r].x, G[r].y), -p.lr, p.eps);
+            adagrad_update2(xb, ab, make_float2(G[r].z, G[r].w), -p.lr, p.eps);
+            x[r] = make_float4(xa.x, xa.y, xb.x, xb.y);
+            acc[r] = make_float4(aa.x, aa.y, ab.x, ab.y);
         }
+        store_row<NV>(row + p.S, acc, lane, S4);
     } else {
 #pragma unroll
         for (int r = 0; r < NV; ++r)
 #pragma unroll
             for (int c = 0; c < 4; ++c) sgd_update(f4c(x[r], c), f4v(G[r], c), p.lr);
     }
-    // plane 0: new x, bias, last_step = step + 1, zero padding
+    const int lcol = ls_col(p.d, s);
 #pragma unroll
     for (int r = 0; r < NV; ++r) {
         const int f = lane + 32 * r;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const int col = 4 * f + c;
-            if (col == p.d + 1) f4c(x[r], c) = __int_as_float(step + 1);
-            else if (col > p.d + 1) f4c(x[r], c) = 0.0f;
-        }
-        if (f < S4) st4(row + 4 * f, x[r]);
+        for (int c = 0; c < 4; ++c)
+            if (4 * f + c == lcol) f4c(x[r], c) = __int_as_float(step + 1);
     }
+    store_row<NV>(row, x, lane, S4);
 }
 
 // ---- K2: update ----------------------------------------------------------------------------------------------------
-template <int NV, int G>
-__global__ void __launch_bounds__(128) update_kernel(const StepParams p) {
+template <int NV>
+__device__ __forceinline__ float dot_row(const float4 (&x)[NV], const float4 (&y)[NV]) {
+    float2 a = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < NV; ++r) {
+        a = __ffma2_rn(make_float2(x[r].x, x[r].y), make_float2(y[r].x, y[r].y), a);
+        a = __ffma2_rn(make_float2(x[r].z, x[r].w), make_float2(y[r].z, y[r].w), a);
+    }
+    return warp_sum(a.x + a.y);
+}
+template <int NV>
+__device__ __forceinline__ void axpy_row(float4 (&acc)[NV], float e, const float4 (&y)[NV]) {
+    const float2 ee = make_float2(e, e);
+#pragma unroll
+    for (int r = 0; r < NV; ++r) {
+        const float2 lo = __ffma2_rn(ee, make_float2(y[r].x, y[r].y), make_float2(acc[r].x, acc[r].y));
+        const float2 hi = __ffma2_rn(ee, make_float2(y[r].z, y[r].w), make_float2(acc[r].z, acc[r].w));
+        acc[r] = make_float4(lo.x, lo.y, hi.x, hi.y);
+    }
+}
+
+template <int NV, int HEAD, bool DP>
+__global__ void __launch_bounds__(128, (NV <= 3 ? 5 : 3)) update_kernel(const StepParams p) {
     int k, step;
     if (!batch_index(p, k, step)) return;
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-    const int it0[2] = {p.side[0].b_item[k], p.side[1].b_item[k]};
-    const int nI0 = p.side[0].b_item[k + 1] - it0[0], nI1 = p.side[1].b_item[k + 1] - it0[1];
     const int S4 = p.S >> 2;
     const float gbias = p.sc->g;
     const float invB = 1.0f / (float)p.B;
     const float ce = (2.0f * p.rs * p.l2) / ((float)p.d * (float)p.B), cbias = (2.0f * p.rs * p.l2) / (float)p.B;
+    const float reg_unscale = (float)p.B / (2.0f * p.rs);  // coef * reg_unscale = l2/d (embedding) | l2 (bias)
 
-    for (int w = warp; w < nI0 + nI1; w += nwarps) {
-        const int s = w >= nI0 ? 1 : 0;
-        const int itl = s ? w - nI0 : w;
+#pragma unroll 1
+    for (int s = 0; s < 2; ++s) {
         const PlanSide &ps = p.side[s];
-        const int it = it0[s] + itl;
-        const int g = ps.item_seg[it];
-        const int slot = g - ps.b_seg[k];
-        const int start = ps.item_start[it];
-        const int seg_begin = ps.seg_start[g], seg_end = ps.seg_start[g + 1];
-        const int end = min(start + kItemMax, seg_end);
-        const float *own = p.cache[s] + (int64_t)slot * p.S;
-        const float *opp_base = p.cache[1 - s];
-
-        float4 x[NV], dv[NV], acc[NV];
-#pragma unroll
-        for (int r = 0; r < NV; ++r) {
-            const int f = lane + 32 * r;
-            x[r] = f < S4 ? ld4(own + 4 * f) : make_float4(0.f, 0.f, 0.f, 0.f);
-            acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const int col = 4 * f + c;
-                f4c(dv[r], c) = col < p.d ? f4c(x[r], c) : (col == p.d ? 1.0f : 0.0f);
-            }
-        }
-        const float bias_own = row_col<NV>(x, p.d, lane);
-        const int ls = __float_as_int(row_col<NV>(x, p.d + 1, lane));
-        float sum_e = 0.0f, loss_d = 0.0f;
-        int n_eff = 0;
-
-        for (int q = start; q < end; q += G) {
-            float4 o[G][NV];
-            float a[G], b[G];
-            bool valid[G];
-#pragma unroll
-            for (int t = 0; t < G; ++t) {
-                valid[t] = (q + t) < end;
-                int os = 0;
-                a[t] = 0.0f; b[t] = 0.0f;
-                if (valid[t] && p.dp_world > 1) valid[t] = (ps.owner[q + t] / p.dp_block) == p.dp_rank;
-                if (valid[t]) { os = ps.oslot[q + t]; a[t] = ps.a[q + t]; b[t] = ps.b[q + t]; }
-                const float *orow = opp_base + (int64_t)os * p.S;
-#pragma unroll
-                for (int r = 0; r < NV; ++r) {
-                    const int f = lane + 32 * r;
-                    o[t][r] = (valid[t] && f < S4) ? ld4_nc(orow + 4 * f) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-            }
-            float dot[G];
-#pragma unroll
-            for (int t = 0; t < G; ++t) {
-                float acc_d = 0.0f;
-#pragma unroll
-                for (int r = 0; r < NV; ++r)
-                    acc_d += dv[r].x * o[t][r].x + dv[r].y * o[t][r].y + dv[r].z * o[t][r].z + dv[r].w * o[t][r].w;
-                dot[t] = acc_d;
-            }
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-#pragma unroll
-                for (int t = 0; t < G; ++t) dot[t] += __shfl_xor_sync(0xffffffffu, dot[t], off);
-            }
-#pragma unroll
-            for (int t = 0; t < G; ++t) {
-                if (!valid[t]) continue;  // warp-uniform
-                const float z = (dot[t] + bias_own) + gbias;  // dot already holds the opposite bias (dv[col d] = 1)
-                float e, l;
-                head_eval(p.head, z, a[t], b[t], invB, p.nf, e, l);
-                sum_e += e;
-                loss_d += l;
-                ++n_eff;
-#pragma unroll
-                for (int r = 0; r < NV; ++r) {
-                    acc[r].x += e * o[t][r].x; acc[r].y += e * o[t][r].y;
-                    acc[r].z += e * o[t][r].z; acc[r].w += e * o[t][r].w;
-                }
-            }
-        }
-
-        // activity-L2 gradient (n occurrences of this id) and loss term; bias gradient goes to column d
-        const float fn = (float)n_eff;
-        float sq = 0.0f;
+        const int it0 = ps.b_item[k], nI = ps.b_item[k + 1] - it0;
+        const float *opp_base = p.snap[1 - s];
+        const int4 *rec = ps.rec;
+        // per-lane activity-L2 coefficients of this side: 2 s l2/(d B) on the embedding columns, 2 s l2/B on the bias
+        // column, 0 elsewhere (a zero also marks the columns of the accumulator that must be cleared)
+        const int bcol = bias_col(p.d, s);
+        float4 coef[NV];
 #pragma unroll
         for (int r = 0; r < NV; ++r) {
             const int f = lane + 32 * r;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 const int col = 4 * f + c;
-                const float xv = f4c(x[r], c);
-                if (col < p.d) { f4c(acc[r], c) += fn * ce * xv; sq += xv * xv; }
-                else if (col == p.d) f4c(acc[r], c) = sum_e + fn * cbias * xv;
-                else f4c(acc[r], c) = 0.0f;
+                f4c(coef[r], c) = col < p.d ? ce : (col == bcol ? cbias : 0.0f);
             }
         }
-        sq = warp_sum(sq);
-        if (lane == 0) {
-            const float regp = fn * ((p.l2 / (float)p.d) * sq + p.l2 * bias_own * bias_own);
-            p.item_out[s][itl] = make_float4(s == 0 ? loss_d : 0.0f, s == 0 ? sum_e : 0.0f, regp, 0.0f);
-        }
+#pragma unroll 1
+        for (int itl = warp; itl < nI; itl += nwarps) {
+            const int4 ir = __ldg(ps.item_rec + it0 + itl);
+            const int slot = ir.y, start = ir.z, n = ir.w & 0xff, part = ir.w >> 8;
 
-        const bool whole = (seg_end - seg_begin) <= kItemMax;
-        if (!whole) {
-            float *dst = p.partial[s] + (int64_t)(ps.item_part[it] - ps.b_part[k]) * p.S;
+            float4 x[NV], acc[NV], bufA[NV], bufB[NV];
+            load_row<NV>(x, p.snap[s] + (int64_t)slot * p.S, lane, S4);
+#pragma unroll
+            for (int r = 0; r < NV; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+            float loss_d = 0.0f, sum_e = 0.0f;
+            int n_eff = 0;
+
+            // two triples per iteration with ping-pong buffers: the opposite row of triple q+1 (q+2) is in flight while
+            // triple q (q+1) is reduced
+            int4 rcA = __ldg(rec + start), rcB = rcA;
+            load_row_nc<NV>(bufA, opp_base + (int64_t)rcA.x * p.S, lane, S4);
+#pragma unroll 1
+            for (int q = 0; q < n; q += 2) {
+                const bool hasB = q + 1 < n;
+                if (hasB) {
+                    rcB = __ldg(rec + start + q + 1);
+                    load_row_nc<NV>(bufB, opp_base + (int64_t)rcB.x * p.S, lane, S4);
+                }
+                {
+                    float e, l;
+                    head_eval(HEAD, dot_row<NV>(x, bufA) + gbias, __int_as_float(rcA.y), __int_as_float(rcA.z), invB, p.nf, e, l);
+                    if (DP) { const bool mine = rcA.w / p.dp_block == p.dp_rank; e = mine ? e : 0.f; l = mine ? l : 0.f; n_eff += mine; }
+                    loss_d += l; sum_e += e;
+                    axpy_row<NV>(acc, e, bufA);
+                }
+                if (hasB) {
+                    if (q + 2 < n) {
+                        rcA = __ldg(rec + start + q + 2);
+                        load_row_nc<NV>(bufA, opp_base + (int64_t)rcA.x * p.S, lane, S4);
+                    }
+                    float e, l;
+                    head_eval(HEAD, dot_row<NV>(x, bufB) + gbias, __int_as_float(rcB.y), __int_as_float(rcB.z), invB, p.nf, e, l);
+                    if (DP) { const bool mine = rcB.w / p.dp_block == p.dp_rank; e = mine ? e : 0.f; l = mine ? l : 0.f; n_eff += mine; }
+                    loss_d += l; sum_e += e;
+                    axpy_row<NV>(acc, e, bufB);
+                }
+            }
+            if (!DP) n_eff = n;
+
+            // activity-L2: gradient n*coef_c*x_c and loss n*(l2/d sum x^2 + l2 bias^2).  The bias column of acc already
+            // holds sum_b e_b; the column where the opposite bias was multiplied in (coef == 0) is cleared.
+            const float fn = (float)n_eff;
+            float sq = 0.0f;
 #pragma unroll
             for (int r = 0; r < NV; ++r) {
-                const int f = lane + 32 * r;
-                if (f < S4) st4(dst + 4 * f, acc[r]);
-            }
-        } else if (p.mode == MODE_GRAD) {
-            float *dst = p.grad[s] + (int64_t)slot * p.S;
 #pragma unroll
-            for (int r = 0; r < NV; ++r) {
-                const int f = lane + 32 * r;
-                if (f < S4) st4(dst + 4 * f, acc[r]);
+                for (int c = 0; c < 4; ++c) {
+                    const float cf = f4c(coef[r], c), xv = f4c(x[r], c);
+                    const float cx = cf * xv;
+                    f4c(acc[r], c) = (cf != 0.0f ? f4c(acc[r], c) : 0.0f) + fn * cx;
+                    sq += cx * xv;
+                }
             }
-        } else {
-            float *row = p.table[s] + (int64_t)ps.seg_id[g] * p.P * p.S;
-            apply_row<NV>(p, row, x, acc, ls, step, lane);
+            sq = warp_sum(sq);
+            if (lane == 0)
+                p.item_out[s][itl] = make_float4(s == 0 ? loss_d : 0.0f, s == 0 ? sum_e : 0.0f, fn * reg_unscale * sq, 0.0f);
+
+            if (part) {
+                store_row<NV>(p.partial[s] + (int64_t)(part - 1) * p.S, acc, lane, S4);
+            } else if (p.mode == MODE_GRAD) {
+                store_row<NV>(p.grad[s] + (int64_t)slot * p.S, acc, lane, S4);
+            } else {
+                apply_row<NV>(p, p.table[s] + (int64_t)ir.x * p.P * p.S, x, acc, s, step, lane);
+            }
         }
     }
 }
@@ -401,52 +400,16 @@ __global__ void __launch_bounds__(128) apply_kernel(const StepParams p) {
         const int id = p.side[s].seg_id[seg0[s] + slot];
         float *row = p.table[s] + (int64_t)id * p.P * p.S;
         float4 x[NV], G[NV];
-#pragma unroll
-        for (int r = 0; r < NV; ++r) {
-            const int f = lane + 32 * r;
-            x[r] = f < S4 ? ld4(p.cache[s] + (int64_t)slot * p.S + 4 * f) : make_float4(0.f, 0.f, 0.f, 0.f);
-            G[r] = f < S4 ? ld4(p.grad[s] + (int64_t)slot * p.S + 4 * f) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        const int ls = __float_as_int(row_col<NV>(x, p.d + 1, lane));
-        apply_row<NV>(p, row, x, G, ls, step, lane);
+        load_row<NV>(x, p.snap[s] + (int64_t)slot * p.S, lane, S4);
+        load_row<NV>(G, p.grad[s] + (int64_t)slot * p.S, lane, S4);
+        apply_row<NV>(p, row, x, G, s, step, lane);
     }
 }
 
 // ---- K3: long segments + finish --------------------------------------------------------------------------------------
-__device__ void finish_step(const StepParams &p, int k, int step, const float *reduced /* MODE_APPLY */) {
-    __shared__ double sh[3][256];
-    const int tid = threadIdx.x;
-    double ld = 0.0, se = 0.0, rg = 0.0;
-    if (reduced == nullptr) {
-        const int nI0 = p.side[0].b_item[k + 1] - p.side[0].b_item[k];
-        const int nI1 = p.side[1].b_item[k + 1] - p.side[1].b_item[k];
-        int i = tid;
-        for (; i + 7 * 256 < nI0; i += 8 * 256) {
-            float4 v[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = p.item_out[0][i + u * 256];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) { ld += v[u].x; se += v[u].y; rg += v[u].z; }
-        }
-        for (; i < nI0; i += 256) { const float4 v = p.item_out[0][i]; ld += v.x; se += v.y; rg += v.z; }
-        i = tid;
-        for (; i + 7 * 256 < nI1; i += 8 * 256) {
-            float4 v[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = p.item_out[1][i + u * 256];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) rg += v[u].z;
-        }
-        for (; i < nI1; i += 256) { const float4 v = p.item_out[1][i]; rg += v.z; }
-    }
-    sh[0][tid] = ld; sh[1][tid] = se; sh[2][tid] = rg;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-        if (tid < o) { sh[0][tid] += sh[0][tid + o]; sh[1][tid] += sh[1][tid + o]; sh[2][tid] += sh[2][tid + o]; }
-        __syncthreads();
-    }
-    if (tid != 0) return;
-    if (reduced) { ld = reduced[0]; se = reduced[1]; rg = reduced[2]; } else { ld = sh[0][0]; se = sh[1][0]; rg = sh[2][0]; }
+__device__ void finish_step(const StepParams &p, int step, const float *reduced /* MODE_APPLY */, double ld = 0.0,
+                            double se = 0.0, double rg = 0.0) {
+    if (reduced) { ld = reduced[0]; se = reduced[1]; rg = reduced[2]; }
     if (p.mode == MODE_GRAD) {
         p.grad_scalars[0] = (float)ld; p.grad_scalars[1] = (float)se; p.grad_scalars[2] = (float)rg; p.grad_scalars[3] = 0.0f;
         p.sc->ticket = 0;
@@ -462,7 +425,7 @@ __device__ void finish_step(const StepParams &p, int k, int step, const float *r
         float m = p.sc->g_s0, v = p.sc->g_s1;
         m = __fadd_rn(m, __fmul_rn(__fsub_rn(dg, m), __fsub_rn(1.0f, p.b1)));
         v = __fadd_rn(v, __fmul_rn(__fsub_rn(__fmul_rn(dg, dg), v), __fsub_rn(1.0f, p.b2)));
-        g = __fsub_rn(g, __fdiv_rn(__fmul_rn(a, m), __fadd_rn(__fsqrt_rn(v), p.eps)));
+        g = __fsub_rn(g, div_pos(__fmul_rn(a, m), __fadd_rn(sqrt_pos(v), p.eps)));
         p.sc->g_s0 = m; p.sc->g_s1 = v;
     } else if (p.opt == GLOVE_OPT_ADAGRAD) {
         float acc = p.sc->g_s0;
@@ -479,9 +442,14 @@ __device__ void finish_step(const StepParams &p, int k, int step, const float *r
     p.sc->step = step + 1;
 }
 
-__global__ void __launch_bounds__(256) fix_kernel(const StepParams p) {
+__global__ void __launch_bounds__(kFixThreads) fix_kernel(const StepParams p) {
     int k, step;
     if (!batch_index(p, k, step)) return;
+    __shared__ __align__(16) float sh_part[kFixThreads / 32][512];  // per-warp partial sums of one long segment (S <= 512)
+    __shared__ double sh_red[3][kFixThreads];
+    __shared__ int is_last;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    constexpr int NW = kFixThreads / 32;
     const int L0[2] = {p.side[0].b_long[k], p.side[1].b_long[k]};
     const int nL0 = p.side[0].b_long[k + 1] - L0[0], nL1 = p.side[1].b_long[k + 1] - L0[1];
     const float a = p.opt == GLOVE_OPT_ADAM ? p.alpha[step] : 0.0f;
@@ -494,27 +462,47 @@ __global__ void __launch_bounds__(256) fix_kernel(const StepParams p) {
         const int len = ps.seg_start[g + 1] - ps.seg_start[g];
         const int npieces = (len + kItemMax - 1) / kItemMax;
         const float *part = p.partial[s] + (int64_t)(ps.item_part[it0] - ps.b_part[k]) * p.S;
+        // level 1: warp w sums pieces [w*chunk, (w+1)*chunk) in piece order; 128-bit loads, 4 pieces x all the float4s of
+        // a lane in flight at once
+        const int chunk = (npieces + NW - 1) / NW;
+        const int q0 = wid * chunk, q1 = min(q0 + chunk, npieces);
+        const int S4 = p.S >> 2;
+        float4 G4[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) G4[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = q0; q < q1; q += 4) {
+            float4 t[4][4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int f = lane + 32 * r;
+                    t[u][r] = (q + u < q1 && f < S4) ? ld4(part + (int64_t)(q + u) * p.S + 4 * f) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) { G4[r].x += t[u][r].x; G4[r].y += t[u][r].y; G4[r].z += t[u][r].z; G4[r].w += t[u][r].w; }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int f = lane + 32 * r;
+            if (f < S4) *reinterpret_cast<float4 *>(&sh_part[wid][4 * f]) = G4[r];
+        }
+        __syncthreads();
+        // level 2: one thread per column adds the NW warp sums in warp order and applies the optimizer
         float *row = p.table[s] + (int64_t)ps.seg_id[g] * p.P * p.S;
-        const float *crow = p.cache[s] + (int64_t)slot * p.S;
-        const int ls = __float_as_int(crow[p.d + 1]);
-        for (int c = threadIdx.x; c < p.S; c += blockDim.x) {
+        const float *crow = p.snap[s] + (int64_t)slot * p.S;
+        const int bcol = bias_col(p.d, s), lcol = ls_col(p.d, s);
+        for (int c = tid; c < p.S; c += kFixThreads) {
             float G = 0.0f;
-            int q = 0;
-            for (; q + 8 <= npieces; q += 8) {  // 8 independent loads in flight, additions stay in piece order
-                float t[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) t[u] = part[(int64_t)(q + u) * p.S + c];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) G += t[u];
-            }
-            for (; q < npieces; ++q) G += part[(int64_t)q * p.S + c];
+            for (int w = 0; w < NW; ++w) G += sh_part[w][c];
             if (p.mode == MODE_GRAD) { p.grad[s][(int64_t)slot * p.S + c] = G; continue; }
-            if (c <= p.d) {
+            if (c < p.d || c == bcol) {
                 float x = crow[c];
                 if (p.opt == GLOVE_OPT_ADAM) {
                     float m = row[p.S + c], v = row[2 * p.S + c];
-                    if (p.adam_mode == GLOVE_ADAM_REPLAY && ls > 0)
-                        for (int t = ls; t < step; ++t) { m = __fmul_rn(m, p.b1); v = __fmul_rn(v, p.b2); }
                     adam_update(x, m, v, G, a, p.b1, p.b2, p.eps);
                     row[p.S + c] = m; row[2 * p.S + c] = v;
                 } else if (p.opt == GLOVE_OPT_ADAGRAD) {
@@ -525,27 +513,58 @@ __global__ void __launch_bounds__(256) fix_kernel(const StepParams p) {
                     sgd_update(x, G, p.lr);
                 }
                 row[c] = x;
-            } else if (c == p.d + 1) {
+            } else if (c == lcol) {
                 row[c] = __int_as_float(step + 1);
             }
         }
+        __syncthreads();
     }
-    // last CTA to arrive finishes the step (fixed-order reduction of the per-item loss terms)
-    __shared__ int is_last;
+    // per-CTA slice of the per-item loss terms, reduced in a fixed order
+    {
+        const int nI0 = p.side[0].b_item[k + 1] - p.side[0].b_item[k];
+        const int nI1 = p.side[1].b_item[k + 1] - p.side[1].b_item[k];
+        const int per0 = (nI0 + gridDim.x - 1) / gridDim.x, per1 = (nI1 + gridDim.x - 1) / gridDim.x;
+        double ld = 0.0, se = 0.0, rg = 0.0;
+        for (int i = blockIdx.x * per0 + tid; i < min((int)(blockIdx.x + 1) * per0, nI0); i += kFixThreads) {
+            const float4 v = p.item_out[0][i]; ld += v.x; se += v.y; rg += v.z;
+        }
+        for (int i = blockIdx.x * per1 + tid; i < min((int)(blockIdx.x + 1) * per1, nI1); i += kFixThreads) rg += p.item_out[1][i].z;
+        sh_red[0][tid] = ld; sh_red[1][tid] = se; sh_red[2][tid] = rg;
+        __syncthreads();
+        for (int o = kFixThreads / 2; o > 0; o >>= 1) {
+            if (tid < o) { sh_red[0][tid] += sh_red[0][tid + o]; sh_red[1][tid] += sh_red[1][tid + o]; sh_red[2][tid] += sh_red[2][tid + o]; }
+            __syncthreads();
+        }
+        if (tid == 0) { p.cta_out[3 * blockIdx.x] = sh_red[0][0]; p.cta_out[3 * blockIdx.x + 1] = sh_red[1][0]; p.cta_out[3 * blockIdx.x + 2] = sh_red[2][0]; }
+    }
+    // last CTA to arrive finishes the step: the per-CTA sums are added in CTA order (fixed tree)
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) is_last = (atomicAdd(&p.sc->ticket, 1) == (int)gridDim.x - 1);
+    if (tid == 0) is_last = (atomicAdd(&p.sc->ticket, 1) == (int)gridDim.x - 1);
     __syncthreads();
     if (is_last) {
         __threadfence();
-        finish_step(p, k, step, nullptr);
+        const bool in = tid < (int)gridDim.x;
+        sh_red[0][tid] = in ? p.cta_out[3 * tid] : 0.0;
+        sh_red[1][tid] = in ? p.cta_out[3 * tid + 1] : 0.0;
+        sh_red[2][tid] = in ? p.cta_out[3 * tid + 2] : 0.0;
+        __syncthreads();
+        for (int o = kFixThreads / 2; o > 0; o >>= 1) {
+            if (tid < o) { sh_red[0][tid] += sh_red[0][tid + o]; sh_red[1][tid] += sh_red[1][tid + o]; sh_red[2][tid] += sh_red[2][tid + o]; }
+            __syncthreads();
+        }
+        if (tid == 0) {
+            const float red[3] = {0.f, 0.f, 0.f};
+            (void)red;
+            finish_step(p, step, nullptr, sh_red[0][0], sh_red[1][0], sh_red[2][0]);
+        }
     }
 }
 
-__global__ void __launch_bounds__(256) apply_finish_kernel(const StepParams p, const float *reduced) {
+__global__ void apply_finish_kernel(const StepParams p, const float *reduced) {
     int k, step;
     if (!batch_index(p, k, step)) return;
-    finish_step(p, k, step, reduced);
+    if (threadIdx.x == 0) finish_step(p, step, reduced);
 }
 
 // ---- host side -------------------------------------------------------------------------------------------------------
@@ -567,9 +586,10 @@ static int fill_params(const glove_step_args *a, StepParams &p, int mode) {
     p.hdr = pv.hdr;
     for (int s = 0; s < 2; ++s) {
         p.side[s] = pv.side[s];
-        p.cache[s] = w.cache[s]; p.partial[s] = w.partial[s]; p.item_out[s] = w.item_out[s];
+        p.snap[s] = w.snap[s]; p.partial[s] = w.partial[s]; p.item_out[s] = w.item_out[s];
         p.grad[s] = nullptr;
     }
+    p.cta_out = w.cta_out;
     p.grad_scalars = nullptr;
     p.alpha = a->alpha; p.alpha_len = a->alpha_len;
     p.loss_out = a->loss_cap > 0 ? a->loss_out : nullptr; p.loss_cap = a->loss_cap > 0 ? a->loss_cap : 1;
@@ -596,20 +616,27 @@ static int occupancy_grid(Kern kern, int threads) {
 template <int NV>
 static int launch_step(const StepParams &p, cudaStream_t stream, cudaEvent_t *ev = nullptr) {
     static int g_stage = 0, g_update = 0, g_apply = 0;
-    if (!g_stage) g_stage = occupancy_grid(stage_kernel<NV>, 256);
-    if (!g_update) g_update = occupancy_grid(update_kernel<NV, 4>, 128);
+    if (!g_stage) g_stage = occupancy_grid(stage_kernel, 256);
+    if (!g_update) g_update = occupancy_grid(update_kernel<NV, GLOVE_HEAD_GLOVE, false>, 128);
     if (!g_apply) g_apply = occupancy_grid(apply_kernel<NV>, 128);
     if (p.mode == MODE_TRAIN || p.mode == MODE_GRAD) {
         if (ev) cudaEventRecord(ev[0], stream);
-        stage_kernel<NV><<<g_stage, 256, 0, stream>>>(p);
+        stage_kernel<<<g_stage, 256, 0, stream>>>(p);
         if (ev) cudaEventRecord(ev[1], stream);
-        update_kernel<NV, 4><<<g_update, 128, 0, stream>>>(p);
+        const bool dp = p.dp_world > 1;
+        if (p.head == GLOVE_HEAD_GLOVE) {
+            if (dp) update_kernel<NV, GLOVE_HEAD_GLOVE, true><<<g_update, 128, 0, stream>>>(p);
+            else update_kernel<NV, GLOVE_HEAD_GLOVE, false><<<g_update, 128, 0, stream>>>(p);
+        } else {
+            if (dp) update_kernel<NV, GLOVE_HEAD_LOGISTIC, true><<<g_update, 128, 0, stream>>>(p);
+            else update_kernel<NV, GLOVE_HEAD_LOGISTIC, false><<<g_update, 128, 0, stream>>>(p);
+        }
         if (ev) cudaEventRecord(ev[2], stream);
-        fix_kernel<<<kNumSMs, 256, 0, stream>>>(p);
+        fix_kernel<<<kFixBlocks, kFixThreads, 0, stream>>>(p);
         if (ev) cudaEventRecord(ev[3], stream);
     } else {
         apply_kernel<NV><<<g_apply, 128, 0, stream>>>(p);
-        apply_finish_kernel<<<1, 256, 0, stream>>>(p, p.grad_scalars);
+        apply_finish_kernel<<<1, 32, 0, stream>>>(p, p.grad_scalars);
     }
     GLOVE_CHECK_LAUNCH();
     return GLOVE_OK;

@@ -15,52 +15,52 @@ int set_error(int code, const char *fmt, ...) {
     return code;
 }
 
-__global__ void table_init_kernel(float *table, int64_t V, int32_t d, int32_t S, int32_t P, int32_t opt) {
+__global__ void table_init_kernel(float *table, int64_t V, int32_t d, int32_t S, int32_t P, int32_t opt, int32_t side) {
     const int64_t total = V * P * S;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int32_t c = (int32_t)(i % S);
         int32_t p = (int32_t)((i / S) % P);
         float val = 0.0f;
-        if (opt == GLOVE_OPT_ADAGRAD && p == 1 && c <= d) val = kAdagradInit;
+        if (opt == GLOVE_OPT_ADAGRAD && p == 1 && (c < d || c == bias_col(d, side))) val = kAdagradInit;
         table[i] = val;
     }
 }
 
 // one thread per (row, column<=d) element; coalesced on the packed side
-__global__ void pack_plane_kernel(float *table, int64_t V, int32_t d, int32_t S, int32_t P, int32_t plane,
+__global__ void pack_plane_kernel(float *table, int64_t V, int32_t d, int32_t S, int32_t P, int32_t plane, int32_t bcol,
                                   const float *__restrict__ emb, const float *__restrict__ bias) {
     const int64_t total = V * (d + 1);
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int64_t r = i / (d + 1);
         int32_t c = (int32_t)(i % (d + 1));
-        float *dst = table + (r * P + plane) * S + c;
-        if (c < d) *dst = emb[r * d + c];
-        else if (bias) *dst = bias[r];
+        float *dst = table + (r * P + plane) * S;
+        if (c < d) dst[c] = emb[r * d + c];
+        else if (bias) dst[bcol] = bias[r];
     }
 }
 __global__ void unpack_plane_kernel(const float *__restrict__ table, int64_t V, int32_t d, int32_t S, int32_t P,
-                                    int32_t plane, float *emb, float *bias) {
+                                    int32_t plane, int32_t bcol, float *emb, float *bias) {
     const int64_t total = V * (d + 1);
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int64_t r = i / (d + 1);
         int32_t c = (int32_t)(i % (d + 1));
-        float val = table[(r * P + plane) * S + c];
-        if (c < d) { if (emb) emb[r * d + c] = val; }
-        else if (bias) bias[r] = val;
+        const float *src = table + (r * P + plane) * S;
+        if (c < d) { if (emb) emb[r * d + c] = src[c]; }
+        else if (bias) bias[r] = src[bcol];
     }
 }
-__global__ void get_ls_kernel(const float *table, int64_t V, int32_t d, int32_t S, int32_t P, int32_t *out) {
+__global__ void get_ls_kernel(const float *table, int64_t V, int32_t lcol, int32_t S, int32_t P, int32_t *out) {
     for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < V; r += (int64_t)gridDim.x * blockDim.x)
-        out[r] = __float_as_int(table[r * P * S + d + 1]);
+        out[r] = __float_as_int(table[r * P * S + lcol]);
 }
-__global__ void set_ls_kernel(float *table, int64_t V, int32_t d, int32_t S, int32_t P, const int32_t *in) {
+__global__ void set_ls_kernel(float *table, int64_t V, int32_t lcol, int32_t S, int32_t P, const int32_t *in) {
     for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < V; r += (int64_t)gridDim.x * blockDim.x)
-        table[r * P * S + d + 1] = __int_as_float(in[r]);
+        table[r * P * S + lcol] = __int_as_float(in[r]);
 }
 
 // Flush: one warp per row, lanes stride the columns.  Rows with last_step == 0 were never updated (m = v = 0): the
 // idle step is an exact no-op on them, so they are skipped and keep last_step == 0.
-__global__ void __launch_bounds__(256) flush_kernel(float *table, int64_t V, int32_t d, int32_t S,
+__global__ void __launch_bounds__(256) flush_kernel(float *table, int64_t V, int32_t d, int32_t S, int32_t side,
                                                     const float *__restrict__ alpha, int32_t to_step, float b1,
                                                     float b2, float eps) {
     const int lane = threadIdx.x & 31;
@@ -68,15 +68,17 @@ __global__ void __launch_bounds__(256) flush_kernel(float *table, int64_t V, int
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t r = warp; r < V; r += nwarps) {
         float *x = table + r * 3 * S, *m = x + S, *v = m + S;
-        const int32_t ls = __float_as_int(x[d + 1]);
+        const int32_t lcol = ls_col(d, side);
+        const int32_t ls = __float_as_int(x[lcol]);
         if (ls <= 0 || ls >= to_step) continue;
-        for (int32_t c = lane; c <= d; c += 32) {
+        for (int32_t cc = lane; cc <= d; cc += 32) {
+            const int32_t c = cc < d ? cc : bias_col(d, side);
             float xv = x[c], mv = m[c], vv = v[c];
             for (int32_t s = ls; s < to_step; ++s) adam_idle_step(xv, mv, vv, alpha[s], b1, b2, eps);
             x[c] = xv; m[c] = mv; v[c] = vv;
         }
         __syncwarp();
-        if (lane == 0) x[d + 1] = __int_as_float(to_step);
+        if (lane == 0) x[lcol] = __int_as_float(to_step);
     }
 }
 
@@ -97,56 +99,59 @@ static inline int grid_for(int64_t n, int threads) {
     return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
-int glove_table_init(float *table, int64_t V, int32_t d, int32_t optimizer, void *stream) {
-    GLOVE_REQUIRE(table && V > 0 && d > 0, "glove_table_init: bad arguments");
+int glove_table_init(float *table, int64_t V, int32_t d, int32_t optimizer, int32_t side, void *stream) {
+    GLOVE_REQUIRE(table && V > 0 && d > 0 && (side == 0 || side == 1), "glove_table_init: bad arguments");
     GLOVE_REQUIRE(optimizer >= 0 && optimizer <= 2, "glove_table_init: unsupported optimizer %d", optimizer);
     const int32_t S = table_stride(d), P = table_planes(optimizer);
-    table_init_kernel<<<grid_for(V * P * S, 256), 256, 0, (cudaStream_t)stream>>>(table, V, d, S, P, optimizer);
+    table_init_kernel<<<grid_for(V * P * S, 256), 256, 0, (cudaStream_t)stream>>>(table, V, d, S, P, optimizer, side);
     GLOVE_CHECK_LAUNCH();
     return GLOVE_OK;
 }
 
-int glove_pack_plane(float *table, int64_t V, int32_t d, int32_t planes, int32_t plane, const float *emb,
+int glove_pack_plane(float *table, int64_t V, int32_t d, int32_t planes, int32_t plane, int32_t side, const float *emb,
                      const float *bias, void *stream) {
-    GLOVE_REQUIRE(table && emb && V > 0 && d > 0 && plane >= 0 && plane < planes, "glove_pack_plane: bad arguments");
-    pack_plane_kernel<<<grid_for(V * (d + 1), 256), 256, 0, (cudaStream_t)stream>>>(table, V, d, table_stride(d),
-                                                                                    planes, plane, emb, bias);
+    GLOVE_REQUIRE(table && emb && V > 0 && d > 0 && plane >= 0 && plane < planes && (side == 0 || side == 1),
+                  "glove_pack_plane: bad arguments");
+    pack_plane_kernel<<<grid_for(V * (d + 1), 256), 256, 0, (cudaStream_t)stream>>>(
+        table, V, d, table_stride(d), planes, plane, bias_col(d, side), emb, bias);
     GLOVE_CHECK_LAUNCH();
     return GLOVE_OK;
 }
 
-int glove_unpack_plane(const float *table, int64_t V, int32_t d, int32_t planes, int32_t plane, float *emb,
-                       float *bias, void *stream) {
-    GLOVE_REQUIRE(table && (emb || bias) && V > 0 && d > 0 && plane >= 0 && plane < planes,
+int glove_unpack_plane(const float *table, int64_t V, int32_t d, int32_t planes, int32_t plane, int32_t side,
+                       float *emb, float *bias, void *stream) {
+    GLOVE_REQUIRE(table && (emb || bias) && V > 0 && d > 0 && plane >= 0 && plane < planes && (side == 0 || side == 1),
                   "glove_unpack_plane: bad arguments");
-    unpack_plane_kernel<<<grid_for(V * (d + 1), 256), 256, 0, (cudaStream_t)stream>>>(table, V, d, table_stride(d),
-                                                                                      planes, plane, emb, bias);
+    unpack_plane_kernel<<<grid_for(V * (d + 1), 256), 256, 0, (cudaStream_t)stream>>>(
+        table, V, d, table_stride(d), planes, plane, bias_col(d, side), emb, bias);
     GLOVE_CHECK_LAUNCH();
     return GLOVE_OK;
 }
 
-int glove_get_last_step(const float *table, int64_t V, int32_t d, int32_t planes, int32_t *out, void *stream) {
-    GLOVE_REQUIRE(table && out && V > 0 && d > 0 && planes >= 1, "glove_get_last_step: bad arguments");
-    get_ls_kernel<<<grid_for(V, 256), 256, 0, (cudaStream_t)stream>>>(table, V, d, table_stride(d), planes, out);
+int glove_get_last_step(const float *table, int64_t V, int32_t d, int32_t planes, int32_t side, int32_t *out,
+                        void *stream) {
+    GLOVE_REQUIRE(table && out && V > 0 && d > 0 && planes >= 1 && (side == 0 || side == 1), "glove_get_last_step: bad arguments");
+    get_ls_kernel<<<grid_for(V, 256), 256, 0, (cudaStream_t)stream>>>(table, V, ls_col(d, side), table_stride(d), planes, out);
     GLOVE_CHECK_LAUNCH();
     return GLOVE_OK;
 }
-int glove_set_last_step(float *table, int64_t V, int32_t d, int32_t planes, const int32_t *in, void *stream) {
-    GLOVE_REQUIRE(table && in && V > 0 && d > 0 && planes >= 1, "glove_set_last_step: bad arguments");
-    set_ls_kernel<<<grid_for(V, 256), 256, 0, (cudaStream_t)stream>>>(table, V, d, table_stride(d), planes, in);
+int glove_set_last_step(float *table, int64_t V, int32_t d, int32_t planes, int32_t side, const int32_t *in,
+                        void *stream) {
+    GLOVE_REQUIRE(table && in && V > 0 && d > 0 && planes >= 1 && (side == 0 || side == 1), "glove_set_last_step: bad arguments");
+    set_ls_kernel<<<grid_for(V, 256), 256, 0, (cudaStream_t)stream>>>(table, V, ls_col(d, side), table_stride(d), planes, in);
     GLOVE_CHECK_LAUNCH();
     return GLOVE_OK;
 }
 
-int glove_flush_lazy_state(float *table, int64_t V, int32_t d, int32_t optimizer, const float *alpha,
+int glove_flush_lazy_state(float *table, int64_t V, int32_t d, int32_t optimizer, int32_t side, const float *alpha,
                            int32_t alpha_len, int32_t to_step, float beta1, float beta2, float epsilon, void *stream) {
-    GLOVE_REQUIRE(table && V > 0 && d > 0, "glove_flush_lazy_state: bad arguments");
+    GLOVE_REQUIRE(table && V > 0 && d > 0 && (side == 0 || side == 1), "glove_flush_lazy_state: bad arguments");
     if (optimizer != GLOVE_OPT_ADAM) return GLOVE_OK;  // Adagrad / SGD are truly sparse: nothing to replay
     GLOVE_REQUIRE(alpha && to_step <= alpha_len, "glove_flush_lazy_state: alpha table too short (%d < %d)", alpha_len,
                   to_step);
     if (to_step <= 0) return GLOVE_OK;
-    flush_kernel<<<grid_for(V * 32, 256), 256, 0, (cudaStream_t)stream>>>(table, V, d, table_stride(d), alpha, to_step,
-                                                                         beta1, beta2, epsilon);
+    flush_kernel<<<grid_for(V * 32, 256), 256, 0, (cudaStream_t)stream>>>(table, V, d, table_stride(d), side, alpha,
+                                                                         to_step, beta1, beta2, epsilon);
     GLOVE_CHECK_LAUNCH();
     return GLOVE_OK;
 }

@@ -68,8 +68,8 @@ class GloveEngine:
         f32 = dict(dtype=torch.float32, device=self.device)
         self.row_table = torch.empty(self.V * self.P * self.S, **f32)
         self.col_table = torch.empty(self.V * self.P * self.S, **f32)
-        for t in (self.row_table, self.col_table):
-            check(lib.glove_table_init(_ptr(t), self.V, self.d, self.opt_id, _stream()), "glove_table_init")
+        for side, t in enumerate((self.row_table, self.col_table)):
+            check(lib.glove_table_init(_ptr(t), self.V, self.d, self.opt_id, side, _stream()), "glove_table_init")
         self.scalars = torch.zeros(8, dtype=torch.int32, device=self.device)
         if optimizer == "Adagrad":
             self._write_scalars(g_s0=0.1)
@@ -107,11 +107,11 @@ class GloveEngine:
 
     def load_state(self, R, C, rb, cb, g=0.0):
         """Inject initial tables (reference layout: R, C [V,d]; rb, cb [V]; scalar g)."""
-        for table, emb, bias in ((self.row_table, R, rb), (self.col_table, C, cb)):
+        for side, (table, emb, bias) in enumerate(((self.row_table, R, rb), (self.col_table, C, cb))):
             e = torch.as_tensor(np.ascontiguousarray(emb, np.float32)).to(self.device)
             b = torch.as_tensor(np.ascontiguousarray(bias, np.float32).reshape(-1)).to(self.device)
             assert e.shape == (self.V, self.d) and b.shape == (self.V,)
-            check(lib.glove_pack_plane(_ptr(table), self.V, self.d, self.P, 0, _ptr(e), _ptr(b), _stream()), "glove_pack_plane")
+            check(lib.glove_pack_plane(_ptr(table), self.V, self.d, self.P, 0, side, _ptr(e), _ptr(b), _stream()), "glove_pack_plane")
         self._write_scalars(g=float(g))
         torch.cuda.synchronize()
 
@@ -124,35 +124,38 @@ class GloveEngine:
     def set_plane(self, side: str, plane: int, emb: torch.Tensor, bias: torch.Tensor):
         """Write optimizer slot plane ``plane`` (1 = Adam m / Adagrad acc, 2 = Adam v) of ``side`` in {'row','col'}."""
         table = self.row_table if side == "row" else self.col_table
-        check(lib.glove_pack_plane(_ptr(table), self.V, self.d, self.P, plane, _ptr(emb.contiguous()),
-                                   _ptr(bias.contiguous()), _stream()), "glove_pack_plane")
+        check(lib.glove_pack_plane(_ptr(table), self.V, self.d, self.P, plane, 0 if side == "row" else 1,
+                                   _ptr(emb.contiguous()), _ptr(bias.contiguous()), _stream()), "glove_pack_plane")
 
     def set_last_step(self, side: str, ls: torch.Tensor):
         table = self.row_table if side == "row" else self.col_table
         ls = ls.to(device=self.device, dtype=torch.int32).contiguous()
-        check(lib.glove_set_last_step(_ptr(table), self.V, self.d, self.P, _ptr(ls), _stream()), "glove_set_last_step")
+        check(lib.glove_set_last_step(_ptr(table), self.V, self.d, self.P, 0 if side == "row" else 1, _ptr(ls), _stream()),
+              "glove_set_last_step")
         torch.cuda.synchronize()
 
     def get_last_step(self, side: str) -> torch.Tensor:
         table = self.row_table if side == "row" else self.col_table
         out = torch.empty(self.V, dtype=torch.int32, device=self.device)
-        check(lib.glove_get_last_step(_ptr(table), self.V, self.d, self.P, _ptr(out), _stream()), "glove_get_last_step")
+        check(lib.glove_get_last_step(_ptr(table), self.V, self.d, self.P, 0 if side == "row" else 1, _ptr(out), _stream()),
+              "glove_get_last_step")
         return out
 
     def init_uniform(self, seed: int = 0):
         """Keras Embedding default initialiser U(-0.05, 0.05) on all four tables, global bias zero
         [ref src/models/model_utils.py:7-15,39]."""
         gen = torch.Generator(device=self.device).manual_seed(seed)
-        for table in (self.row_table, self.col_table):
+        for side, table in enumerate((self.row_table, self.col_table)):
             e = torch.empty(self.V, self.d, dtype=torch.float32, device=self.device).uniform_(-0.05, 0.05, generator=gen)
             b = torch.empty(self.V, dtype=torch.float32, device=self.device).uniform_(-0.05, 0.05, generator=gen)
-            check(lib.glove_pack_plane(_ptr(table), self.V, self.d, self.P, 0, _ptr(e), _ptr(b), _stream()), "glove_pack_plane")
+            check(lib.glove_pack_plane(_ptr(table), self.V, self.d, self.P, 0, side, _ptr(e), _ptr(b), _stream()), "glove_pack_plane")
         torch.cuda.synchronize()
 
     def _unpack(self, table, plane):
         e = torch.empty(self.V, self.d, dtype=torch.float32, device=self.device)
         b = torch.empty(self.V, dtype=torch.float32, device=self.device)
-        check(lib.glove_unpack_plane(_ptr(table), self.V, self.d, self.P, plane, _ptr(e), _ptr(b), _stream()), "glove_unpack_plane")
+        side = 0 if table is self.row_table else 1
+        check(lib.glove_unpack_plane(_ptr(table), self.V, self.d, self.P, plane, side, _ptr(e), _ptr(b), _stream()), "glove_unpack_plane")
         return e, b
 
     def get_state(self, slots: bool = False, flush: bool = True) -> Dict[str, np.ndarray]:
@@ -183,8 +186,8 @@ class GloveEngine:
     def flush(self):
         if self.optimizer != "Adam" or self.adam_mode == "lazy":
             return
-        for t in (self.row_table, self.col_table):
-            check(lib.glove_flush_lazy_state(_ptr(t), self.V, self.d, self.opt_id, _ptr(self.alpha), self.max_steps,
+        for side, t in enumerate((self.row_table, self.col_table)):
+            check(lib.glove_flush_lazy_state(_ptr(t), self.V, self.d, self.opt_id, side, _ptr(self.alpha), self.max_steps,
                                              self.host_step, ADAM_BETA1, ADAM_BETA2, KERAS_EPSILON, _stream()),
                   "glove_flush_lazy_state")
 

@@ -19,8 +19,10 @@
  * Table layout ("packed table"): one buffer per side (row / col), float32 [V][P][S]:
  *     S = glove_table_stride(d) = roundup(d + 2, 8) floats (so every plane row is a whole number of 32-byte sectors)
  *     P = glove_table_planes(optimizer): Adam 3 (x, m, v); Adagrad 2 (x, accumulator); SGD 1 (x)
- *     plane 0 row = [ x_0 .. x_{d-1} | bias | last_step bits (int32) | 0 .. ]
- *     plane p>0   = optimizer slot for the same columns (bias slot in column d)
+ *     plane 0 row = [ x_0 .. x_{d-1} | c_d | c_{d+1} | 0 .. ] with, for side s (0 = row table, 1 = col table),
+ *                   the bias in column d+s and the last_step word (int32 bits) in column d+1-s.  The two sides are
+ *                   mirrored so that the dot product of a row-side and a col-side snapshot row needs no masking.
+ *     plane p>0   = optimizer slot for the same columns (bias slot in column d+s)
  *   The reference keeps 4 Keras Embedding variables (R,C [V,d]; rb,cb [V,1]; src/models/model_utils.py:31-39) plus Keras
  *   optimizer slots; glove_pack_plane / glove_unpack_plane convert between the two layouts.
  */
@@ -71,15 +73,17 @@ int32_t glove_abi_version(void);
 int32_t glove_table_stride(int32_t d);
 int32_t glove_table_planes(int32_t optimizer);
 /* zero the table, last_step = 0, Adagrad accumulator plane = 0.1 (Keras initial_accumulator_value) */
-int glove_table_init(float *table, int64_t V, int32_t d, int32_t optimizer, void *stream);
+int glove_table_init(float *table, int64_t V, int32_t d, int32_t optimizer, int32_t side, void *stream);
 /* plane <- (emb [V,d], bias [V] (may be NULL)) ; replaces 4x ResourceGather-able Keras variables [ref model_utils.py:31-37] */
-int glove_pack_plane(float *table, int64_t V, int32_t d, int32_t planes, int32_t plane, const float *emb,
+int glove_pack_plane(float *table, int64_t V, int32_t d, int32_t planes, int32_t plane, int32_t side, const float *emb,
                      const float *bias, void *stream);
-int glove_unpack_plane(const float *table, int64_t V, int32_t d, int32_t planes, int32_t plane, float *emb,
-                       float *bias, void *stream);
+int glove_unpack_plane(const float *table, int64_t V, int32_t d, int32_t planes, int32_t plane, int32_t side,
+                       float *emb, float *bias, void *stream);
 /* read / write the per-row last_step column (int32 [V]) -- checkpoint / resume */
-int glove_get_last_step(const float *table, int64_t V, int32_t d, int32_t planes, int32_t *out, void *stream);
-int glove_set_last_step(float *table, int64_t V, int32_t d, int32_t planes, const int32_t *in, void *stream);
+int glove_get_last_step(const float *table, int64_t V, int32_t d, int32_t planes, int32_t side, int32_t *out,
+                        void *stream);
+int glove_set_last_step(float *table, int64_t V, int32_t d, int32_t planes, int32_t side, const int32_t *in,
+                        void *stream);
 
 /* ---- input pipeline: replaces make_csv_dataset shuffle/batch [ref src/models/data_utils.py:4-26] -------------- */
 /* out[k] = position in the COO of global sample (first + k): epoch e = n / nnz uses the keyed bijection with key
@@ -139,7 +143,7 @@ int glove_apply_step(const glove_step_args *args, const float *grad_rows, const 
 /* Replays the missed zero-gradient Adam steps of every row up to (not including) step to_step.  Required before the
  * tables are read from outside the step (eval, export, checkpoint) in GLOVE_ADAM_REPLAY mode; calling it after every
  * step gives the literal dense-sweep schedule of legacy Keras Adam. */
-int glove_flush_lazy_state(float *table, int64_t V, int32_t d, int32_t optimizer, const float *alpha,
+int glove_flush_lazy_state(float *table, int64_t V, int32_t d, int32_t optimizer, int32_t side, const float *alpha,
                            int32_t alpha_len, int32_t to_step, float beta1, float beta2, float epsilon, void *stream);
 
 /* ---- EVAL: model_fn(mode=EVAL), RegressionHead metrics [ref src/models/estimator.py:87-92] -------------------- */
