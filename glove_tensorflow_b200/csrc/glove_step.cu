@@ -208,39 +208,35 @@ __global__ void __launch_bounds__(256) stage_kernel(const StepParams p) {
 // stage kernel has already decayed m, v through step-1, so the moments are read as-is.
 template <int NV>
 __device__ __forceinline__ void apply_row(const StepParams &p, float *row, float4 (&x)[NV], const float4 (&G)[NV],
-                                          int s, int step, int lane) {
+                                          float4 (&s1)[NV], float4 (&s2)[NV], int s, int step, int lane) {
+    // s1 / s2 = optimizer slot planes 1 / 2 of the row, already loaded by the caller (prefetched at item start)
     const int S4 = p.S >> 2;
     if (p.opt == GLOVE_OPT_ADAM) {
-        float4 m[NV], v[NV];
-        load_row<NV>(m, row + p.S, lane, S4);
-        load_row<NV>(v, row + 2 * p.S, lane, S4);
         const float na = -__ldg(p.alpha + step);
 #pragma unroll
         for (int r = 0; r < NV; ++r) {
             float2 xa = make_float2(x[r].x, x[r].y), xb = make_float2(x[r].z, x[r].w);
-            float2 ma = make_float2(m[r].x, m[r].y), mb = make_float2(m[r].z, m[r].w);
-            float2 va = make_float2(v[r].x, v[r].y), vb = make_float2(v[r].z, v[r].w);
+            float2 ma = make_float2(s1[r].x, s1[r].y), mb = make_float2(s1[r].z, s1[r].w);
+            float2 va = make_float2(s2[r].x, s2[r].y), vb = make_float2(s2[r].z, s2[r].w);
             adam_update2(xa, ma, va, make_float2(G[r].x, G[r].y), na, p.b1, p.b2, p.eps);
             adam_update2(xb, mb, vb, make_float2(G[r].z, G[r].w), na, p.b1, p.b2, p.eps);
             x[r] = make_float4(xa.x, xa.y, xb.x, xb.y);
-            m[r] = make_float4(ma.x, ma.y, mb.x, mb.y);
-            v[r] = make_float4(va.x, va.y, vb.x, vb.y);
+            s1[r] = make_float4(ma.x, ma.y, mb.x, mb.y);
+            s2[r] = make_float4(va.x, va.y, vb.x, vb.y);
         }
-        store_row<NV>(row + p.S, m, lane, S4);
-        store_row<NV>(row + 2 * p.S, v, lane, S4);
+        store_row<NV>(row + p.S, s1, lane, S4);
+        store_row<NV>(row + 2 * p.S, s2, lane, S4);
     } else if (p.opt == GLOVE_OPT_ADAGRAD) {
-        float4 acc[NV];
-        load_row<NV>(acc, row + p.S, lane, S4);
 #pragma unroll
         for (int r = 0; r < NV; ++r) {
             float2 xa = make_float2(x[r].x, x[r].y), xb = make_float2(x[r].z, x[r].w);
-            float2 aa = make_float2(acc[r].x, acc[r].y), ab = make_float2(acc[r].z, acc[r].w);
+            float2 aa = make_float2(s1[r].x, s1[r].y), ab = make_float2(s1[r].z, s1[r].w);
             adagrad_update2(xa, aa, make_float2(G[r].x, G[r].y), -p.lr, p.eps);
             adagrad_update2(xb, ab, make_float2(G[r].z, G[r].w), -p.lr, p.eps);
             x[r] = make_float4(xa.x, xa.y, xb.x, xb.y);
-            acc[r] = make_float4(aa.x, aa.y, ab.x, ab.y);
+            s1[r] = make_float4(aa.x, aa.y, ab.x, ab.y);
         }
-        store_row<NV>(row + p.S, acc, lane, S4);
+        store_row<NV>(row + p.S, s1, lane, S4);
     } else {
 #pragma unroll
         for (int r = 0; r < NV; ++r)
@@ -281,7 +277,7 @@ __device__ __forceinline__ void axpy_row(float4 (&acc)[NV], float e, const float
 }
 
 template <int NV, int HEAD, bool DP>
-__global__ void __launch_bounds__(128, (NV <= 3 ? 5 : 3)) update_kernel(const StepParams p) {
+__global__ void __launch_bounds__(128, (NV <= 3 ? 4 : 3)) update_kernel(const StepParams p) {
     int k, step;
     if (!batch_index(p, k, step)) return;
     const int lane = threadIdx.x & 31;
@@ -291,6 +287,7 @@ __global__ void __launch_bounds__(128, (NV <= 3 ? 5 : 3)) update_kernel(const St
     const float invB = 1.0f / (float)p.B;
     const float ce = (2.0f * p.rs * p.l2) / ((float)p.d * (float)p.B), cbias = (2.0f * p.rs * p.l2) / (float)p.B;
     const float reg_unscale = (float)p.B / (2.0f * p.rs);  // coef * reg_unscale = l2/d (embedding) | l2 (bias)
+    const bool train = p.mode == MODE_TRAIN;
 
 #pragma unroll 1
     for (int s = 0; s < 2; ++s) {
@@ -298,72 +295,76 @@ __global__ void __launch_bounds__(128, (NV <= 3 ? 5 : 3)) update_kernel(const St
         const int it0 = ps.b_item[k], nI = ps.b_item[k + 1] - it0;
         const float *opp_base = p.snap[1 - s];
         const int4 *rec = ps.rec;
-        // per-lane activity-L2 coefficients of this side: 2 s l2/(d B) on the embedding columns, 2 s l2/B on the bias
-        // column, 0 elsewhere (a zero also marks the columns of the accumulator that must be cleared)
         const int bcol = bias_col(p.d, s);
-        float4 coef[NV];
-#pragma unroll
-        for (int r = 0; r < NV; ++r) {
-            const int f = lane + 32 * r;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const int col = 4 * f + c;
-                f4c(coef[r], c) = col < p.d ? ce : (col == bcol ? cbias : 0.0f);
-            }
-        }
+        int itl = warp;
+        int4 ir = itl < nI ? __ldg(ps.item_rec + it0 + itl) : make_int4(0, 0, 0, 0);
 #pragma unroll 1
-        for (int itl = warp; itl < nI; itl += nwarps) {
-            const int4 ir = __ldg(ps.item_rec + it0 + itl);
+        while (itl < nI) {
+            // ---- memory round 1: everything whose address the item record gives, issued back to back: the records of
+            // the item's (<= 32) triples, one per lane; the own snapshot row; the optimizer slot planes (needed only in
+            // the epilogue, so their HBM latency hides behind the whole gather loop); the next item's record.
             const int slot = ir.y, start = ir.z, n = ir.w & 0xff, part = ir.w >> 8;
-
-            float4 x[NV], acc[NV], bufA[NV], bufB[NV];
+            const int4 myrec = lane < n ? __ldg(rec + start + lane) : make_int4(0, 0, 0, 0);
+            float *row = p.table[s] + (int64_t)ir.x * p.P * p.S;
+            float4 x[NV], acc[NV], bufA[NV], bufB[NV], s1[NV], s2[NV];
             load_row<NV>(x, p.snap[s] + (int64_t)slot * p.S, lane, S4);
+            const bool applies = train && part == 0;
+            if (applies && p.P >= 2) load_row<NV>(s1, row + p.S, lane, S4);
+            if (applies && p.P >= 3) load_row<NV>(s2, row + 2 * p.S, lane, S4);
+            const int itn = itl + nwarps;
+            const int4 ir_next = itn < nI ? __ldg(ps.item_rec + it0 + itn) : ir;
 #pragma unroll
             for (int r = 0; r < NV; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
             float loss_d = 0.0f, sum_e = 0.0f;
             int n_eff = 0;
 
-            // two triples per iteration with ping-pong buffers: the opposite row of triple q+1 (q+2) is in flight while
-            // triple q (q+1) is reduced
-            int4 rcA = __ldg(rec + start), rcB = rcA;
-            load_row_nc<NV>(bufA, opp_base + (int64_t)rcA.x * p.S, lane, S4);
+            // ---- memory round 2: opposite snapshot rows, two triples per iteration with ping-pong buffers
+            load_row_nc<NV>(bufA, opp_base + (int64_t)__shfl_sync(0xffffffffu, myrec.x, 0) * p.S, lane, S4);
 #pragma unroll 1
             for (int q = 0; q < n; q += 2) {
                 const bool hasB = q + 1 < n;
-                if (hasB) {
-                    rcB = __ldg(rec + start + q + 1);
-                    load_row_nc<NV>(bufB, opp_base + (int64_t)rcB.x * p.S, lane, S4);
-                }
+                if (hasB) load_row_nc<NV>(bufB, opp_base + (int64_t)__shfl_sync(0xffffffffu, myrec.x, q + 1) * p.S, lane, S4);
                 {
+                    const float a = __int_as_float(__shfl_sync(0xffffffffu, myrec.y, q));
+                    const float b = __int_as_float(__shfl_sync(0xffffffffu, myrec.z, q));
                     float e, l;
-                    head_eval(HEAD, dot_row<NV>(x, bufA) + gbias, __int_as_float(rcA.y), __int_as_float(rcA.z), invB, p.nf, e, l);
-                    if (DP) { const bool mine = rcA.w / p.dp_block == p.dp_rank; e = mine ? e : 0.f; l = mine ? l : 0.f; n_eff += mine; }
+                    head_eval(HEAD, dot_row<NV>(x, bufA) + gbias, a, b, invB, p.nf, e, l);
+                    if (DP) {
+                        const bool mine = __shfl_sync(0xffffffffu, myrec.w, q) / p.dp_block == p.dp_rank;
+                        e = mine ? e : 0.f; l = mine ? l : 0.f; n_eff += mine;
+                    }
                     loss_d += l; sum_e += e;
                     axpy_row<NV>(acc, e, bufA);
                 }
                 if (hasB) {
-                    if (q + 2 < n) {
-                        rcA = __ldg(rec + start + q + 2);
-                        load_row_nc<NV>(bufA, opp_base + (int64_t)rcA.x * p.S, lane, S4);
-                    }
+                    if (q + 2 < n) load_row_nc<NV>(bufA, opp_base + (int64_t)__shfl_sync(0xffffffffu, myrec.x, q + 2) * p.S, lane, S4);
+                    const float a = __int_as_float(__shfl_sync(0xffffffffu, myrec.y, q + 1));
+                    const float b = __int_as_float(__shfl_sync(0xffffffffu, myrec.z, q + 1));
                     float e, l;
-                    head_eval(HEAD, dot_row<NV>(x, bufB) + gbias, __int_as_float(rcB.y), __int_as_float(rcB.z), invB, p.nf, e, l);
-                    if (DP) { const bool mine = rcB.w / p.dp_block == p.dp_rank; e = mine ? e : 0.f; l = mine ? l : 0.f; n_eff += mine; }
+                    head_eval(HEAD, dot_row<NV>(x, bufB) + gbias, a, b, invB, p.nf, e, l);
+                    if (DP) {
+                        const bool mine = __shfl_sync(0xffffffffu, myrec.w, q + 1) / p.dp_block == p.dp_rank;
+                        e = mine ? e : 0.f; l = mine ? l : 0.f; n_eff += mine;
+                    }
                     loss_d += l; sum_e += e;
                     axpy_row<NV>(acc, e, bufB);
                 }
             }
             if (!DP) n_eff = n;
 
-            // activity-L2: gradient n*coef_c*x_c and loss n*(l2/d sum x^2 + l2 bias^2).  The bias column of acc already
-            // holds sum_b e_b; the column where the opposite bias was multiplied in (coef == 0) is cleared.
+            // activity-L2: gradient n*coef_c*x_c and loss n*(l2/d sum x^2 + l2 bias^2), coef = 2 s l2/(d B) on the embedding
+            // columns, 2 s l2/B on the bias column, 0 elsewhere.  The bias column of acc already holds sum_b e_b; the
+            // column where the opposite bias was multiplied in (coef == 0) is cleared.
             const float fn = (float)n_eff;
             float sq = 0.0f;
 #pragma unroll
             for (int r = 0; r < NV; ++r) {
+                const int f = lane + 32 * r;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    const float cf = f4c(coef[r], c), xv = f4c(x[r], c);
+                    const int col = 4 * f + c;
+                    const float cf = col < p.d ? ce : (col == bcol ? cbias : 0.0f);
+                    const float xv = f4c(x[r], c);
                     const float cx = cf * xv;
                     f4c(acc[r], c) = (cf != 0.0f ? f4c(acc[r], c) : 0.0f) + fn * cx;
                     sq += cx * xv;
@@ -375,11 +376,13 @@ __global__ void __launch_bounds__(128, (NV <= 3 ? 5 : 3)) update_kernel(const St
 
             if (part) {
                 store_row<NV>(p.partial[s] + (int64_t)(part - 1) * p.S, acc, lane, S4);
-            } else if (p.mode == MODE_GRAD) {
+            } else if (!train) {
                 store_row<NV>(p.grad[s] + (int64_t)slot * p.S, acc, lane, S4);
             } else {
-                apply_row<NV>(p, p.table[s] + (int64_t)ir.x * p.P * p.S, x, acc, s, step, lane);
+                apply_row<NV>(p, row, x, acc, s1, s2, s, step, lane);
             }
+            ir = ir_next;
+            itl = itn;
         }
     }
 }
@@ -399,10 +402,12 @@ __global__ void __launch_bounds__(128) apply_kernel(const StepParams p) {
         const int slot = s ? w - U0 : w;
         const int id = p.side[s].seg_id[seg0[s] + slot];
         float *row = p.table[s] + (int64_t)id * p.P * p.S;
-        float4 x[NV], G[NV];
+        float4 x[NV], G[NV], s1[NV], s2[NV];
         load_row<NV>(x, p.snap[s] + (int64_t)slot * p.S, lane, S4);
         load_row<NV>(G, p.grad[s] + (int64_t)slot * p.S, lane, S4);
-        apply_row<NV>(p, row, x, G, s, step, lane);
+        if (p.P >= 2) load_row<NV>(s1, row + p.S, lane, S4);
+        if (p.P >= 3) load_row<NV>(s2, row + 2 * p.S, lane, S4);
+        apply_row<NV>(p, row, x, G, s1, s2, s, step, lane);
     }
 }
 
