@@ -82,6 +82,7 @@ class GloveEngine:
         self.plan_bytes = lib.glove_plan_bytes(self.K, self.B)
         self.plans = [torch.empty(self.plan_bytes, **u8) for _ in range(2)]
         self.plan_first = [None, None]
+        self._plan_counts = [None, None]
         self.prep_ws = torch.empty(lib.glove_prepare_workspace_bytes(self.K, self.B), **u8)
         self.step_ws = torch.empty(lib.glove_step_workspace_bytes(self.B, self.d), **u8)
         self.coo = None
@@ -247,6 +248,7 @@ class GloveEngine:
                                         self.V, _stream()), "glove_prepare_batches")
         self._keep = sidx  # keep the index chunk alive until the stream has consumed it
         self.plan_first[which] = first_step
+        self._plan_counts[which] = None
 
     def _plan_for(self, step: int) -> int:
         first = (step // self.K) * self.K
@@ -264,26 +266,53 @@ class GloveEngine:
         which = self._plan_for(self.host_step)
         if self.dp_world > 1:
             self._step_dp(which)
-        else:
-            check(lib.glove_train_step(ctypes.byref(self._args[which]), _stream()), "glove_train_step")
+            return
+        check(lib.glove_train_step(ctypes.byref(self._args[which]), _stream()), "glove_train_step")
+        self.host_step += 1
+        if self.adam_mode == "dense":
+            self.flush()
+
+    def grad_step(self):
+        """Data-parallel half-step 1: this rank's gradient partial sums for every global segment (dense, slot order).
+        Returns (grad_rows, grad_cols, grad_scalars) device tensors to be all-reduced."""
+        which = self._plan_for(self.host_step)
+        if self.grad is None:
+            f32 = dict(dtype=torch.float32, device=self.device)
+            self.grad = (torch.zeros(self.B * self.S, **f32), torch.zeros(self.B * self.S, **f32), torch.zeros(4, **f32))
+        gr, gc, gs = self.grad
+        check(lib.glove_grad_step(ctypes.byref(self._args[which]), _ptr(gr), _ptr(gc), _ptr(gs), _stream()), "glove_grad_step")
+        return gr, gc, gs
+
+    def apply_step(self):
+        """Data-parallel half-step 2: apply the optimizer on every replica from the all-reduced buffers."""
+        which = self._plan_for(self.host_step)
+        gr, gc, gs = self.grad
+        check(lib.glove_apply_step(ctypes.byref(self._args[which]), _ptr(gr), _ptr(gc), _ptr(gs), _stream()), "glove_apply_step")
         self.host_step += 1
         if self.adam_mode == "dense":
             self.flush()
 
     def _step_dp(self, which):
         import torch.distributed as dist
-        if self.grad is None:
-            f32 = dict(dtype=torch.float32, device=self.device)
-            self.grad = (torch.zeros(self.B * self.S, **f32), torch.zeros(self.B * self.S, **f32), torch.zeros(4, **f32))
-        gr, gc, gs = self.grad
-        a = self._args[which]
-        check(lib.glove_grad_step(ctypes.byref(a), _ptr(gr), _ptr(gc), _ptr(gs), _stream()), "glove_grad_step")
-        # exchange: only the touched rows (dense in slot order) are reduced; counts are known on the host from the plan
-        n_r, n_c = self.batch_counts(self.host_step)[:2]
+        gr, gc, gs = self.grad_step()
+        # exchange only the touched rows: the buffers are dense in slot order and the per-batch segment counts of the
+        # whole plan were fetched once when the plan was built
+        n_r, n_c = self._counts_for(self.host_step)
         dist.all_reduce(gr[: n_r * self.S])
         dist.all_reduce(gc[: n_c * self.S])
         dist.all_reduce(gs)
-        check(lib.glove_apply_step(ctypes.byref(a), _ptr(gr), _ptr(gc), _ptr(gs), _stream()), "glove_apply_step")
+        self.apply_step()
+
+    def _counts_for(self, step):
+        which = self._plan_for(step)
+        if self._plan_counts[which] is None:
+            out = (ctypes.c_int32 * 4)()
+            counts = []
+            for k in range(self.K):
+                check(lib.glove_plan_batch_counts(_ptr(self.plans[which]), self.K, self.B, k, out, _stream()), "glove_plan_batch_counts")
+                counts.append((out[0], out[1]))
+            self._plan_counts[which] = counts
+        return self._plan_counts[which][step - self.plan_first[which]]
 
     def step_profiled(self):
         """One TRAIN step with per-kernel device timings (ms): (stage, update, fix+finish).  Synchronises."""

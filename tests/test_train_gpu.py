@@ -159,3 +159,43 @@ def test_unsupported_inputs_fail_loudly():
         GloveEngine(10, 4, optimizer="RMSprop")
     with pytest.raises(ValueError):
         GloveEngine(10, 600)
+
+
+@pytest.mark.parametrize("world,adam_mode,optimizer", [(2, "replay", "Adam"), (4, "lazy", "Adam"), (2, "replay", "Adagrad")])
+def test_data_parallel_replicas_on_one_gpu(world, adam_mode, optimizer):
+    """Emulates `world` data-parallel ranks as `world` replica engines on one GPU (the real thing differs only in the
+    NCCL all-reduce, replaced here by summing the ranks' buffers in rank order): the replicas must stay bit-identical
+    and match the single-process oracle step on the global batch."""
+    import torch
+    from glove_tensorflow_b200.engine import GloveEngine
+    V, d, B, steps, n = 600, 48, 512, 12, 20000
+    coo = make_coo(V, n, 31, hot=0.15)
+    batches = np.random.default_rng(32).integers(0, n, (steps, B))
+    st = o.init_state(V, d, 33)
+    ref = st.copy()
+    ref_losses = np.array(o.train(ref, coo, batches, optimizer=optimizer, learning_rate=0.01,
+                                  adam_mode="lazy" if adam_mode == "lazy" else "keras_dense"))
+    engs = []
+    for r in range(world):
+        e = GloveEngine(V, d, optimizer=optimizer, adam_mode=adam_mode, learning_rate=0.01, batch_size=B, plan_steps=5,
+                        max_steps=steps + 8, dp_rank=r, dp_world=world)
+        e.load_state(st.R, st.C, st.rb, st.cb, st.g)
+        e.set_coo(coo["row"], coo["col"], coo["target"], coo["weight"])
+        e.set_batches(batches)
+        engs.append(e)
+    losses = []
+    for s in range(steps):
+        bufs = [e.grad_step() for e in engs]
+        total = [torch.stack([b[i] for b in bufs]).sum(0) for i in range(3)]
+        for e, b in zip(engs, bufs):
+            for i in range(3):
+                b[i].copy_(total[i])
+            e.apply_step()
+        torch.cuda.synchronize()
+        losses.append(float(engs[0].read_scalars()["loss"]))
+    states = [e.get_state() for e in engs]
+    for k in ("R", "C", "rb", "cb"):
+        for stt in states[1:]:
+            assert np.array_equal(states[0][k], stt[k]), k
+        assert _rel(states[0][k], getattr(ref, k)) < 3e-5, (k, _rel(states[0][k], getattr(ref, k)))
+    assert np.max(np.abs(np.array(losses) - ref_losses) / np.abs(ref_losses)) < RTOL
