@@ -92,6 +92,7 @@ class GloveEngine:
         self.sample_idx = None  # explicit [n_steps, B] injected batch order (parity tests)
         self._args = [self._make_args(i) for i in range(2)]
         self.grad = None
+        self._norm_cache = None
 
     # ---- state ---------------------------------------------------------------------------------------------------
     def _write_scalars(self, **kw):
@@ -361,6 +362,34 @@ class GloveEngine:
         if sc["error"] or sc["step"] != self.host_step:
             raise _lib.GloveError("device step counter %d != host %d (error flag %d)" % (sc["step"], self.host_step, sc["error"]))
         return np.concatenate(losses) if losses else np.zeros(0, np.float32)
+
+    # ---- predict -------------------------------------------------------------------------------------------------
+    def topk(self, query_ids, k: int, exact_fp32: bool = False):
+        """Cosine top-k of the ROW embeddings of ``query_ids`` against the whole row table
+        (get_predictions, ref src/models/model_utils.py:81-110).  Returns (sim [n,k] f32, idx [n,k] i32) as numpy:
+        similarities descending, ties -> lower id.  ``exact_fp32`` forces the CUDA-core scan."""
+        self.flush()
+        q = torch.as_tensor(np.ascontiguousarray(query_ids, np.int32)).to(self.device)
+        n = int(q.numel())
+        if self._norm_cache is None or self._norm_cache[0] != self.host_step:
+            Kp, Vp = lib.glove_topk_kpad(self.d), lib.glove_topk_vpad(self.V)
+            inv = torch.empty(self.V, dtype=torch.float32, device=self.device)
+            nb = torch.empty(Vp * Kp, dtype=torch.bfloat16, device=self.device)
+            check(lib.glove_normalize_rows(_ptr(self.row_table), self.V, self.d, self.P, _ptr(nb), _ptr(inv), _stream()),
+                  "glove_normalize_rows")
+            self._norm_cache = (self.host_step, inv, nb)
+        _, inv, nb = self._norm_cache
+        sim = torch.empty(n * k, dtype=torch.float32, device=self.device)
+        idx = torch.empty(n * k, dtype=torch.int32, device=self.device)
+        ws = torch.empty(max(lib.glove_topk_workspace_bytes(self.V, self.d, n, k), 256), dtype=torch.uint8, device=self.device)
+        if exact_fp32:
+            check(lib.glove_topk_cosine_fp32(_ptr(self.row_table), self.V, self.d, self.P, _ptr(inv), _ptr(q), n, k,
+                                             _ptr(sim), _ptr(idx), _ptr(ws), ws.numel(), _stream()), "glove_topk_cosine_fp32")
+        else:
+            check(lib.glove_topk_cosine(_ptr(self.row_table), self.V, self.d, self.P, _ptr(nb), _ptr(inv), _ptr(q), n, k,
+                                        _ptr(sim), _ptr(idx), _ptr(ws), ws.numel(), _stream()), "glove_topk_cosine")
+        torch.cuda.synchronize()
+        return sim.cpu().numpy().reshape(n, k), idx.cpu().numpy().reshape(n, k)
 
     # ---- eval ----------------------------------------------------------------------------------------------------
     def eval_sums(self, batch_size: Optional[int] = None, first: int = 0, count: Optional[int] = None) -> np.ndarray:

@@ -1,0 +1,67 @@
+"""PREDICT path: cosine top-k against the oracle (ids exact, ties broken by lower id)."""
+import numpy as np
+import pytest
+
+from oracle import glove_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+
+def _table(V, d, seed, dup=True):
+    rng = np.random.default_rng(seed)
+    T = rng.uniform(-0.05, 0.05, (V, d)).astype(np.float32)
+    if dup:
+        T[V // 2] = T[7]                 # exact duplicate rows: identical similarity to everything -> tie by id
+        T[V - 1] = T[7]
+        T[11] = 0.0                       # zero row: l2_normalize's 1e-12 floor
+    return T
+
+
+def _check(sim, idx, T, q, k):
+    want_sim, want_idx = o.cosine_topk(T, q, k)
+    assert np.all(np.diff(sim, axis=1) <= 0)
+    np.testing.assert_allclose(sim, want_sim, atol=2e-6)
+    bad = idx != want_idx
+    if bad.any():   # a swap is legitimate only between entries whose similarities agree to fp32 summation noise
+        r, c = np.nonzero(bad)
+        assert np.all(np.abs(want_sim[r, c] - sim[r, c]) < 5e-7), (idx[r[0]], want_idx[r[0]])
+        for rr in np.unique(r):
+            assert set(idx[rr]) == set(want_idx[rr]) or np.abs(want_sim[rr, -1] - sim[rr, -1]) < 5e-7
+
+
+@pytest.mark.parametrize("V,d,k,exact", [(3000, 64, 20, True), (3000, 64, 20, False), (5000, 300, 10, True),
+                                          (5000, 300, 10, False), (700, 30, 1, True), (40, 8, 32, True), (40, 8, 32, False)])
+def test_topk_matches_oracle(V, d, k, exact):
+    from glove_tensorflow_b200.engine import GloveEngine
+    T = _table(V, d, 1)
+    eng = GloveEngine(V, d, batch_size=64, plan_steps=1, max_steps=4)
+    eng.load_state(T, T[::-1].copy(), np.zeros(V, np.float32) + 0.3, np.zeros(V, np.float32))
+    q = np.array([7, V // 2, V - 1, 0, 11, 3, V - 2] + list(range(20, 20 + 57)), np.int32) % V
+    sim, idx = eng.topk(q, k, exact_fp32=exact)
+    _check(sim, idx, T, q, k)
+    # the three duplicates of row 7 lead every one of their own lists in id order
+    if k >= 3:
+        for r in range(3):
+            assert list(idx[r, :3]) == sorted([7, V // 2, V - 1])
+
+
+def test_topk_every_vocab_row_like_the_exporter():
+    """export_embeddings runs PREDICT over every vocab line (ref src/models/estimator.py:59-69)."""
+    from glove_tensorflow_b200.engine import GloveEngine
+    V, d, k = 2000, 64, 20
+    T = _table(V, d, 2, dup=False)
+    eng = GloveEngine(V, d, batch_size=64, plan_steps=1, max_steps=4)
+    eng.load_state(T, T, np.zeros(V, np.float32), np.zeros(V, np.float32))
+    q = np.arange(V, dtype=np.int32)
+    sim, idx = eng.topk(q, k)
+    assert np.array_equal(idx[:, 0], q)                      # every row is its own nearest neighbour
+    _check(sim, idx, T, q, k)
+
+
+def test_topk_rejects_unsupported_k():
+    from glove_tensorflow_b200.engine import GloveEngine
+    from glove_tensorflow_b200._lib import GloveError
+    eng = GloveEngine(100, 8, batch_size=8, plan_steps=1, max_steps=2)
+    eng.init_uniform(0)
+    with pytest.raises(GloveError):
+        eng.topk(np.array([1], np.int32), 33, exact_fp32=True)
