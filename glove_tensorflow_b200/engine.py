@@ -93,6 +93,7 @@ class GloveEngine:
         self._args = [self._make_args(i) for i in range(2)]
         self.grad = None
         self._norm_cache = None
+        self.last_topk_fallbacks = None
 
     # ---- state ---------------------------------------------------------------------------------------------------
     def _write_scalars(self, **kw):
@@ -388,8 +389,16 @@ class GloveEngine:
         else:
             check(lib.glove_topk_cosine(_ptr(self.row_table), self.V, self.d, self.P, _ptr(nb), _ptr(inv), _ptr(q), n, k,
                                         _ptr(sim), _ptr(idx), _ptr(ws), ws.numel(), _stream()), "glove_topk_cosine")
+            if self.tc_path_covers(k):
+                cnt = ctypes.c_int32(0)
+                check(lib.glove_topk_flagged(_ptr(ws), self.V, self.d, n, k, ctypes.byref(cnt), _stream()), "glove_topk_flagged")
+                self.last_topk_fallbacks = int(cnt.value)
         torch.cuda.synchronize()
         return sim.cpu().numpy().reshape(n, k), idx.cpu().numpy().reshape(n, k)
+
+    def tc_path_covers(self, k: int) -> bool:
+        """Shapes the tcgen05 candidate pass handles (everything else runs the exact fp32 scan)."""
+        return lib.glove_topk_kpad(self.d) <= 320 and k <= 24 and self.V >= 1024
 
     # ---- eval ----------------------------------------------------------------------------------------------------
     def eval_sums(self, batch_size: Optional[int] = None, first: int = 0, count: Optional[int] = None) -> np.ndarray:

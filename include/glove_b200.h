@@ -170,6 +170,10 @@ size_t glove_topk_workspace_bytes(int64_t V, int32_t d, int32_t n_queries, int32
 int glove_topk_cosine(const float *table, int64_t V, int32_t d, int32_t planes, const void *norm_bf16,
                       const float *inv_norm, const int32_t *query_ids, int32_t n_queries, int32_t k, float *out_sim,
                       int32_t *out_idx, void *workspace, size_t workspace_bytes, void *stream);
+/* Diagnostics: number of queries of the last glove_topk_cosine call on `workspace` that failed the candidate guarantee
+ * check and were recomputed by the exact scan (0 in the common case).  Synchronises. */
+int glove_topk_flagged(const void *workspace, int64_t V, int32_t d, int32_t n_queries, int32_t k, int32_t *host_count,
+                       void *stream);
 /* exact fp32 CUDA-core reference implementation of the same contract (no tensor cores); used by tests and as the
  * fallback for shapes the tensor-core path does not cover */
 int glove_topk_cosine_fp32(const float *table, int64_t V, int32_t d, int32_t planes, const float *inv_norm,

@@ -39,6 +39,9 @@ def test_topk_matches_oracle(V, d, k, exact):
     q = np.array([7, V // 2, V - 1, 0, 11, 3, V - 2] + list(range(20, 20 + 57)), np.int32) % V
     sim, idx = eng.topk(q, k, exact_fp32=exact)
     _check(sim, idx, T, q, k)
+    if not exact and eng.tc_path_covers(k):
+        # the tensor-core candidates must carry the answer themselves: at most a few queries may need the exact fallback
+        assert eng.last_topk_fallbacks is not None and eng.last_topk_fallbacks <= len(q) // 8, eng.last_topk_fallbacks
     # the three duplicates of row 7 lead every one of their own lists in id order
     if k >= 3:
         for r in range(3):
@@ -56,6 +59,23 @@ def test_topk_every_vocab_row_like_the_exporter():
     sim, idx = eng.topk(q, k)
     assert np.array_equal(idx[:, 0], q)                      # every row is its own nearest neighbour
     _check(sim, idx, T, q, k)
+    assert eng.last_topk_fallbacks <= V // 8, eng.last_topk_fallbacks
+
+
+def test_tensor_core_candidates_alone_are_correct():
+    """Large-ish table, no fallback allowed to hide a broken MMA: compare the tensor-core result with the exact scan and
+    require (almost) no guarantee-check fallbacks on well separated data."""
+    from glove_tensorflow_b200.engine import GloveEngine
+    V, d, k = 40000, 300, 10
+    T = _table(V, d, 5, dup=False)
+    eng = GloveEngine(V, d, batch_size=64, plan_steps=1, max_steps=4)
+    eng.load_state(T, T, np.zeros(V, np.float32), np.zeros(V, np.float32))
+    q = np.random.default_rng(6).integers(0, V, 777).astype(np.int32)
+    s1, i1 = eng.topk(q, k)
+    fallbacks = eng.last_topk_fallbacks
+    s2, i2 = eng.topk(q, k, exact_fp32=True)
+    assert np.array_equal(i1, i2) and np.array_equal(s1, s2)     # same fp32 routine => bit-identical similarities
+    assert fallbacks <= len(q) // 20, fallbacks
 
 
 def test_topk_rejects_unsupported_k():
