@@ -170,6 +170,26 @@ __global__ void fill_kernel(int32_t N, int32_t B, PrepSide ps, const int32_t *__
     }
 }
 
+// seg_prev[g] = 1 when the id of segment g (batch k) also occurs in batch k-1 of the same plan: binary search in the
+// sorted id list of that batch.  The first batch of a plan gets 1 ("unknown": it is never pre-replayed).
+__global__ void segprev_kernel(int32_t N, int32_t B, PrepSide ps, PlanSide out) {
+    for (int32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < N; q += gridDim.x * blockDim.x) {
+        if (!ps.f_seg[q]) continue;
+        const int32_t g = ps.e_seg[q], k = q / B;
+        int32_t flag = 1;
+        if (k > 0) {
+            const int32_t id = out.seg_id[g];
+            int32_t lo = out.b_seg[k - 1], hi = out.b_seg[k];
+            while (lo < hi) {
+                const int32_t mid = (lo + hi) >> 1;
+                if (out.seg_id[mid] < id) lo = mid + 1; else hi = mid;
+            }
+            flag = (lo < out.b_seg[k] && out.seg_id[lo] == id) ? 1 : 0;
+        }
+        out.seg_prev[g] = flag;
+    }
+}
+
 __global__ void itemrec_kernel(int32_t B, const int32_t *__restrict__ n_items, PlanSide out) {
     const int32_t NI = *n_items;
     for (int32_t it = blockIdx.x * blockDim.x + threadIdx.x; it < NI; it += gridDim.x * blockDim.x) {
@@ -262,6 +282,7 @@ int glove_prepare_batches(void *plan, void *workspace, size_t workspace_bytes, c
         items_kernel<<<blocks, threads, 0, stream>>>(N, B, K, ps, pv.side[s], pv.hdr, s);
         slots_kernel<<<blocks, threads, 0, stream>>>(N, B, ps, pv.side[s]);
         itemrec_kernel<<<blocks, threads, 0, stream>>>(B, &pv.hdr->n_item[s], pv.side[s]);
+        segprev_kernel<<<blocks, threads, 0, stream>>>(N, B, ps, pv.side[s]);
         GLOVE_CHECK_LAUNCH();
     }
     for (int s = 0; s < 2; ++s)

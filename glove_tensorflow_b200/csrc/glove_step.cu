@@ -138,9 +138,21 @@ __device__ __forceinline__ void head_eval(int head, float z, float a, float b, f
 // Flat mapping: one thread per (slot, float4) of the snapshot, a warp per 32 consecutive float4s.  Rows that need no
 // replay are a pure 128-bit copy; rows that do are replayed 4 columns per thread, so a long gap is spread over the
 // ~S/4 threads of the row instead of serialising on one warp, and the many small chunks balance across the SMs.
-__global__ void __launch_bounds__(256) stage_kernel(const StepParams p) {
+//
+// CATCHUP = true is the same arithmetic run AHEAD of time for the batch of step `step_arg` while the previous step is
+// still executing on another stream: rows of that batch which are NOT in the previous batch (seg_prev == 0) cannot be
+// touched by the step in flight, so their idle steps through step_arg-1 are replayed now and written back in place
+// (x, m, v, last_step = step_arg).  The regular stage of step_arg then finds them current and degenerates to a copy;
+// rows it could not pre-replay (seg_prev == 1, or no catch-up launched) are replayed there as before, so correctness
+// never depends on the catch-up having run.
+template <bool CATCHUP>
+__global__ void __launch_bounds__(256) stage_kernel(const StepParams p, int step_arg) {
     int k, step;
-    if (!batch_index(p, k, step)) return;
+    if (CATCHUP) {
+        step = step_arg;
+        k = step - p.hdr->first_step;
+        if (p.hdr->magic != kPlanMagic || k < 1 || k >= p.hdr->K || p.hdr->B != p.B || step > p.alpha_len) return;
+    } else if (!batch_index(p, k, step)) return;
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     const int seg0[2] = {p.side[0].b_seg[k], p.side[1].b_seg[k]};
@@ -159,7 +171,8 @@ __global__ void __launch_bounds__(256) stage_kernel(const StepParams p) {
         const int lcol = ls_col(p.d, s);
         float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
         int ls = 0;
-        if (active) { x = ld4(row + 4 * f); ls = __float_as_int(__ldg(row + lcol)); }
+        if (active) { x = ld4(row + 4 * f); ls = __float_as_int(row[lcol]); }
+        if (CATCHUP && active && p.side[s].seg_prev[seg0[s] + slot]) ls = 0;   // may be in flight: leave it to the stage
         if (replay) {
             const bool need = active && ls > 0 && ls < step;
             float4 m = make_float4(0.f, 0.f, 0.f, 0.f), v = m;
@@ -192,13 +205,33 @@ __global__ void __launch_bounds__(256) stage_kernel(const StepParams p) {
                 x = make_float4(xa.x, xa.y, xb.x, xb.y);
                 st4(const_cast<float *>(row) + p.S + 4 * f, make_float4(ma.x, ma.y, mb.x, mb.y));
                 st4(const_cast<float *>(row) + 2 * p.S + 4 * f, make_float4(va.x, va.y, vb.x, vb.y));
+                // catch-up: x goes back in place too; last_step is NOT touched here (other threads of the row may still
+                // have to read it) -- commit_ls_kernel sets it once this kernel has finished
+                if (CATCHUP) st4(const_cast<float *>(row) + 4 * f, x);
             }
         }
+        if (CATCHUP) continue;
         if (active) {
             // snapshot: 1.0 in the other side's bias column (= this side's last_step column)
             if ((lcol >> 2) == f) f4c(x, lcol & 3) = 1.0f;
             st4(p.snap[s] + (int64_t)slot * p.S + 4 * f, x);
         }
+    }
+}
+
+// second half of the catch-up: mark the pre-replayed rows current (same predicate as stage_kernel<true>)
+__global__ void __launch_bounds__(256) commit_ls_kernel(const StepParams p, int step) {
+    const int k = step - p.hdr->first_step;
+    if (p.hdr->magic != kPlanMagic || k < 1 || k >= p.hdr->K || p.hdr->B != p.B || step > p.alpha_len) return;
+    const int seg0[2] = {p.side[0].b_seg[k], p.side[1].b_seg[k]};
+    const int U0 = p.side[0].b_seg[k + 1] - seg0[0], U1 = p.side[1].b_seg[k + 1] - seg0[1];
+    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < U0 + U1; w += gridDim.x * blockDim.x) {
+        const int s = w >= U0 ? 1 : 0;
+        const int g = seg0[s] + (s ? w - U0 : w);
+        if (p.side[s].seg_prev[g]) continue;
+        float *ls_word = p.table[s] + (int64_t)p.side[s].seg_id[g] * p.P * p.S + ls_col(p.d, s);
+        const int ls = __float_as_int(*ls_word);
+        if (ls > 0 && ls < step) *ls_word = __int_as_float(step);
     }
 }
 
@@ -621,12 +654,12 @@ static int occupancy_grid(Kern kern, int threads) {
 template <int NV>
 static int launch_step(const StepParams &p, cudaStream_t stream, cudaEvent_t *ev = nullptr) {
     static int g_stage = 0, g_update = 0, g_apply = 0;
-    if (!g_stage) g_stage = occupancy_grid(stage_kernel, 256);
+    if (!g_stage) g_stage = occupancy_grid(stage_kernel<false>, 256);
     if (!g_update) g_update = occupancy_grid(update_kernel<NV, GLOVE_HEAD_GLOVE, false>, 128);
     if (!g_apply) g_apply = occupancy_grid(apply_kernel<NV>, 128);
     if (p.mode == MODE_TRAIN || p.mode == MODE_GRAD) {
         if (ev) cudaEventRecord(ev[0], stream);
-        stage_kernel<<<g_stage, 256, 0, stream>>>(p);
+        stage_kernel<false><<<g_stage, 256, 0, stream>>>(p, 0);
         if (ev) cudaEventRecord(ev[1], stream);
         const bool dp = p.dp_world > 1;
         if (p.head == GLOVE_HEAD_GLOVE) {
@@ -674,6 +707,20 @@ int glove_train_step(const glove_step_args *args, void *stream) {
     int rc = fill_params(args, p, MODE_TRAIN);
     if (rc != GLOVE_OK) return rc;
     return dispatch(p, (cudaStream_t)stream);
+}
+
+int glove_catchup_step(const glove_step_args *args, int32_t step_index, void *stream) {
+    StepParams p;
+    int rc = fill_params(args, p, MODE_TRAIN);
+    if (rc != GLOVE_OK) return rc;
+    if (p.opt != GLOVE_OPT_ADAM || p.adam_mode != GLOVE_ADAM_REPLAY) return GLOVE_OK;
+    static int grid = 0;
+    if (!grid) grid = occupancy_grid(stage_kernel<true>, 256);
+    // leave room for the step in flight: the catch-up is arithmetic-bound and is meant to fill its memory stalls
+    stage_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(p, step_index);
+    commit_ls_kernel<<<kNumSMs, 256, 0, (cudaStream_t)stream>>>(p, step_index);
+    GLOVE_CHECK_LAUNCH();
+    return GLOVE_OK;
 }
 
 int glove_train_step_profiled(const glove_step_args *args, void *stream_, float *ms3) {

@@ -92,6 +92,14 @@ class GloveEngine:
         self.sample_idx = None  # explicit [n_steps, B] injected batch order (parity tests)
         self._args = [self._make_args(i) for i in range(2)]
         self.grad = None
+        # overlap machinery: plan construction and the Adam catch-up of the NEXT step run on side streams
+        self.overlap = True
+        self._side = torch.cuda.Stream(device=self.device)
+        self._prep_stream = torch.cuda.Stream(device=self.device)
+        self._ev_step_done = [torch.cuda.Event(), torch.cuda.Event()]   # completion of step s -> slot s & 1
+        self._ev_catchup = None                                         # (step, event) of the launched catch-up
+        self._ev_plan = [None, None]                                    # plan buffer ready
+        self._keep = [None, None]
         self._norm_cache = None
         self.last_topk_fallbacks = None
 
@@ -110,6 +118,7 @@ class GloveEngine:
 
     def load_state(self, R, C, rb, cb, g=0.0):
         """Inject initial tables (reference layout: R, C [V,d]; rb, cb [V]; scalar g)."""
+        self._join_side()
         for side, (table, emb, bias) in enumerate(((self.row_table, R, rb), (self.col_table, C, cb))):
             e = torch.as_tensor(np.ascontiguousarray(emb, np.float32)).to(self.device)
             b = torch.as_tensor(np.ascontiguousarray(bias, np.float32).reshape(-1)).to(self.device)
@@ -120,17 +129,20 @@ class GloveEngine:
 
     def set_step(self, step: int):
         """Resume at a given global_step (checkpoint restore / steady-state benchmarking)."""
+        self._join_side()
         self._write_scalars(step=int(step))
         self.host_step = int(step)
         self.plan_first = [None, None]
 
     def set_plane(self, side: str, plane: int, emb: torch.Tensor, bias: torch.Tensor):
         """Write optimizer slot plane ``plane`` (1 = Adam m / Adagrad acc, 2 = Adam v) of ``side`` in {'row','col'}."""
+        self._join_side()
         table = self.row_table if side == "row" else self.col_table
         check(lib.glove_pack_plane(_ptr(table), self.V, self.d, self.P, plane, 0 if side == "row" else 1,
                                    _ptr(emb.contiguous()), _ptr(bias.contiguous()), _stream()), "glove_pack_plane")
 
     def set_last_step(self, side: str, ls: torch.Tensor):
+        self._join_side()
         table = self.row_table if side == "row" else self.col_table
         ls = ls.to(device=self.device, dtype=torch.int32).contiguous()
         check(lib.glove_set_last_step(_ptr(table), self.V, self.d, self.P, 0 if side == "row" else 1, _ptr(ls), _stream()),
@@ -186,7 +198,16 @@ class GloveEngine:
         self.flush()
         return self._unpack(self.row_table, 0)[0]
 
+    def _join_side(self):
+        """Order the current stream after everything in flight on the side streams (catch-up, plan prefetch): required
+        before the tables are read or written from outside the step sequence."""
+        main = torch.cuda.current_stream()
+        main.wait_stream(self._side)
+        main.wait_stream(self._prep_stream)
+        self._ev_catchup = None
+
     def flush(self):
+        self._join_side()
         if self.optimizer != "Adam" or self.adam_mode == "lazy":
             return
         for side, t in enumerate((self.row_table, self.col_table)):
@@ -248,16 +269,64 @@ class GloveEngine:
                                         _ptr(col), _ptr(ca), _ptr(cb), self.nnz, _ptr(sidx),
                                         int(first_step) * self.B, self.shuffle_key, int(first_step), self.K, self.B,
                                         self.V, _stream()), "glove_prepare_batches")
-        self._keep = sidx  # keep the index chunk alive until the stream has consumed it
+        self._keep[which] = sidx  # keep the index chunk alive until the stream has consumed it
         self.plan_first[which] = first_step
         self._plan_counts[which] = None
+        self._ev_plan[which] = None
+
+    def _prefetch_plan(self, step: int):
+        """Build the plan of the chunk AFTER the one `step` is in, on the side stream, while this chunk trains."""
+        nxt_first = (step // self.K + 1) * self.K
+        which = (nxt_first // self.K) & 1
+        if self.plan_first[which] == nxt_first or nxt_first >= self.max_steps:
+            return
+        if self.sample_idx is not None and nxt_first - self.sample_idx_first >= self.sample_idx.shape[0]:
+            return
+        main = torch.cuda.current_stream()
+        # the buffer being overwritten belonged to the chunk before the current one: every step of it has completed
+        # before the current chunk's first step was enqueued on `main`, so ordering after `main` here is sufficient
+        self._prep_stream.wait_stream(main)
+        with torch.cuda.stream(self._prep_stream):
+            self.prepare(nxt_first, which)
+            ev = torch.cuda.Event()
+            ev.record(self._prep_stream)
+        self._ev_plan[which] = ev
 
     def _plan_for(self, step: int) -> int:
         first = (step // self.K) * self.K
         which = (step // self.K) & 1
         if self.plan_first[which] != first:
+            torch.cuda.current_stream().wait_stream(self._prep_stream)   # one prepare at a time (shared workspace)
             self.prepare(first, which)
+        elif self._ev_plan[which] is not None:      # built on the side stream: order the consumer after it
+            torch.cuda.current_stream().wait_event(self._ev_plan[which])
+            self._ev_plan[which] = None
         return which
+
+    def _before_step(self, which):
+        """Overlap hooks run before step `host_step` is enqueued: (1) start the catch-up of step+1 on the side stream
+        (it only needs step-1 to have finished), (2) make this step wait for its own catch-up, (3) prefetch the next plan."""
+        s = self.host_step
+        if not self.overlap:
+            return
+        main = torch.cuda.current_stream()
+        if self._ev_catchup is not None and self._ev_catchup[0] == s:
+            main.wait_event(self._ev_catchup[1])
+        self._ev_catchup = None
+        if (self.optimizer == "Adam" and self.adam_mode == "replay" and (s + 1) % self.K != 0 and s + 1 < self.max_steps
+                and s >= 1):
+            self._side.wait_event(self._ev_step_done[(s - 1) & 1])
+            check(lib.glove_catchup_step(ctypes.byref(self._args[which]), s + 1, ctypes.c_void_p(self._side.cuda_stream)),
+                  "glove_catchup_step")
+            ev = torch.cuda.Event()
+            ev.record(self._side)
+            self._ev_catchup = (s + 1, ev)
+        if s % self.K == 0:
+            self._prefetch_plan(s)
+
+    def _after_step(self):
+        if self.overlap:
+            self._ev_step_done[self.host_step & 1].record(torch.cuda.current_stream())
 
     # ---- train ---------------------------------------------------------------------------------------------------
     def step(self):
@@ -266,10 +335,12 @@ class GloveEngine:
         if self.host_step >= self.max_steps:
             raise RuntimeError("max_steps exhausted; construct the engine with a larger max_steps")
         which = self._plan_for(self.host_step)
+        self._before_step(which)
         if self.dp_world > 1:
             self._step_dp(which)
             return
         check(lib.glove_train_step(ctypes.byref(self._args[which]), _stream()), "glove_train_step")
+        self._after_step()
         self.host_step += 1
         if self.adam_mode == "dense":
             self.flush()
@@ -290,6 +361,7 @@ class GloveEngine:
         which = self._plan_for(self.host_step)
         gr, gc, gs = self.grad
         check(lib.glove_apply_step(ctypes.byref(self._args[which]), _ptr(gr), _ptr(gc), _ptr(gs), _stream()), "glove_apply_step")
+        self._after_step()
         self.host_step += 1
         if self.adam_mode == "dense":
             self.flush()
@@ -318,6 +390,7 @@ class GloveEngine:
 
     def step_profiled(self):
         """One TRAIN step with per-kernel device timings (ms): (stage, update, fix+finish).  Synchronises."""
+        self._join_side()
         which = self._plan_for(self.host_step)
         ms = (ctypes.c_float * 3)()
         check(lib.glove_train_step_profiled(ctypes.byref(self._args[which]), _stream(), ms), "glove_train_step_profiled")
@@ -332,6 +405,7 @@ class GloveEngine:
         if getattr(self, "_host_staging", None) is None:
             self._host_staging = torch.empty(lib.glove_host_staging_bytes(self.K, self.B), dtype=torch.uint8, device=self.device)
         assert host_row.numel() == self.K * self.B and not host_row.is_cuda
+        self._join_side()
         check(lib.glove_train_steps_host(ctypes.byref(self._args[0]), _ptr(self.plans[0]), _ptr(self.prep_ws),
                                          self.prep_ws.numel(), _ptr(self._host_staging), self._host_staging.numel(),
                                          _ptr(host_row), _ptr(host_col), _ptr(host_a), _ptr(host_b), self.K,

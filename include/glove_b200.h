@@ -129,6 +129,11 @@ typedef struct glove_step_args {
 size_t glove_step_workspace_bytes(int32_t B, int32_t d);
 /* one full TRAIN step; increments scalars->step */
 int glove_train_step(const glove_step_args *args, void *stream);
+/* Optional overlap aid for GLOVE_ADAM_REPLAY: replays, ahead of time and on ANOTHER stream, the idle Adam steps of the
+ * rows of step `step_index`'s batch that are not in the batch of step_index-1 (so the step in flight cannot touch
+ * them).  Must be ordered after the completion of step_index-2 and before the start of step_index (events); a no-op
+ * for the first batch of a plan and for other optimizers / modes.  Results are bit-identical with or without it. */
+int glove_catchup_step(const glove_step_args *args, int32_t step_index, void *stream);
 /* same step, with CUDA events recorded around its three kernels on `stream`; synchronises and returns their device
  * durations in milliseconds: ms3 = {stage, update, fix+finish}.  Measurement aid for bench.py (roofline). */
 int glove_train_step_profiled(const glove_step_args *args, void *stream, float *ms3);

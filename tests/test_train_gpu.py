@@ -199,3 +199,23 @@ def test_data_parallel_replicas_on_one_gpu(world, adam_mode, optimizer):
             assert np.array_equal(states[0][k], stt[k]), k
         assert _rel(states[0][k], getattr(ref, k)) < 3e-5, (k, _rel(states[0][k], getattr(ref, k)))
     assert np.max(np.abs(np.array(losses) - ref_losses) / np.abs(ref_losses)) < RTOL
+
+
+def test_overlap_streams_do_not_change_results():
+    """Catch-up on the side stream + plan prefetch vs everything on one stream: bit-identical tables and losses."""
+    from glove_tensorflow_b200.engine import GloveEngine
+    V, d, B, steps, n = 5000, 64, 1024, 70, 60000
+    coo = make_coo(V, n, 41)
+    st = o.init_state(V, d, 42)
+    out = []
+    for overlap in (True, False):
+        eng = GloveEngine(V, d, learning_rate=0.01, batch_size=B, plan_steps=6, max_steps=steps + 8)
+        eng.overlap = overlap
+        eng.load_state(st.R, st.C, st.rb, st.cb, st.g)
+        eng.set_coo(coo["row"], coo["col"], coo["target"], coo["weight"], shuffle_key=3)
+        l = np.concatenate([eng.train(25), eng.train(45)])          # a flush-free pause in the middle
+        s = eng.get_state(slots=True)
+        out.append((l, s))
+    assert np.array_equal(out[0][0], out[1][0])
+    for k in ("R", "C", "rb", "cb", "R/s0", "R/s1", "C/s0", "cb/s1"):
+        assert np.array_equal(out[0][1][k], out[1][1][k]), k
