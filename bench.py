@@ -113,32 +113,41 @@ def steady_state(eng, V, B_global, seed):
 
 # ------------------------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
+    """One persistent `nvidia-smi -lms 100` process; samples are time-stamped so that those inside the timed region can
+    be picked out (the region is short: when no sample falls inside it, the nearest ones under load are used)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
 
     def run(self):
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([x.strip() for x in out.strip().split(",")])
-            except Exception:
-                pass
-            time.sleep(0.1)
+        if self.proc is None:
+            return
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.strip().split(",")]))
 
-    def summary(self):
-        self.stop_flag = True
-        rows = [r for r in self.rows if len(r) >= 7 and r[0].isdigit()]
+    def summary(self, t_start, t_end):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+        rows = [(t, r) for t, r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
         if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        inside = [r for t, r in rows if t_start - 0.05 <= t <= t_end + 0.15]
+        used = inside if inside else [r for _, r in sorted(rows, key=lambda tr: abs(tr[0] - t_end))[:3]]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in rows)]
-        return {"sm_mhz": float(np.median([float(r[0]) for r in rows])), "sm_max_mhz": float(rows[0][1]),
-                "reasons": reasons, "samples": len(rows)}
+        reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in used)]
+        return {"sm_mhz": float(np.median([float(r[0]) for r in used])), "sm_max_mhz": float(used[0][1]),
+                "reasons": reasons, "samples": len(used), "samples_in_timed_region": len(inside),
+                "power_w_max": max(float(r[2]) for r in used)}
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -211,6 +220,9 @@ def main():
 
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    sampler = ClockSampler(local_rank)          # started early: nvidia-smi takes a while to deliver its first sample
+    if rank == 0:
+        sampler.start()
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     N = max(world, 1)
@@ -236,12 +248,9 @@ def main():
     first_timed = eng.host_step
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n_prep0 = 0
+    t_start = time.time()
     e0.record()
     for _ in range(args.steps):
         eng.step()
@@ -250,7 +259,8 @@ def main():
     if world > 1:
         dist.barrier()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.summary() if rank == 0 else None
+    t_end = time.time()
+    clocks = sampler.summary(t_start, t_end) if rank == 0 else None
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -268,7 +278,7 @@ def main():
     roofline, kernels_ms = None, None
     if N == 1:
         prof = np.array([eng.step_profiled() for _ in range(32)])
-        kernels_ms = {"stage": float(prof[:, 0].mean()), "update": float(prof[:, 1].mean()), "fix_finish": float(prof[:, 2].mean())}
+        kernels_ms = {"stage": float(prof[:, 0].mean()), "update": float(prof[:, 1].mean())}
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -279,7 +289,7 @@ def main():
         achieved = bytes_alg / (step_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6650",
-                    "kernel": "whole step = stage_kernel + update_kernel + fix_kernel (algorithmic bytes are per step)",
+                    "kernel": "whole step = stage_kernel + update_kernel (algorithmic bytes are per step)",
                     "algorithmic_bytes_per_step": bytes_alg, "U_row": U_r, "U_col": U_c,
                     "rho": (U_r + U_c) / (2.0 * B), "frac_of_nominal_8000": achieved / 8000.0,
                     "kernels_ms": kernels_ms,
@@ -287,7 +297,7 @@ def main():
 
     # ---- e2e: HOST buffers through the C ABI (glove_train_steps_host): H2D of every batch + D2H of every loss --------
     e2e = None
-    if not args.no_e2e and N == 1:
+    if not args.no_e2e:
         n_chunks = max(1, args.steps // K)
         pool = 4
         hr = [torch.empty(K * B, dtype=torch.int32).pin_memory() for _ in range(pool)]
@@ -296,23 +306,35 @@ def main():
         hb = [torch.empty(K * B, dtype=torch.float32).pin_memory() for _ in range(pool)]
         hl = torch.empty(K, dtype=torch.float32).pin_memory()
         for i in range(pool):
-            s = (i * K * B) % max(1, nnz - K * B)
-            hr[i].copy_(row[s:s + K * B]); hc[i].copy_(col[s:s + K * B]); ha[i].copy_(tgt[s:s + K * B]); hb[i].copy_(wgt[s:s + K * B])
+            sel = (torch.arange(K * B, device=dev, dtype=torch.int64) + i * K * B) % nnz
+            hr[i].copy_(row[sel]); hc[i].copy_(col[sel]); ha[i].copy_(tgt[sel]); hb[i].copy_(wgt[sel])
         torch.cuda.synchronize()
-        eng.train_steps_host(hr[0], hc[0], ha[0], hb[0], hl)       # warm
+
+        def chunk(i):
+            if N == 1:
+                eng.train_steps_host(hr[i], hc[i], ha[i], hb[i], hl)      # one C-ABI call, HOST buffers in / losses out
+            else:
+                eng.train_chunk_from_host(hr[i], hc[i], ha[i], hb[i])
+        chunk(0)                                                          # warm
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
         t0 = time.perf_counter()
         for c in range(n_chunks):
-            i = c % pool
-            eng.train_steps_host(hr[i], hc[i], ha[i], hb[i], hl)
+            chunk(c % pool)
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
         dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
         e2e = {"value": n_chunks * K * B / dt, "unit": "updates/s", "h2d_bytes_per_step": B * 16,
                "d2h_bytes_per_step": 4 + 4.0 / K, "steps": n_chunks * K,
-               "path": "glove_train_steps_host: pinned host COO -> H2D -> plan -> K steps -> D2H losses, per call"}
-    elif N > 1:
-        e2e = {"value": None, "unit": "updates/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
-               "path": "not measured at N>1 this round"}
+               "path": ("glove_train_steps_host: pinned host COO -> H2D -> plan -> K steps -> D2H losses, per call" if N == 1 else
+                        "GloveEngine.train_chunk_from_host on every rank: pinned host COO (global batch) -> H2D -> plan -> "
+                        "K x (grad_step, NCCL all-reduce, apply_step) -> D2H losses")}
 
     if rank != 0:
         if world > 1:
@@ -335,7 +357,7 @@ def main():
                            l2_flush="inputs larger than L2 (tables+slots %.1f GB, COO %.1f GB)"
                                     % (2 * V * eng.P * eng.S * 4 / 1e9, nnz * 16 / 1e9),
                            state="cold" if args.cold_state else "steady-state emulation at step %d" % T0),
-            "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * 3 + n_prep * 14,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * (2 + (2 if args.adam_mode == "replay" else 0)) + n_prep * 20,
             "roofline": roofline, "cpu_baseline": cpu, "final_loss": float(losses[-1])}
     print(json.dumps(line))
     if world > 1:

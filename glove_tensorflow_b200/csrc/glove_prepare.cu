@@ -131,6 +131,7 @@ __global__ void items_kernel(int32_t N, int32_t B, int32_t K, PrepSide ps, PlanS
             out.item_start[it] = q;
             out.item_part[it] = ps.f_part[q] ? ps.e_part[q] : -1;
         }
+        if (ps.f_seg[q]) out.seg_long[g] = ps.f_long[q] ? ps.e_long[q] : -1;
         if (ps.f_long[q]) {
             const int32_t l = ps.e_long[q];
             out.long_seg[l] = g;
@@ -198,7 +199,19 @@ __global__ void itemrec_kernel(int32_t B, const int32_t *__restrict__ n_items, P
         const int32_t seg_end = out.seg_start[g + 1], seg_len = seg_end - out.seg_start[g];
         const int32_t n = min(start + kItemMax, seg_end) - start;
         const int32_t part = seg_len > kItemMax ? out.item_part[it] - out.b_part[k] + 1 : 0;
-        out.item_rec[it] = make_int4(out.seg_id[g], g - out.b_seg[k], start, n | (part << 8));
+        out.item_rec[it] = make_int4(part ? out.seg_long[g] - out.b_long[k] : out.seg_id[g], g - out.b_seg[k], start,
+                                     n | (part << 8));
+    }
+}
+
+__global__ void longrec_kernel(int32_t B, const int32_t *__restrict__ n_long, PlanSide out) {
+    const int32_t NL = *n_long;
+    for (int32_t l = blockIdx.x * blockDim.x + threadIdx.x; l < NL; l += gridDim.x * blockDim.x) {
+        const int32_t g = out.long_seg[l], it0 = out.long_item[l];
+        const int32_t k = out.seg_start[g] / B;
+        const int32_t len = out.seg_start[g + 1] - out.seg_start[g];
+        out.long_rec[l] = make_int4(out.seg_id[g], g - out.b_seg[k], out.item_part[it0] - out.b_part[k],
+                                    (len + kItemMax - 1) / kItemMax);
     }
 }
 
@@ -282,6 +295,7 @@ int glove_prepare_batches(void *plan, void *workspace, size_t workspace_bytes, c
         items_kernel<<<blocks, threads, 0, stream>>>(N, B, K, ps, pv.side[s], pv.hdr, s);
         slots_kernel<<<blocks, threads, 0, stream>>>(N, B, ps, pv.side[s]);
         itemrec_kernel<<<blocks, threads, 0, stream>>>(B, &pv.hdr->n_item[s], pv.side[s]);
+        longrec_kernel<<<blocks, threads, 0, stream>>>(B, &pv.hdr->n_long[s], pv.side[s]);
         segprev_kernel<<<blocks, threads, 0, stream>>>(N, B, ps, pv.side[s]);
         GLOVE_CHECK_LAUNCH();
     }

@@ -22,8 +22,7 @@
 namespace glove {
 
 enum { MODE_TRAIN = 0, MODE_GRAD = 1, MODE_APPLY = 2 };
-constexpr int kFixThreads = 256;
-constexpr int kFixBlocks = kNumSMs;
+constexpr int kMaxWarps = 148 * 64;  // upper bound on resident warps of the update grid
 
 struct StepParams {
     float *table[2];
@@ -32,8 +31,9 @@ struct StepParams {
     PlanSide side[2];
     float *snap[2];       // [B][S] pre-step snapshot rows
     float *partial[2];    // [max parts][S] partial gradient sums of split segments
-    float4 *item_out[2];  // [max items] {data loss, sum e, reg term, 0}
-    double *cta_out;      // [kFixBlocks][3] per-CTA pre-reduced loss terms
+    int32_t *long_cnt[2]; // [max long segments] chunks finished so far (self-resetting; workspace starts zeroed)
+    int32_t *chunk_cnt[2];  // [max parts] pieces finished in the chunk that starts at this partial slot (self-resetting)
+    double *warp_out;     // [kMaxWarps][3] per-warp sums of {data loss, sum e, reg term}
     float *grad[2];       // MODE_GRAD / MODE_APPLY: dense per-slot gradient buffers
     float *grad_scalars;  // [4]
     const float *alpha;
@@ -49,8 +49,9 @@ struct StepParams {
 struct StepWs {
     float *snap[2];
     float *partial[2];
-    float4 *item_out[2];
-    double *cta_out;
+    int32_t *long_cnt[2];
+    int32_t *chunk_cnt[2];
+    double *warp_out;
     size_t bytes;
 };
 static inline int64_t max_items_per_batch(int32_t B) { return (int64_t)B + B / kItemMax + 2; }
@@ -63,8 +64,9 @@ static StepWs step_ws_view(void *base, int32_t B, int32_t d) {
     const int32_t S = table_stride(d);
     for (int s = 0; s < 2; ++s) w.snap[s] = (float *)take(sizeof(float) * (size_t)B * S);
     for (int s = 0; s < 2; ++s) w.partial[s] = (float *)take(sizeof(float) * (size_t)max_parts_per_batch(B) * S);
-    for (int s = 0; s < 2; ++s) w.item_out[s] = (float4 *)take(sizeof(float4) * (size_t)max_items_per_batch(B));
-    w.cta_out = (double *)take(sizeof(double) * 3 * kFixBlocks);
+    for (int s = 0; s < 2; ++s) w.long_cnt[s] = (int32_t *)take(sizeof(int32_t) * (size_t)(B / kItemMax + 2));
+    for (int s = 0; s < 2; ++s) w.chunk_cnt[s] = (int32_t *)take(sizeof(int32_t) * (size_t)max_parts_per_batch(B));
+    w.warp_out = (double *)take(sizeof(double) * 3 * kMaxWarps);
     w.bytes = off;
     return w;
 }
@@ -287,6 +289,42 @@ __device__ __forceinline__ void apply_row(const StepParams &p, float *row, float
     store_row<NV>(row, x, lane, S4);
 }
 
+// ---- end of step: loss, global bias, step counter --------------------------------------------------------------------------------------
+__device__ void finish_step(const StepParams &p, int step, const float *reduced /* MODE_APPLY */, double ld = 0.0,
+                            double se = 0.0, double rg = 0.0) {
+    if (reduced) { ld = reduced[0]; se = reduced[1]; rg = reduced[2]; }
+    if (p.mode == MODE_GRAD) {
+        p.grad_scalars[0] = (float)ld; p.grad_scalars[1] = (float)se; p.grad_scalars[2] = (float)rg; p.grad_scalars[3] = 0.0f;
+        p.sc->ticket = 0;
+        return;
+    }
+    const double B = (double)p.B;
+    float g = p.sc->g;
+    const double reg = (double)p.rs * (rg / B + (double)p.l2 * (double)g * (double)g);
+    const float loss = (float)(ld / B + reg);
+    const float dg = (float)se + (2.0f * p.rs * p.l2) * g;
+    if (p.opt == GLOVE_OPT_ADAM) {  // dense ResourceApplyAdam form for the scalar variable
+        const float a = p.alpha[step];
+        float m = p.sc->g_s0, v = p.sc->g_s1;
+        m = __fadd_rn(m, __fmul_rn(__fsub_rn(dg, m), __fsub_rn(1.0f, p.b1)));
+        v = __fadd_rn(v, __fmul_rn(__fsub_rn(__fmul_rn(dg, dg), v), __fsub_rn(1.0f, p.b2)));
+        g = __fsub_rn(g, div_pos(__fmul_rn(a, m), __fadd_rn(sqrt_pos(v), p.eps)));
+        p.sc->g_s0 = m; p.sc->g_s1 = v;
+    } else if (p.opt == GLOVE_OPT_ADAGRAD) {
+        float acc = p.sc->g_s0;
+        adagrad_update(g, acc, dg, p.lr, p.eps);
+        p.sc->g_s0 = acc;
+    } else {
+        sgd_update(g, dg, p.lr);
+    }
+    p.sc->g = g;
+    p.sc->loss = loss;
+    if (p.loss_out) p.loss_out[step % p.loss_cap] = loss;
+    p.sc->ticket = 0;
+    __threadfence();
+    p.sc->step = step + 1;
+}
+
 // ---- K2: update ----------------------------------------------------------------------------------------------------
 template <int NV>
 __device__ __forceinline__ float dot_row(const float4 (&x)[NV], const float4 (&y)[NV]) {
@@ -309,6 +347,39 @@ __device__ __forceinline__ void axpy_row(float4 (&acc)[NV], float e, const float
     }
 }
 
+constexpr int kChunk = 16;  // pieces per first-level combine of a split segment
+
+// acc = sum_{i < n} rows[i * stride_rows] in index order; 4 rows in flight (the caller lends 4 dead row buffers).
+// L2-coherent loads (the rows were written by other SMs in this launch).
+template <int NV>
+__device__ __forceinline__ void sum_partials(float4 (&acc)[NV], const float *base, int n, int stride_rows, int S,
+                                             float4 (&b0)[NV], float4 (&b1)[NV], float4 (&b2)[NV], float4 (&b3)[NV],
+                                             int lane, int S4) {
+#pragma unroll
+    for (int r = 0; r < NV; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+    for (int q = 0; q < n; q += 4) {
+#pragma unroll
+        for (int r = 0; r < NV; ++r) {
+            const int f = lane + 32 * r;
+            const bool in = r < NV - 1 || f < S4;
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float *p0 = base + (int64_t)q * stride_rows * S + 4 * f;
+            b0[r] = in ? __ldcg(reinterpret_cast<const float4 *>(p0)) : z;
+            b1[r] = (in && q + 1 < n) ? __ldcg(reinterpret_cast<const float4 *>(p0 + (int64_t)stride_rows * S)) : z;
+            b2[r] = (in && q + 2 < n) ? __ldcg(reinterpret_cast<const float4 *>(p0 + 2 * (int64_t)stride_rows * S)) : z;
+            b3[r] = (in && q + 3 < n) ? __ldcg(reinterpret_cast<const float4 *>(p0 + 3 * (int64_t)stride_rows * S)) : z;
+        }
+#pragma unroll
+        for (int r = 0; r < NV; ++r) {
+            acc[r].x += b0[r].x; acc[r].y += b0[r].y; acc[r].z += b0[r].z; acc[r].w += b0[r].w;
+            acc[r].x += b1[r].x; acc[r].y += b1[r].y; acc[r].z += b1[r].z; acc[r].w += b1[r].w;
+            acc[r].x += b2[r].x; acc[r].y += b2[r].y; acc[r].z += b2[r].z; acc[r].w += b2[r].w;
+            acc[r].x += b3[r].x; acc[r].y += b3[r].y; acc[r].z += b3[r].z; acc[r].w += b3[r].w;
+        }
+    }
+}
+
 template <int NV, int HEAD, bool DP>
 __global__ void __launch_bounds__(128, (NV <= 3 ? 4 : 3)) update_kernel(const StepParams p) {
     int k, step;
@@ -321,6 +392,7 @@ __global__ void __launch_bounds__(128, (NV <= 3 ? 4 : 3)) update_kernel(const St
     const float ce = (2.0f * p.rs * p.l2) / ((float)p.d * (float)p.B), cbias = (2.0f * p.rs * p.l2) / (float)p.B;
     const float reg_unscale = (float)p.B / (2.0f * p.rs);  // coef * reg_unscale = l2/d (embedding) | l2 (bias)
     const bool train = p.mode == MODE_TRAIN;
+    double w_ld = 0.0, w_se = 0.0, w_rg = 0.0;   // this warp's share of the step's loss terms (fixed item order)
 
 #pragma unroll 1
     for (int s = 0; s < 2; ++s) {
@@ -338,7 +410,7 @@ __global__ void __launch_bounds__(128, (NV <= 3 ? 4 : 3)) update_kernel(const St
             // the epilogue, so their HBM latency hides behind the whole gather loop); the next item's record.
             const int slot = ir.y, start = ir.z, n = ir.w & 0xff, part = ir.w >> 8;
             const int4 myrec = lane < n ? __ldg(rec + start + lane) : make_int4(0, 0, 0, 0);
-            float *row = p.table[s] + (int64_t)ir.x * p.P * p.S;
+            float *row = p.table[s] + (int64_t)(part ? 0 : ir.x) * p.P * p.S;
             float4 x[NV], acc[NV], bufA[NV], bufB[NV], s1[NV], s2[NV];
             load_row<NV>(x, p.snap[s] + (int64_t)slot * p.S, lane, S4);
             const bool applies = train && part == 0;
@@ -404,11 +476,47 @@ __global__ void __launch_bounds__(128, (NV <= 3 ? 4 : 3)) update_kernel(const St
                 }
             }
             sq = warp_sum(sq);
-            if (lane == 0)
-                p.item_out[s][itl] = make_float4(s == 0 ? loss_d : 0.0f, s == 0 ? sum_e : 0.0f, fn * reg_unscale * sq, 0.0f);
+            if (s == 0) { w_ld += (double)loss_d; w_se += (double)sum_e; }
+            w_rg += (double)(fn * reg_unscale * sq);
 
             if (part) {
+                // Piece of a split segment.  Two-level, fixed-order combine with no extra launch: pieces are grouped in
+                // chunks of kChunk; the warp that completes the LAST piece of a chunk adds the chunk's partial sums in
+                // piece order into the chunk's first slot; the warp that completes the LAST chunk adds the chunk sums in
+                // chunk order and applies the update.  Which warp does it is timing-dependent, what it computes is not.
                 store_row<NV>(p.partial[s] + (int64_t)(part - 1) * p.S, acc, lane, S4);
+                const int4 lr = __ldg(ps.long_rec + ps.b_long[k] + ir.x);   // {token id, slot, first partial, pieces}
+                const int piece = (part - 1) - lr.z, chunk = piece / kChunk;
+                const int c_first = lr.z + chunk * kChunk;                    // partial slot of the chunk's first piece
+                const int c_n = min(kChunk, lr.w - chunk * kChunk);
+                __threadfence();
+                int last = 0;
+                if (lane == 0) last = atomicAdd(p.chunk_cnt[s] + c_first, 1) == c_n - 1;
+                if (__shfl_sync(0xffffffffu, last, 0)) {
+                    __threadfence();
+                    if (lane == 0) p.chunk_cnt[s][c_first] = 0;
+                    sum_partials<NV>(acc, p.partial[s] + (int64_t)c_first * p.S, c_n, 1, p.S, bufA, bufB, x, s1, lane, S4);
+                    const int n_chunks = (lr.w + kChunk - 1) / kChunk;
+                    if (n_chunks > 1) store_row<NV>(p.partial[s] + (int64_t)c_first * p.S, acc, lane, S4);
+                    __threadfence();
+                    last = 0;
+                    if (lane == 0) last = atomicAdd(p.long_cnt[s] + ir.x, 1) == n_chunks - 1;
+                    if (__shfl_sync(0xffffffffu, last, 0)) {
+                        __threadfence();
+                        if (lane == 0) p.long_cnt[s][ir.x] = 0;     // ready for the next step
+                        if (n_chunks > 1)
+                            sum_partials<NV>(acc, p.partial[s] + (int64_t)lr.z * p.S, n_chunks, kChunk, p.S, bufA, bufB, x, s1, lane, S4);
+                        if (!train) {
+                            store_row<NV>(p.grad[s] + (int64_t)lr.y * p.S, acc, lane, S4);
+                        } else {
+                            float *lrow = p.table[s] + (int64_t)lr.x * p.P * p.S;
+                            load_row<NV>(x, p.snap[s] + (int64_t)lr.y * p.S, lane, S4);
+                            if (p.P >= 2) load_row<NV>(s1, lrow + p.S, lane, S4);
+                            if (p.P >= 3) load_row<NV>(s2, lrow + 2 * p.S, lane, S4);
+                            apply_row<NV>(p, lrow, x, acc, s1, s2, s, step, lane);
+                        }
+                    }
+                }
             } else if (!train) {
                 store_row<NV>(p.grad[s] + (int64_t)slot * p.S, acc, lane, S4);
             } else {
@@ -417,6 +525,29 @@ __global__ void __launch_bounds__(128, (NV <= 3 ? 4 : 3)) update_kernel(const St
             ir = ir_next;
             itl = itn;
         }
+    }
+    // ---- end of step: per-warp loss terms -> last CTA (ticket) adds them in warp order and finishes the step
+    __shared__ double sh_red[3][128];
+    __shared__ int is_last;
+    if (lane == 0) { p.warp_out[3 * warp] = w_ld; p.warp_out[3 * warp + 1] = w_se; p.warp_out[3 * warp + 2] = w_rg; }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(&p.sc->ticket, 1) == (int)gridDim.x - 1);
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        const int tid = threadIdx.x;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+        for (int w = tid; w < nwarps; w += 128) {
+            a0 += __ldcg(p.warp_out + 3 * w); a1 += __ldcg(p.warp_out + 3 * w + 1); a2 += __ldcg(p.warp_out + 3 * w + 2);
+        }
+        sh_red[0][tid] = a0; sh_red[1][tid] = a1; sh_red[2][tid] = a2;
+        __syncthreads();
+        for (int o = 64; o > 0; o >>= 1) {
+            if (tid < o) { sh_red[0][tid] += sh_red[0][tid + o]; sh_red[1][tid] += sh_red[1][tid + o]; sh_red[2][tid] += sh_red[2][tid + o]; }
+            __syncthreads();
+        }
+        if (tid == 0) finish_step(p, step, nullptr, sh_red[0][0], sh_red[1][0], sh_red[2][0]);
     }
 }
 
@@ -441,161 +572,6 @@ __global__ void __launch_bounds__(128) apply_kernel(const StepParams p) {
         if (p.P >= 2) load_row<NV>(s1, row + p.S, lane, S4);
         if (p.P >= 3) load_row<NV>(s2, row + 2 * p.S, lane, S4);
         apply_row<NV>(p, row, x, G, s1, s2, s, step, lane);
-    }
-}
-
-// ---- K3: long segments + finish --------------------------------------------------------------------------------------
-__device__ void finish_step(const StepParams &p, int step, const float *reduced /* MODE_APPLY */, double ld = 0.0,
-                            double se = 0.0, double rg = 0.0) {
-    if (reduced) { ld = reduced[0]; se = reduced[1]; rg = reduced[2]; }
-    if (p.mode == MODE_GRAD) {
-        p.grad_scalars[0] = (float)ld; p.grad_scalars[1] = (float)se; p.grad_scalars[2] = (float)rg; p.grad_scalars[3] = 0.0f;
-        p.sc->ticket = 0;
-        return;
-    }
-    const double B = (double)p.B;
-    float g = p.sc->g;
-    const double reg = (double)p.rs * (rg / B + (double)p.l2 * (double)g * (double)g);
-    const float loss = (float)(ld / B + reg);
-    const float dg = (float)se + (2.0f * p.rs * p.l2) * g;
-    if (p.opt == GLOVE_OPT_ADAM) {  // dense ResourceApplyAdam form for the scalar variable
-        const float a = p.alpha[step];
-        float m = p.sc->g_s0, v = p.sc->g_s1;
-        m = __fadd_rn(m, __fmul_rn(__fsub_rn(dg, m), __fsub_rn(1.0f, p.b1)));
-        v = __fadd_rn(v, __fmul_rn(__fsub_rn(__fmul_rn(dg, dg), v), __fsub_rn(1.0f, p.b2)));
-        g = __fsub_rn(g, div_pos(__fmul_rn(a, m), __fadd_rn(sqrt_pos(v), p.eps)));
-        p.sc->g_s0 = m; p.sc->g_s1 = v;
-    } else if (p.opt == GLOVE_OPT_ADAGRAD) {
-        float acc = p.sc->g_s0;
-        adagrad_update(g, acc, dg, p.lr, p.eps);
-        p.sc->g_s0 = acc;
-    } else {
-        sgd_update(g, dg, p.lr);
-    }
-    p.sc->g = g;
-    p.sc->loss = loss;
-    if (p.loss_out) p.loss_out[step % p.loss_cap] = loss;
-    p.sc->ticket = 0;
-    __threadfence();
-    p.sc->step = step + 1;
-}
-
-__global__ void __launch_bounds__(kFixThreads) fix_kernel(const StepParams p) {
-    int k, step;
-    if (!batch_index(p, k, step)) return;
-    __shared__ __align__(16) float sh_part[kFixThreads / 32][512];  // per-warp partial sums of one long segment (S <= 512)
-    __shared__ double sh_red[3][kFixThreads];
-    __shared__ int is_last;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    constexpr int NW = kFixThreads / 32;
-    const int L0[2] = {p.side[0].b_long[k], p.side[1].b_long[k]};
-    const int nL0 = p.side[0].b_long[k + 1] - L0[0], nL1 = p.side[1].b_long[k + 1] - L0[1];
-    const float a = p.opt == GLOVE_OPT_ADAM ? p.alpha[step] : 0.0f;
-    for (int l = blockIdx.x; l < nL0 + nL1; l += gridDim.x) {
-        const int s = l >= nL0 ? 1 : 0;
-        const PlanSide &ps = p.side[s];
-        const int ll = L0[s] + (s ? l - nL0 : l);
-        const int g = ps.long_seg[ll], it0 = ps.long_item[ll];
-        const int slot = g - ps.b_seg[k];
-        const int len = ps.seg_start[g + 1] - ps.seg_start[g];
-        const int npieces = (len + kItemMax - 1) / kItemMax;
-        const float *part = p.partial[s] + (int64_t)(ps.item_part[it0] - ps.b_part[k]) * p.S;
-        // level 1: warp w sums pieces [w*chunk, (w+1)*chunk) in piece order; 128-bit loads, 4 pieces x all the float4s of
-        // a lane in flight at once
-        const int chunk = (npieces + NW - 1) / NW;
-        const int q0 = wid * chunk, q1 = min(q0 + chunk, npieces);
-        const int S4 = p.S >> 2;
-        float4 G4[4];
-#pragma unroll
-        for (int r = 0; r < 4; ++r) G4[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int q = q0; q < q1; q += 4) {
-            float4 t[4][4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const int f = lane + 32 * r;
-                    t[u][r] = (q + u < q1 && f < S4) ? ld4(part + (int64_t)(q + u) * p.S + 4 * f) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-#pragma unroll
-                for (int r = 0; r < 4; ++r) { G4[r].x += t[u][r].x; G4[r].y += t[u][r].y; G4[r].z += t[u][r].z; G4[r].w += t[u][r].w; }
-        }
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int f = lane + 32 * r;
-            if (f < S4) *reinterpret_cast<float4 *>(&sh_part[wid][4 * f]) = G4[r];
-        }
-        __syncthreads();
-        // level 2: one thread per column adds the NW warp sums in warp order and applies the optimizer
-        float *row = p.table[s] + (int64_t)ps.seg_id[g] * p.P * p.S;
-        const float *crow = p.snap[s] + (int64_t)slot * p.S;
-        const int bcol = bias_col(p.d, s), lcol = ls_col(p.d, s);
-        for (int c = tid; c < p.S; c += kFixThreads) {
-            float G = 0.0f;
-#pragma unroll
-            for (int w = 0; w < NW; ++w) G += sh_part[w][c];
-            if (p.mode == MODE_GRAD) { p.grad[s][(int64_t)slot * p.S + c] = G; continue; }
-            if (c < p.d || c == bcol) {
-                float x = crow[c];
-                if (p.opt == GLOVE_OPT_ADAM) {
-                    float m = row[p.S + c], v = row[2 * p.S + c];
-                    adam_update(x, m, v, G, a, p.b1, p.b2, p.eps);
-                    row[p.S + c] = m; row[2 * p.S + c] = v;
-                } else if (p.opt == GLOVE_OPT_ADAGRAD) {
-                    float acc = row[p.S + c];
-                    adagrad_update(x, acc, G, p.lr, p.eps);
-                    row[p.S + c] = acc;
-                } else {
-                    sgd_update(x, G, p.lr);
-                }
-                row[c] = x;
-            } else if (c == lcol) {
-                row[c] = __int_as_float(step + 1);
-            }
-        }
-        __syncthreads();
-    }
-    // per-CTA slice of the per-item loss terms, reduced in a fixed order
-    {
-        const int nI0 = p.side[0].b_item[k + 1] - p.side[0].b_item[k];
-        const int nI1 = p.side[1].b_item[k + 1] - p.side[1].b_item[k];
-        const int per0 = (nI0 + gridDim.x - 1) / gridDim.x, per1 = (nI1 + gridDim.x - 1) / gridDim.x;
-        double ld = 0.0, se = 0.0, rg = 0.0;
-        for (int i = blockIdx.x * per0 + tid; i < min((int)(blockIdx.x + 1) * per0, nI0); i += kFixThreads) {
-            const float4 v = p.item_out[0][i]; ld += v.x; se += v.y; rg += v.z;
-        }
-        for (int i = blockIdx.x * per1 + tid; i < min((int)(blockIdx.x + 1) * per1, nI1); i += kFixThreads) rg += p.item_out[1][i].z;
-        sh_red[0][tid] = ld; sh_red[1][tid] = se; sh_red[2][tid] = rg;
-        __syncthreads();
-        for (int o = kFixThreads / 2; o > 0; o >>= 1) {
-            if (tid < o) { sh_red[0][tid] += sh_red[0][tid + o]; sh_red[1][tid] += sh_red[1][tid + o]; sh_red[2][tid] += sh_red[2][tid + o]; }
-            __syncthreads();
-        }
-        if (tid == 0) { p.cta_out[3 * blockIdx.x] = sh_red[0][0]; p.cta_out[3 * blockIdx.x + 1] = sh_red[1][0]; p.cta_out[3 * blockIdx.x + 2] = sh_red[2][0]; }
-    }
-    // last CTA to arrive finishes the step: the per-CTA sums are added in CTA order (fixed tree)
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) is_last = (atomicAdd(&p.sc->ticket, 1) == (int)gridDim.x - 1);
-    __syncthreads();
-    if (is_last) {
-        __threadfence();
-        const bool in = tid < (int)gridDim.x;
-        sh_red[0][tid] = in ? p.cta_out[3 * tid] : 0.0;
-        sh_red[1][tid] = in ? p.cta_out[3 * tid + 1] : 0.0;
-        sh_red[2][tid] = in ? p.cta_out[3 * tid + 2] : 0.0;
-        __syncthreads();
-        for (int o = kFixThreads / 2; o > 0; o >>= 1) {
-            if (tid < o) { sh_red[0][tid] += sh_red[0][tid + o]; sh_red[1][tid] += sh_red[1][tid + o]; sh_red[2][tid] += sh_red[2][tid + o]; }
-            __syncthreads();
-        }
-        if (tid == 0) {
-            const float red[3] = {0.f, 0.f, 0.f};
-            (void)red;
-            finish_step(p, step, nullptr, sh_red[0][0], sh_red[1][0], sh_red[2][0]);
-        }
     }
 }
 
@@ -624,10 +600,10 @@ static int fill_params(const glove_step_args *a, StepParams &p, int mode) {
     p.hdr = pv.hdr;
     for (int s = 0; s < 2; ++s) {
         p.side[s] = pv.side[s];
-        p.snap[s] = w.snap[s]; p.partial[s] = w.partial[s]; p.item_out[s] = w.item_out[s];
+        p.snap[s] = w.snap[s]; p.partial[s] = w.partial[s]; p.long_cnt[s] = w.long_cnt[s]; p.chunk_cnt[s] = w.chunk_cnt[s];
         p.grad[s] = nullptr;
     }
-    p.cta_out = w.cta_out;
+    p.warp_out = w.warp_out;
     p.grad_scalars = nullptr;
     p.alpha = a->alpha; p.alpha_len = a->alpha_len;
     p.loss_out = a->loss_cap > 0 ? a->loss_out : nullptr; p.loss_cap = a->loss_cap > 0 ? a->loss_cap : 1;
@@ -669,9 +645,7 @@ static int launch_step(const StepParams &p, cudaStream_t stream, cudaEvent_t *ev
             if (dp) update_kernel<NV, GLOVE_HEAD_LOGISTIC, true><<<g_update, 128, 0, stream>>>(p);
             else update_kernel<NV, GLOVE_HEAD_LOGISTIC, false><<<g_update, 128, 0, stream>>>(p);
         }
-        if (ev) cudaEventRecord(ev[2], stream);
-        fix_kernel<<<kFixBlocks, kFixThreads, 0, stream>>>(p);
-        if (ev) cudaEventRecord(ev[3], stream);
+        if (ev) { cudaEventRecord(ev[2], stream); cudaEventRecord(ev[3], stream); }
     } else {
         apply_kernel<NV><<<g_apply, 128, 0, stream>>>(p);
         apply_finish_kernel<<<1, 32, 0, stream>>>(p, p.grad_scalars);

@@ -84,7 +84,7 @@ class GloveEngine:
         self.plan_first = [None, None]
         self._plan_counts = [None, None]
         self.prep_ws = torch.empty(lib.glove_prepare_workspace_bytes(self.K, self.B), **u8)
-        self.step_ws = torch.empty(lib.glove_step_workspace_bytes(self.B, self.d), **u8)
+        self.step_ws = torch.zeros(lib.glove_step_workspace_bytes(self.B, self.d), **u8)   # must start zeroed
         self.coo = None
         self.nnz = 0
         self.shuffle_key = 0
@@ -389,7 +389,7 @@ class GloveEngine:
         return self._plan_counts[which][step - self.plan_first[which]]
 
     def step_profiled(self):
-        """One TRAIN step with per-kernel device timings (ms): (stage, update, fix+finish).  Synchronises."""
+        """One TRAIN step with per-kernel device timings (ms): (stage, update, 0).  Synchronises."""
         self._join_side()
         which = self._plan_for(self.host_step)
         ms = (ctypes.c_float * 3)()
@@ -412,6 +412,45 @@ class GloveEngine:
                                          _ptr(host_losses), _stream()), "glove_train_steps_host")
         self.host_step += self.K
         self.plan_first = [None, None]
+
+    def train_chunk_from_host(self, host_row, host_col, host_a, host_b):
+        """End-to-end chunk for any world size (data-parallel aware): K*B explicit triples from pinned HOST tensors are
+        copied to a device staging COO, planned in file order and trained for K steps; returns the K losses (numpy).
+        At world size 1 prefer train_steps_host (same thing behind one C-ABI call)."""
+        n = self.K * self.B
+        assert host_row.numel() == n
+        self._join_side()
+        if getattr(self, "_stage_coo", None) is None:
+            i32 = dict(dtype=torch.int32, device=self.device)
+            f32 = dict(dtype=torch.float32, device=self.device)
+            self._stage_coo = (torch.empty(n, **i32), torch.empty(n, **i32), torch.empty(n, **f32), torch.empty(n, **f32))
+            self._stage_idx = torch.arange(n, dtype=torch.int64, device=self.device)
+        for dst, src in zip(self._stage_coo, (host_row, host_col, host_a, host_b)):
+            dst.copy_(src, non_blocking=True)
+        first = self.host_step
+        which = 0
+        row, col, ca, cb = self._stage_coo
+        check(lib.glove_prepare_batches(_ptr(self.plans[which]), _ptr(self.prep_ws), self.prep_ws.numel(), _ptr(row),
+                                        _ptr(col), _ptr(ca), _ptr(cb), n, _ptr(self._stage_idx), 0, 0, first, self.K,
+                                        self.B, self.V, _stream()), "glove_prepare_batches")
+        self._plan_counts[which] = None
+        self.plan_first = [None, None]
+        a = self._args[which]
+        for _ in range(self.K):
+            if self.dp_world > 1:
+                import torch.distributed as dist
+                if self.grad is None:
+                    f32 = dict(dtype=torch.float32, device=self.device)
+                    self.grad = (torch.zeros(self.B * self.S, **f32), torch.zeros(self.B * self.S, **f32), torch.zeros(4, **f32))
+                gr, gc, gs = self.grad
+                check(lib.glove_grad_step(ctypes.byref(a), _ptr(gr), _ptr(gc), _ptr(gs), _stream()), "glove_grad_step")
+                dist.all_reduce(gr); dist.all_reduce(gc); dist.all_reduce(gs)
+                check(lib.glove_apply_step(ctypes.byref(a), _ptr(gr), _ptr(gc), _ptr(gs), _stream()), "glove_apply_step")
+            else:
+                check(lib.glove_train_step(ctypes.byref(a), _stream()), "glove_train_step")
+            self.host_step += 1
+        idx = torch.arange(first, first + self.K, device=self.device) % self.loss_cap
+        return self.loss_out[idx].cpu().numpy()      # D2H of the K losses (synchronises)
 
     def batch_counts(self, step: int):
         which = self._plan_for(step)

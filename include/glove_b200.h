@@ -109,7 +109,7 @@ typedef struct glove_step_args {
     float *row_table, *col_table; /* packed tables */
     glove_scalars *scalars;       /* device */
     const void *plan;             /* from glove_prepare_batches; the batch used is (scalars->step - plan.first_step) */
-    void *workspace;              /* glove_step_workspace_bytes(B, d) */
+    void *workspace;              /* glove_step_workspace_bytes(B, d); ZERO-FILLED before its first use */
     size_t workspace_bytes;
     const float *alpha;           /* device fp32 [alpha_len]: Adam step size per 0-based step (lr*sqrt(1-b2^t)/(1-b1^t)) */
     int32_t alpha_len;
@@ -135,7 +135,7 @@ int glove_train_step(const glove_step_args *args, void *stream);
  * for the first batch of a plan and for other optimizers / modes.  Results are bit-identical with or without it. */
 int glove_catchup_step(const glove_step_args *args, int32_t step_index, void *stream);
 /* same step, with CUDA events recorded around its three kernels on `stream`; synchronises and returns their device
- * durations in milliseconds: ms3 = {stage, update, fix+finish}.  Measurement aid for bench.py (roofline). */
+ * durations in milliseconds: ms3 = {stage, update (incl. split-segment combine and step finish), 0}.  Measurement aid for bench.py (roofline). */
 int glove_train_step_profiled(const glove_step_args *args, void *stream, float *ms3);
 /* data-parallel split of the same step: grad_step writes this rank's partial gradient sums for every global segment
  * into grad_rows / grad_cols ([n_segments][S], dense in slot order) and {sum w*l.., sum e} into grad_scalars[4];
