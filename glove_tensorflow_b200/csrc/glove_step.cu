@@ -17,6 +17,8 @@
 //                  step counter.
 //
 // Everything is deterministic: no floating-point atomics, fixed summation order given (B, kItemMax, grid size).
+#include <stdlib.h>
+
 #include "glove_common.cuh"
 
 namespace glove {
@@ -689,7 +691,16 @@ int glove_catchup_step(const glove_step_args *args, int32_t step_index, void *st
     if (rc != GLOVE_OK) return rc;
     if (p.opt != GLOVE_OPT_ADAM || p.adam_mode != GLOVE_ADAM_REPLAY) return GLOVE_OK;
     static int grid = 0;
-    if (!grid) grid = occupancy_grid(stage_kernel<true>, 256);
+    if (!grid) {
+        grid = occupancy_grid(stage_kernel<true>, 256);
+        // tuning knob: resident catch-up CTAs per SM (the catch-up shares the SMs with the step in flight)
+        if (const char *e = getenv("GLOVE_CATCHUP_CTAS_PER_SM")) {
+            int dev = 0, sms = kNumSMs;
+            if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            const int n = atoi(e);
+            if (n > 0 && n * sms < grid) grid = n * sms;
+        }
+    }
     // leave room for the step in flight: the catch-up is arithmetic-bound and is meant to fill its memory stalls
     stage_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(p, step_index);
     commit_ls_kernel<<<kNumSMs, 256, 0, (cudaStream_t)stream>>>(p, step_index);
