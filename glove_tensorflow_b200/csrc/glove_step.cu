@@ -164,6 +164,42 @@ __global__ void __launch_bounds__(256) stage_kernel(const StepParams p, int step
     const int S4 = p.S >> 2;
     const bool replay = (p.opt == GLOVE_OPT_ADAM && p.adam_mode == GLOVE_ADAM_REPLAY);
     const int total = (U0 + U1) * S4;
+
+    // ---- pass 1 (stage only): rows that are current are a pure 128-bit copy; 4 chunks per warp in flight
+    if (!CATCHUP) {
+        constexpr int UN = 4;
+        for (int base0 = warp * 32 * UN; base0 < total; base0 += nwarps * 32 * UN) {
+            float4 x[UN];
+            int ls[UN], dsti[UN], fsel[UN];
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                const int idx = base0 + u * 32 + lane;
+                dsti[u] = -1;
+                if (idx < total) {
+                    const int w = idx / S4, f = idx - w * S4;
+                    const int s = w >= U0 ? 1 : 0;
+                    const int slot = s ? w - U0 : w;
+                    const float *row = p.table[s] + (int64_t)p.side[s].seg_id[seg0[s] + slot] * p.P * p.S;
+                    const int lcol = ls_col(p.d, s);
+                    x[u] = ld4(row + 4 * f);
+                    ls[u] = __float_as_int(row[lcol]);
+                    dsti[u] = (s * p.B + slot) * S4 + f;            // float4 index into snap[0] (snap[1] follows at B*S)
+                    fsel[u] = (lcol >> 2) == f ? (lcol & 3) : -1;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                if (dsti[u] < 0) continue;
+                if (replay && ls[u] > 0 && ls[u] < step) continue;  // needs replay: pass 2
+                if (fsel[u] >= 0) f4c(x[u], fsel[u]) = 1.0f;        // 1.0 in the other side's bias column
+                const int sidx = dsti[u] / (p.B * S4);
+                st4(p.snap[sidx] + (int64_t)(dsti[u] - sidx * p.B * S4) * 4, x[u]);
+            }
+        }
+        if (!replay) return;
+    }
+
+    // ---- pass 2: rows with missed idle Adam steps
     for (int base = warp * 32; base < total; base += nwarps * 32) {
         const int idx = base + lane;
         const bool active = idx < total;
@@ -173,52 +209,59 @@ __global__ void __launch_bounds__(256) stage_kernel(const StepParams p, int step
         const int id = p.side[s].seg_id[seg0[s] + slot];
         const float *row = p.table[s] + (int64_t)id * p.P * p.S;
         const int lcol = ls_col(p.d, s);
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-        int ls = 0;
-        if (active) { x = ld4(row + 4 * f); ls = __float_as_int(row[lcol]); }
+        int ls = active ? __float_as_int(row[lcol]) : 0;
         if (CATCHUP && active && p.side[s].seg_prev[seg0[s] + slot]) ls = 0;   // may be in flight: leave it to the stage
-        if (replay) {
-            const bool need = active && ls > 0 && ls < step;
-            float4 m = make_float4(0.f, 0.f, 0.f, 0.f), v = m;
-            if (need) { m = ld4(row + p.S + 4 * f); v = ld4(row + 2 * p.S + 4 * f); }
-            float2 xa = make_float2(x.x, x.y), xb = make_float2(x.z, x.w);
-            float2 ma = make_float2(m.x, m.y), mb = make_float2(m.z, m.w);
-            float2 va = make_float2(v.x, v.y), vb = make_float2(v.z, v.w);
-            int t = need ? ls : step;
-            bool moving = need;
-            // |increment| shrinks monotonically (x0.9 per step from m, at most x1.012 from alpha and sqrt(v)): once an
-            // element stops moving it never moves again; from then on only the m, v decays remain (2 packed multiplies).
-            while (__any_sync(0xffffffffu, t < step)) {
-                if (t < step) {
-                    if (moving) {
-                        const float na = -__ldg(p.alpha + t);
-                        const float2 oa = xa, ob = xb;
+        const bool need = active && ls > 0 && ls < step;
+        if (!__any_sync(0xffffffffu, need)) continue;
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f), m = x, v = x;
+        if (need) { x = ld4(row + 4 * f); m = ld4(row + p.S + 4 * f); v = ld4(row + 2 * p.S + 4 * f); }
+        float2 xa = make_float2(x.x, x.y), xb = make_float2(x.z, x.w);
+        float2 ma = make_float2(m.x, m.y), mb = make_float2(m.z, m.w);
+        float2 va = make_float2(v.x, v.y), vb = make_float2(v.z, v.w);
+        const int gap = need ? step - ls : 0;
+        const int trips = __reduce_max_sync(0xffffffffu, gap);
+        const float *al = p.alpha + (need ? ls : 0);
+        bool moving = need;
+        // |increment| shrinks monotonically (x0.9 per step from m, at most x1.012 from alpha and sqrt(v)): once an element
+        // has not moved for a whole block of 4 steps it never moves again; from then on only the m, v decays remain
+        // (2 packed multiplies per pair).  The test is made once per block of 4 steps.
+#pragma unroll 1
+        for (int i = 0; i < trips; i += 4) {
+            if (moving) {
+                const float2 oa = xa, ob = xb;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (i + j < gap) {
+                        const float na = -__ldg(al + i + j);
                         adam_idle_step2(xa, ma, va, na, p.b1, p.b2, p.eps);
                         adam_idle_step2(xb, mb, vb, na, p.b1, p.b2, p.eps);
-                        moving = (xa.x != oa.x) | (xa.y != oa.y) | (xb.x != ob.x) | (xb.y != ob.y);
-                    } else {
+                    }
+                }
+                moving = (xa.x != oa.x) | (xa.y != oa.y) | (xb.x != ob.x) | (xb.y != ob.y);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (i + j < gap) {
                         ma = __fmul2_rn(ma, f2(p.b1)); mb = __fmul2_rn(mb, f2(p.b1));
                         va = __fmul2_rn(va, f2(p.b2)); vb = __fmul2_rn(vb, f2(p.b2));
                     }
-                    ++t;
                 }
             }
-            if (need) {
-                // the row is current through step-1 now: publish the decayed moments so that the update kernel reads
-                // them as-is (the x plane of the table is rewritten by the update in this same step)
-                x = make_float4(xa.x, xa.y, xb.x, xb.y);
-                st4(const_cast<float *>(row) + p.S + 4 * f, make_float4(ma.x, ma.y, mb.x, mb.y));
-                st4(const_cast<float *>(row) + 2 * p.S + 4 * f, make_float4(va.x, va.y, vb.x, vb.y));
+        }
+        if (need) {
+            // the row is current through step-1 now: publish the decayed moments so that the update kernel reads them
+            // as-is (the x plane of the table is rewritten by the update in this same step)
+            x = make_float4(xa.x, xa.y, xb.x, xb.y);
+            st4(const_cast<float *>(row) + p.S + 4 * f, make_float4(ma.x, ma.y, mb.x, mb.y));
+            st4(const_cast<float *>(row) + 2 * p.S + 4 * f, make_float4(va.x, va.y, vb.x, vb.y));
+            if (CATCHUP) {
                 // catch-up: x goes back in place too; last_step is NOT touched here (other threads of the row may still
                 // have to read it) -- commit_ls_kernel sets it once this kernel has finished
-                if (CATCHUP) st4(const_cast<float *>(row) + 4 * f, x);
+                st4(const_cast<float *>(row) + 4 * f, x);
+            } else {
+                if ((lcol >> 2) == f) f4c(x, lcol & 3) = 1.0f;
+                st4(p.snap[s] + (int64_t)slot * p.S + 4 * f, x);
             }
-        }
-        if (CATCHUP) continue;
-        if (active) {
-            // snapshot: 1.0 in the other side's bias column (= this side's last_step column)
-            if ((lcol >> 2) == f) f4c(x, lcol & 3) = 1.0f;
-            st4(p.snap[s] + (int64_t)slot * p.S + 4 * f, x);
         }
     }
 }
