@@ -287,8 +287,11 @@ def main():
         peak = float(peaks.get("hbm_gbs", 6650.0))
         step_ms = ms / args.steps
         achieved = bytes_alg / (step_ms * 1e-3) / 1e9
+        # ncu --set full (profiles/r01_step_kernels_ncu_full.txt): dram read+write per launch of stage_kernel<false> (91 MB) +
+        # update_kernel (355 MB), cold caches, default workload only
+        traffic = 446e6 if (args.workload == "wiki6b" and B_local == 65_536) else None
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6650",
+                    "traffic": traffic, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6650",
                     "kernel": "whole step = stage_kernel + update_kernel (algorithmic bytes are per step)",
                     "algorithmic_bytes_per_step": bytes_alg, "U_row": U_r, "U_col": U_c,
                     "rho": (U_r + U_c) / (2.0 * B), "frac_of_nominal_8000": achieved / 8000.0,
