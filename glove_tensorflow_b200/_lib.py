@@ -29,7 +29,7 @@ class StepArgs(ctypes.Structure):
                 ("loss_out", c_void), ("loss_cap", c_i32), ("plan_K", c_i32), ("V", c_i64), ("d", c_i32), ("B", c_i32),
                 ("head", c_i32), ("optimizer", c_i32), ("adam_mode", c_i32), ("learning_rate", c_f32),
                 ("l2_reg", c_f32), ("reg_scale", c_f32), ("neg_factor", c_f32), ("beta1", c_f32), ("beta2", c_f32),
-                ("epsilon", c_f32), ("dp_rank", c_i32), ("dp_world", c_i32)]
+                ("epsilon", c_f32), ("dp_rank", c_i32), ("dp_world", c_i32), ("n_shards", c_i32), ("shard", c_i32)]
 
 
 # name -> (restype, argtypes); every symbol include/glove_b200.h declares
@@ -48,6 +48,9 @@ SIGNATURES = {
     "glove_prepare_workspace_bytes": (c_size, [c_i32, c_i32]),
     "glove_prepare_batches": (ctypes.c_int, [c_void, c_void, c_size, c_void, c_void, c_void, c_void, c_i64, c_void,
                                              c_i64, c_u32, c_i32, c_i32, c_i32, c_i32, c_void]),
+    "glove_prepare_batches_sharded": (ctypes.c_int, [c_void, c_void, c_size, c_void, c_void, c_void, c_void, c_i64, c_void,
+                                                     c_i64, c_u32, c_i32, c_i32, c_i32, c_i32, c_i32, c_void]),
+    "glove_plan_shard_info": (ctypes.c_int, [c_void, c_i32, c_i32, c_i32, ctypes.POINTER(c_i32), c_void]),
     "glove_plan_batch_counts": (ctypes.c_int, [c_void, c_i32, c_i32, c_i32, ctypes.POINTER(c_i32), c_void]),
     "glove_step_workspace_bytes": (c_size, [c_i32, c_i32]),
     "glove_train_step": (ctypes.c_int, [ctypes.POINTER(StepArgs), c_void]),
@@ -55,6 +58,10 @@ SIGNATURES = {
     "glove_train_step_profiled": (ctypes.c_int, [ctypes.POINTER(StepArgs), c_void, ctypes.POINTER(c_f32)]),
     "glove_grad_step": (ctypes.c_int, [ctypes.POINTER(StepArgs), c_void, c_void, c_void, c_void]),
     "glove_apply_step": (ctypes.c_int, [ctypes.POINTER(StepArgs), c_void, c_void, c_void, c_void]),
+    "glove_shard_stage_step": (ctypes.c_int, [ctypes.POINTER(StepArgs), c_void]),
+    "glove_shard_grad_step": (ctypes.c_int, [ctypes.POINTER(StepArgs), c_void, c_void, c_void, c_void]),
+    "glove_step_snapshot_rows": (c_i64, [c_i32]),
+    "glove_step_snapshot_offset": (c_size, [c_i32, c_i32, c_i32]),
     "glove_flush_lazy_state": (ctypes.c_int, [c_void, c_i64, c_i32, c_i32, c_i32, c_void, c_i32, c_i32, c_f32, c_f32, c_f32,
                                               c_void]),
     "glove_eval_workspace_bytes": (c_size, [c_i64, c_i32]),

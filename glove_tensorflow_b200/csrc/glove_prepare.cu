@@ -72,7 +72,7 @@ __global__ void shuffle_indices_kernel(uint32_t key, int64_t nnz, int64_t first,
 __global__ void gather_kernel(const int32_t *__restrict__ row, const int32_t *__restrict__ col,
                               const float *__restrict__ colA, const float *__restrict__ colB, int64_t nnz,
                               const int64_t *__restrict__ sample_idx, int64_t first_sample, uint32_t key, int h,
-                              int32_t N, int32_t B, int vbits, PrepWs w) {
+                              int32_t N, int32_t B, int vbits, int32_t n_shards, int32_t v_loc, PrepWs w) {
     for (int32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < N; p += gridDim.x * blockDim.x) {
         int64_t src;
         if (sample_idx) {
@@ -82,8 +82,13 @@ __global__ void gather_kernel(const int32_t *__restrict__ row, const int32_t *__
             src = (int64_t)feistel_permute((uint64_t)(n % nnz), (uint64_t)nnz, key + (uint32_t)(n / nnz), h);
         }
         const uint32_t kb = (uint32_t)(p / B) << vbits;
-        w.side[0].keys_in[p] = kb | (uint32_t)row[src];
-        w.side[1].keys_in[p] = kb | (uint32_t)col[src];
+        uint32_t i = (uint32_t)row[src], j = (uint32_t)col[src];
+        if (n_shards > 1) {  // owner-major id: rows of one owner are contiguous in every sorted list
+            i = (i % n_shards) * v_loc + i / n_shards;
+            j = (j % n_shards) * v_loc + j / n_shards;
+        }
+        w.side[0].keys_in[p] = kb | i;
+        w.side[1].keys_in[p] = kb | j;
         w.vals_in[p] = (uint32_t)p;
         w.A[p] = colA[src];
         w.Bv[p] = colB[src];
@@ -156,10 +161,34 @@ __global__ void items_kernel(int32_t N, int32_t B, int32_t K, PrepSide ps, PlanS
     }
 }
 
-__global__ void slots_kernel(int32_t N, int32_t B, PrepSide ps, PlanSide out) {
+// per batch: first slot owned by each shard (binary search of owner * v_loc in the sorted ids) and the padded block size
+__global__ void owners_kernel(int32_t K, int32_t n_shards, int32_t v_loc, PlanSide out) {
+    for (int32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < K * (kMaxShards + 1); t += gridDim.x * blockDim.x) {
+        const int32_t k = t / (kMaxShards + 1), r = t % (kMaxShards + 1);
+        int32_t lo = out.b_seg[k], hi = out.b_seg[k + 1];
+        const int32_t end = hi;
+        if (r >= n_shards) { out.b_own[t] = end - out.b_seg[k]; continue; }
+        const int32_t key = r * v_loc;
+        while (lo < hi) {
+            const int32_t mid = (lo + hi) >> 1;
+            if (out.seg_id[mid] < key) lo = mid + 1; else hi = mid;
+        }
+        out.b_own[t] = lo - out.b_seg[k];
+    }
+}
+__global__ void upad_kernel(int32_t K, int32_t n_shards, PlanSide out) {
+    for (int32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < K; k += gridDim.x * blockDim.x) {
+        int32_t m = 0;
+        for (int r = 0; r < n_shards; ++r)
+            m = max(m, out.b_own[k * (kMaxShards + 1) + r + 1] - out.b_own[k * (kMaxShards + 1) + r]);
+        out.b_upad[k] = m;
+    }
+}
+
+__global__ void slots_kernel(int32_t N, int32_t B, int32_t n_shards, int32_t v_loc, PrepSide ps, PlanSide out) {
     for (int32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < N; q += gridDim.x * blockDim.x) {
         const int32_t g = ps.e_seg[q] + ps.f_seg[q] - 1;
-        ps.slot_of_p[ps.vals_out[q]] = g - out.b_seg[q / B];
+        ps.slot_of_p[ps.vals_out[q]] = plan_pos(out, q / B, g, n_shards, v_loc);
     }
 }
 
@@ -191,7 +220,7 @@ __global__ void segprev_kernel(int32_t N, int32_t B, PrepSide ps, PlanSide out) 
     }
 }
 
-__global__ void itemrec_kernel(int32_t B, const int32_t *__restrict__ n_items, PlanSide out) {
+__global__ void itemrec_kernel(int32_t B, int32_t n_shards, int32_t v_loc, const int32_t *__restrict__ n_items, PlanSide out) {
     const int32_t NI = *n_items;
     for (int32_t it = blockIdx.x * blockDim.x + threadIdx.x; it < NI; it += gridDim.x * blockDim.x) {
         const int32_t g = out.item_seg[it], start = out.item_start[it];
@@ -199,27 +228,29 @@ __global__ void itemrec_kernel(int32_t B, const int32_t *__restrict__ n_items, P
         const int32_t seg_end = out.seg_start[g + 1], seg_len = seg_end - out.seg_start[g];
         const int32_t n = min(start + kItemMax, seg_end) - start;
         const int32_t part = seg_len > kItemMax ? out.item_part[it] - out.b_part[k] + 1 : 0;
-        out.item_rec[it] = make_int4(part ? out.seg_long[g] - out.b_long[k] : out.seg_id[g], g - out.b_seg[k], start,
-                                     n | (part << 8));
+        out.item_rec[it] = make_int4(part ? out.seg_long[g] - out.b_long[k] : out.seg_id[g],
+                                     plan_pos(out, k, g, n_shards, v_loc), start, n | (part << 8));
     }
 }
 
-__global__ void longrec_kernel(int32_t B, const int32_t *__restrict__ n_long, PlanSide out) {
+__global__ void longrec_kernel(int32_t B, int32_t n_shards, int32_t v_loc, const int32_t *__restrict__ n_long, PlanSide out) {
     const int32_t NL = *n_long;
     for (int32_t l = blockIdx.x * blockDim.x + threadIdx.x; l < NL; l += gridDim.x * blockDim.x) {
         const int32_t g = out.long_seg[l], it0 = out.long_item[l];
         const int32_t k = out.seg_start[g] / B;
         const int32_t len = out.seg_start[g + 1] - out.seg_start[g];
-        out.long_rec[l] = make_int4(out.seg_id[g], g - out.b_seg[k], out.item_part[it0] - out.b_part[k],
+        out.long_rec[l] = make_int4(out.seg_id[g], plan_pos(out, k, g, n_shards, v_loc), out.item_part[it0] - out.b_part[k],
                                     (len + kItemMax - 1) / kItemMax);
     }
 }
 
-__global__ void header_kernel(PlanHeader *hdr, int32_t K, int32_t B, int32_t first_step) {
+__global__ void header_kernel(PlanHeader *hdr, int32_t K, int32_t B, int32_t first_step, int32_t n_shards, int32_t v_loc) {
     hdr->magic = kPlanMagic;
     hdr->K = K;
     hdr->B = B;
     hdr->first_step = first_step;
+    hdr->n_shards = n_shards;
+    hdr->v_loc = v_loc;
 }
 
 }  // namespace glove
@@ -252,13 +283,24 @@ int glove_prepare_batches(void *plan, void *workspace, size_t workspace_bytes, c
                           const float *colA, const float *colB, int64_t nnz, const int64_t *sample_idx,
                           int64_t first_sample, uint32_t shuffle_key, int32_t first_step, int32_t K, int32_t B,
                           int32_t V, void *stream_) {
+    return glove_prepare_batches_sharded(plan, workspace, workspace_bytes, row, col, colA, colB, nnz, sample_idx,
+                                         first_sample, shuffle_key, first_step, K, B, V, 1, stream_);
+}
+
+int glove_prepare_batches_sharded(void *plan, void *workspace, size_t workspace_bytes, const int32_t *row,
+                                  const int32_t *col, const float *colA, const float *colB, int64_t nnz,
+                                  const int64_t *sample_idx, int64_t first_sample, uint32_t shuffle_key,
+                                  int32_t first_step, int32_t K, int32_t B, int32_t V, int32_t n_shards, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
+    GLOVE_REQUIRE(n_shards >= 1 && n_shards <= kMaxShards, "glove_prepare_batches: n_shards %d not in [1, %d]", n_shards, kMaxShards);
+    const int32_t v_loc = (V + n_shards - 1) / n_shards;
+    const int64_t V_ids = (int64_t)v_loc * n_shards;  // range of the (remapped) ids
     GLOVE_REQUIRE(plan && workspace && row && col && colA && colB, "glove_prepare_batches: null pointer");
     GLOVE_REQUIRE(K > 0 && B > 0 && V > 0 && nnz > 0 && first_sample >= 0, "glove_prepare_batches: bad sizes");
     const int64_t N64 = (int64_t)K * B;
     GLOVE_REQUIRE(N64 < (1ll << 30), "glove_prepare_batches: K*B = %lld too large (max 2^30)", (long long)N64);
     int vbits = 1;
-    while ((1ll << vbits) < V) ++vbits;
+    while ((1ll << vbits) < V_ids) ++vbits;
     int kbits = 0;
     while ((1ll << kbits) < K) ++kbits;
     GLOVE_REQUIRE(vbits + kbits <= 32, "glove_prepare_batches: K=%d batches x V=%d ids do not fit 32-bit sort keys", K, V);
@@ -271,9 +313,9 @@ int glove_prepare_batches(void *plan, void *workspace, size_t workspace_bytes, c
     int blocks = (N + threads - 1) / threads;
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
 
-    header_kernel<<<1, 1, 0, stream>>>(pv.hdr, K, B, first_step);
+    header_kernel<<<1, 1, 0, stream>>>(pv.hdr, K, B, first_step, n_shards, v_loc);
     gather_kernel<<<blocks, threads, 0, stream>>>(row, col, colA, colB, nnz, sample_idx, first_sample, shuffle_key,
-                                                  feistel_half_bits((uint64_t)nnz), N, B, vbits, w);
+                                                  feistel_half_bits((uint64_t)nnz), N, B, vbits, n_shards, v_loc, w);
     GLOVE_CHECK_LAUNCH();
     const uint32_t idmask = (uint32_t)((1ull << vbits) - 1);
     for (int s = 0; s < 2; ++s) {
@@ -293,15 +335,30 @@ int glove_prepare_batches(void *plan, void *workspace, size_t workspace_bytes, c
         tb = w.cub_bytes;
         GLOVE_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(w.cub_temp, tb, ps.f_part, ps.e_part, N, stream));
         items_kernel<<<blocks, threads, 0, stream>>>(N, B, K, ps, pv.side[s], pv.hdr, s);
-        slots_kernel<<<blocks, threads, 0, stream>>>(N, B, ps, pv.side[s]);
-        itemrec_kernel<<<blocks, threads, 0, stream>>>(B, &pv.hdr->n_item[s], pv.side[s]);
-        longrec_kernel<<<blocks, threads, 0, stream>>>(B, &pv.hdr->n_long[s], pv.side[s]);
+        owners_kernel<<<(K * (kMaxShards + 1) + 255) / 256, 256, 0, stream>>>(K, n_shards, v_loc, pv.side[s]);
+        upad_kernel<<<(K + 255) / 256, 256, 0, stream>>>(K, n_shards, pv.side[s]);
+        slots_kernel<<<blocks, threads, 0, stream>>>(N, B, n_shards, v_loc, ps, pv.side[s]);
+        itemrec_kernel<<<blocks, threads, 0, stream>>>(B, n_shards, v_loc, &pv.hdr->n_item[s], pv.side[s]);
+        longrec_kernel<<<blocks, threads, 0, stream>>>(B, n_shards, v_loc, &pv.hdr->n_long[s], pv.side[s]);
         segprev_kernel<<<blocks, threads, 0, stream>>>(N, B, ps, pv.side[s]);
         GLOVE_CHECK_LAUNCH();
     }
     for (int s = 0; s < 2; ++s)
         fill_kernel<<<blocks, threads, 0, stream>>>(N, B, w.side[s], w.side[1 - s].slot_of_p, w.A, w.Bv, pv.side[s]);
     GLOVE_CHECK_LAUNCH();
+    return GLOVE_OK;
+}
+
+int glove_plan_shard_info(const void *plan, int32_t K, int32_t B, int32_t k, int32_t *out20, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    GLOVE_REQUIRE(plan && out20 && k >= 0 && k < K, "glove_plan_shard_info: bad arguments");
+    PlanView pv = plan_view(const_cast<void *>(plan), K, B);
+    for (int s = 0; s < 2; ++s) {
+        GLOVE_CHECK_CUDA(cudaMemcpyAsync(out20 + 10 * s, pv.side[s].b_own + (size_t)k * (kMaxShards + 1),
+                                         4 * (kMaxShards + 1), cudaMemcpyDeviceToHost, stream));
+        GLOVE_CHECK_CUDA(cudaMemcpyAsync(out20 + 10 * s + 9, pv.side[s].b_upad + k, 4, cudaMemcpyDeviceToHost, stream));
+    }
+    GLOVE_CHECK_CUDA(cudaStreamSynchronize(stream));
     return GLOVE_OK;
 }
 

@@ -46,6 +46,8 @@ struct StepParams {
     int32_t head, opt, adam_mode, mode;
     float lr, l2, rs, nf, b1, b2, eps;
     int32_t dp_rank, dp_world, dp_block;
+    int32_t n_shards, shard, v_loc;   // row-sharded tables (n_shards = 1: everything is owned by shard 0)
+    int32_t run_stage, run_update;
 };
 
 struct StepWs {
@@ -56,6 +58,7 @@ struct StepWs {
     double *warp_out;
     size_t bytes;
 };
+static inline int64_t snapshot_rows(int32_t B) { return (int64_t)B + B / 4 + 64; }  // room for padded shard blocks
 static inline int64_t max_items_per_batch(int32_t B) { return (int64_t)B + B / kItemMax + 2; }
 static inline int64_t max_parts_per_batch(int32_t B) { return 2 * (int64_t)B / kItemMax + 2; }
 static StepWs step_ws_view(void *base, int32_t B, int32_t d) {
@@ -64,7 +67,7 @@ static StepWs step_ws_view(void *base, int32_t B, int32_t d) {
     size_t off = 0;
     auto take = [&](size_t bytes) { char *r = p ? p + off : nullptr; off += align_up(bytes); return r; };
     const int32_t S = table_stride(d);
-    for (int s = 0; s < 2; ++s) w.snap[s] = (float *)take(sizeof(float) * (size_t)B * S);
+    for (int s = 0; s < 2; ++s) w.snap[s] = (float *)take(sizeof(float) * (size_t)snapshot_rows(B) * S);
     for (int s = 0; s < 2; ++s) w.partial[s] = (float *)take(sizeof(float) * (size_t)max_parts_per_batch(B) * S);
     for (int s = 0; s < 2; ++s) w.long_cnt[s] = (int32_t *)take(sizeof(int32_t) * (size_t)(B / kItemMax + 2));
     for (int s = 0; s < 2; ++s) w.chunk_cnt[s] = (int32_t *)take(sizeof(int32_t) * (size_t)max_parts_per_batch(B));
@@ -160,7 +163,12 @@ __global__ void __launch_bounds__(256) stage_kernel(const StepParams p, int step
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     const int seg0[2] = {p.side[0].b_seg[k], p.side[1].b_seg[k]};
-    const int U0 = p.side[0].b_seg[k + 1] - seg0[0], U1 = p.side[1].b_seg[k + 1] - seg0[1];
+    // this shard's block of slots on each side (everything when the tables are not sharded)
+    const int own0[2] = {p.side[0].b_own[k * (kMaxShards + 1) + p.shard], p.side[1].b_own[k * (kMaxShards + 1) + p.shard]};
+    const int U0 = p.side[0].b_own[k * (kMaxShards + 1) + p.shard + 1] - own0[0];
+    const int U1 = p.side[1].b_own[k * (kMaxShards + 1) + p.shard + 1] - own0[1];
+    const int pos0[2] = {p.shard * p.side[0].b_upad[k], p.shard * p.side[1].b_upad[k]};  // first snapshot row of the block
+    const int64_t id0 = (int64_t)p.shard * p.v_loc;                                       // first (remapped) id owned
     const int S4 = p.S >> 2;
     const bool replay = (p.opt == GLOVE_OPT_ADAM && p.adam_mode == GLOVE_ADAM_REPLAY);
     const int total = (U0 + U1) * S4;
@@ -178,12 +186,12 @@ __global__ void __launch_bounds__(256) stage_kernel(const StepParams p, int step
                 if (idx < total) {
                     const int w = idx / S4, f = idx - w * S4;
                     const int s = w >= U0 ? 1 : 0;
-                    const int slot = s ? w - U0 : w;
-                    const float *row = p.table[s] + (int64_t)p.side[s].seg_id[seg0[s] + slot] * p.P * p.S;
+                    const int j = s ? w - U0 : w;
+                    const float *row = p.table[s] + ((int64_t)p.side[s].seg_id[seg0[s] + own0[s] + j] - id0) * p.P * p.S;
                     const int lcol = ls_col(p.d, s);
                     x[u] = ld4(row + 4 * f);
                     ls[u] = __float_as_int(row[lcol]);
-                    dsti[u] = (s * p.B + slot) * S4 + f;            // float4 index into snap[0] (snap[1] follows at B*S)
+                    dsti[u] = (s << 30) | ((pos0[s] + j) * S4 + f);  // side in bit 30, float4 index into snap[side]
                     fsel[u] = (lcol >> 2) == f ? (lcol & 3) : -1;
                 }
             }
@@ -192,8 +200,7 @@ __global__ void __launch_bounds__(256) stage_kernel(const StepParams p, int step
                 if (dsti[u] < 0) continue;
                 if (replay && ls[u] > 0 && ls[u] < step) continue;  // needs replay: pass 2
                 if (fsel[u] >= 0) f4c(x[u], fsel[u]) = 1.0f;        // 1.0 in the other side's bias column
-                const int sidx = dsti[u] / (p.B * S4);
-                st4(p.snap[sidx] + (int64_t)(dsti[u] - sidx * p.B * S4) * 4, x[u]);
+                st4(p.snap[dsti[u] >> 30] + (int64_t)(dsti[u] & 0x3fffffff) * 4, x[u]);
             }
         }
         if (!replay) return;
@@ -205,12 +212,12 @@ __global__ void __launch_bounds__(256) stage_kernel(const StepParams p, int step
         const bool active = idx < total;
         const int w = active ? idx / S4 : 0, f = active ? idx - w * S4 : 0;
         const int s = w >= U0 ? 1 : 0;
-        const int slot = s ? w - U0 : w;
-        const int id = p.side[s].seg_id[seg0[s] + slot];
-        const float *row = p.table[s] + (int64_t)id * p.P * p.S;
+        const int j = s ? w - U0 : w;
+        const int g = seg0[s] + own0[s] + j;
+        const float *row = p.table[s] + ((int64_t)(active ? p.side[s].seg_id[g] : id0) - id0) * p.P * p.S;
         const int lcol = ls_col(p.d, s);
         int ls = active ? __float_as_int(row[lcol]) : 0;
-        if (CATCHUP && active && p.side[s].seg_prev[seg0[s] + slot]) ls = 0;   // may be in flight: leave it to the stage
+        if (CATCHUP && active && p.side[s].seg_prev[g]) ls = 0;   // may be in flight: leave it to the stage
         const bool need = active && ls > 0 && ls < step;
         if (!__any_sync(0xffffffffu, need)) continue;
         float4 x = make_float4(0.f, 0.f, 0.f, 0.f), m = x, v = x;
@@ -260,7 +267,7 @@ __global__ void __launch_bounds__(256) stage_kernel(const StepParams p, int step
                 st4(const_cast<float *>(row) + 4 * f, x);
             } else {
                 if ((lcol >> 2) == f) f4c(x, lcol & 3) = 1.0f;
-                st4(p.snap[s] + (int64_t)slot * p.S + 4 * f, x);
+                st4(p.snap[s] + (int64_t)(pos0[s] + j) * p.S + 4 * f, x);
             }
         }
     }
@@ -271,12 +278,15 @@ __global__ void __launch_bounds__(256) commit_ls_kernel(const StepParams p, int 
     const int k = step - p.hdr->first_step;
     if (p.hdr->magic != kPlanMagic || k < 1 || k >= p.hdr->K || p.hdr->B != p.B || step > p.alpha_len) return;
     const int seg0[2] = {p.side[0].b_seg[k], p.side[1].b_seg[k]};
-    const int U0 = p.side[0].b_seg[k + 1] - seg0[0], U1 = p.side[1].b_seg[k + 1] - seg0[1];
+    const int own0[2] = {p.side[0].b_own[k * (kMaxShards + 1) + p.shard], p.side[1].b_own[k * (kMaxShards + 1) + p.shard]};
+    const int U0 = p.side[0].b_own[k * (kMaxShards + 1) + p.shard + 1] - own0[0];
+    const int U1 = p.side[1].b_own[k * (kMaxShards + 1) + p.shard + 1] - own0[1];
+    const int64_t id0 = (int64_t)p.shard * p.v_loc;
     for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < U0 + U1; w += gridDim.x * blockDim.x) {
         const int s = w >= U0 ? 1 : 0;
-        const int g = seg0[s] + (s ? w - U0 : w);
+        const int g = seg0[s] + own0[s] + (s ? w - U0 : w);
         if (p.side[s].seg_prev[g]) continue;
-        float *ls_word = p.table[s] + (int64_t)p.side[s].seg_id[g] * p.P * p.S + ls_col(p.d, s);
+        float *ls_word = p.table[s] + ((int64_t)p.side[s].seg_id[g] - id0) * p.P * p.S + ls_col(p.d, s);
         const int ls = __float_as_int(*ls_word);
         if (ls > 0 && ls < step) *ls_word = __int_as_float(step);
     }
@@ -604,16 +614,19 @@ __global__ void __launch_bounds__(128) apply_kernel(const StepParams p) {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     const int seg0[2] = {p.side[0].b_seg[k], p.side[1].b_seg[k]};
-    const int U0 = p.side[0].b_seg[k + 1] - seg0[0], U1 = p.side[1].b_seg[k + 1] - seg0[1];
+    const int own0[2] = {p.side[0].b_own[k * (kMaxShards + 1) + p.shard], p.side[1].b_own[k * (kMaxShards + 1) + p.shard]};
+    const int U0 = p.side[0].b_own[k * (kMaxShards + 1) + p.shard + 1] - own0[0];
+    const int U1 = p.side[1].b_own[k * (kMaxShards + 1) + p.shard + 1] - own0[1];
+    const int pos0[2] = {p.shard * p.side[0].b_upad[k], p.shard * p.side[1].b_upad[k]};
+    const int64_t id0 = (int64_t)p.shard * p.v_loc;
     const int S4 = p.S >> 2;
     for (int w = warp; w < U0 + U1; w += nwarps) {
         const int s = w >= U0 ? 1 : 0;
-        const int slot = s ? w - U0 : w;
-        const int id = p.side[s].seg_id[seg0[s] + slot];
-        float *row = p.table[s] + (int64_t)id * p.P * p.S;
+        const int j = s ? w - U0 : w;     // index inside this shard's block: also the index into its gradient block
+        float *row = p.table[s] + ((int64_t)p.side[s].seg_id[seg0[s] + own0[s] + j] - id0) * p.P * p.S;
         float4 x[NV], G[NV], s1[NV], s2[NV];
-        load_row<NV>(x, p.snap[s] + (int64_t)slot * p.S, lane, S4);
-        load_row<NV>(G, p.grad[s] + (int64_t)slot * p.S, lane, S4);
+        load_row<NV>(x, p.snap[s] + (int64_t)(pos0[s] + j) * p.S, lane, S4);
+        load_row<NV>(G, p.grad[s] + (int64_t)j * p.S, lane, S4);
         if (p.P >= 2) load_row<NV>(s1, row + p.S, lane, S4);
         if (p.P >= 3) load_row<NV>(s2, row + 2 * p.S, lane, S4);
         apply_row<NV>(p, row, x, G, s1, s2, s, step, lane);
@@ -660,6 +673,12 @@ static int fill_params(const glove_step_args *a, StepParams &p, int mode) {
     p.dp_rank = a->dp_rank;
     if (p.dp_world > 1) GLOVE_REQUIRE(a->B % p.dp_world == 0 && a->dp_rank >= 0 && a->dp_rank < p.dp_world, "step: bad dp split");
     p.dp_block = a->B / p.dp_world;
+    p.n_shards = a->n_shards > 1 ? a->n_shards : 1;
+    p.shard = p.n_shards > 1 ? a->shard : 0;
+    GLOVE_REQUIRE(p.n_shards <= kMaxShards && p.shard >= 0 && p.shard < p.n_shards, "step: bad shard %d of %d", a->shard, a->n_shards);
+    GLOVE_REQUIRE(p.n_shards == 1 || mode != MODE_TRAIN, "step: row-sharded tables need the grad / apply split");
+    p.v_loc = (int32_t)((a->V + p.n_shards - 1) / p.n_shards);
+    p.run_stage = p.run_update = 1;
     return GLOVE_OK;
 }
 
@@ -680,10 +699,11 @@ static int launch_step(const StepParams &p, cudaStream_t stream, cudaEvent_t *ev
     if (!g_apply) g_apply = occupancy_grid(apply_kernel<NV>, 128);
     if (p.mode == MODE_TRAIN || p.mode == MODE_GRAD) {
         if (ev) cudaEventRecord(ev[0], stream);
-        stage_kernel<false><<<g_stage, 256, 0, stream>>>(p, 0);
+        if (p.run_stage) stage_kernel<false><<<g_stage, 256, 0, stream>>>(p, 0);
         if (ev) cudaEventRecord(ev[1], stream);
         const bool dp = p.dp_world > 1;
-        if (p.head == GLOVE_HEAD_GLOVE) {
+        if (!p.run_update) {
+        } else if (p.head == GLOVE_HEAD_GLOVE) {
             if (dp) update_kernel<NV, GLOVE_HEAD_GLOVE, true><<<g_update, 128, 0, stream>>>(p);
             else update_kernel<NV, GLOVE_HEAD_GLOVE, false><<<g_update, 128, 0, stream>>>(p);
         } else {
@@ -719,6 +739,12 @@ extern "C" {
 size_t glove_step_workspace_bytes(int32_t B, int32_t d) {
     if (B <= 0 || d <= 0) return 0;
     return step_ws_view(nullptr, B, d).bytes;
+}
+int64_t glove_step_snapshot_rows(int32_t B) { return B > 0 ? snapshot_rows(B) : 0; }
+size_t glove_step_snapshot_offset(int32_t B, int32_t d, int32_t side) {
+    if (B <= 0 || d <= 0 || side < 0 || side > 1) return 0;
+    StepWs w = step_ws_view((void *)256, B, d);   // any non-null base: offsets are relative to it
+    return (size_t)((char *)w.snap[side] - (char *)256);
 }
 
 int glove_train_step(const glove_step_args *args, void *stream) {
@@ -774,6 +800,25 @@ int glove_grad_step(const glove_step_args *args, float *grad_rows, float *grad_c
     if (rc != GLOVE_OK) return rc;
     GLOVE_REQUIRE(grad_rows && grad_cols && grad_scalars, "glove_grad_step: null gradient buffer");
     p.grad[0] = grad_rows; p.grad[1] = grad_cols; p.grad_scalars = grad_scalars;
+    return dispatch(p, (cudaStream_t)stream);
+}
+
+int glove_shard_stage_step(const glove_step_args *args, void *stream) {
+    StepParams p;
+    int rc = fill_params(args, p, MODE_GRAD);
+    if (rc != GLOVE_OK) return rc;
+    p.run_update = 0;
+    return dispatch(p, (cudaStream_t)stream);
+}
+
+int glove_shard_grad_step(const glove_step_args *args, float *grad_rows, float *grad_cols, float *grad_scalars,
+                          void *stream) {
+    StepParams p;
+    int rc = fill_params(args, p, MODE_GRAD);
+    if (rc != GLOVE_OK) return rc;
+    GLOVE_REQUIRE(grad_rows && grad_cols && grad_scalars, "glove_shard_grad_step: null gradient buffer");
+    p.grad[0] = grad_rows; p.grad[1] = grad_cols; p.grad_scalars = grad_scalars;
+    p.run_stage = 0;
     return dispatch(p, (cudaStream_t)stream);
 }
 

@@ -349,12 +349,18 @@ class GloveEngine:
         """Data-parallel half-step 1: this rank's gradient partial sums for every global segment (dense, slot order).
         Returns (grad_rows, grad_cols, grad_scalars) device tensors to be all-reduced."""
         which = self._plan_for(self.host_step)
-        if self.grad is None:
-            f32 = dict(dtype=torch.float32, device=self.device)
-            self.grad = (torch.zeros(self.B * self.S, **f32), torch.zeros(self.B * self.S, **f32), torch.zeros(4, **f32))
-        gr, gc, gs = self.grad
+        gr, gc, gs = self._grad_buffers()
         check(lib.glove_grad_step(ctypes.byref(self._args[which]), _ptr(gr), _ptr(gc), _ptr(gs), _stream()), "glove_grad_step")
         return gr, gc, gs
+
+    def _grad_buffers(self):
+        """One contiguous buffer [scalars(4, padded to 8) | rows B*S | cols B*S] so that a step needs ONE collective when
+        the touched slots of both sides are packed next to each other (see _step_dp)."""
+        if self.grad is None:
+            self._grad_flat = torch.zeros(8 + 2 * self.B * self.S, dtype=torch.float32, device=self.device)
+            n = self.B * self.S
+            self.grad = (self._grad_flat[8:8 + n], self._grad_flat[8 + n:8 + 2 * n], self._grad_flat[0:4])
+        return self.grad
 
     def apply_step(self):
         """Data-parallel half-step 2: apply the optimizer on every replica from the all-reduced buffers."""
@@ -372,9 +378,9 @@ class GloveEngine:
         # exchange only the touched rows: the buffers are dense in slot order and the per-batch segment counts of the
         # whole plan were fetched once when the plan was built
         n_r, n_c = self._counts_for(self.host_step)
-        dist.all_reduce(gr[: n_r * self.S])
+        # [scalars | touched row slots] is contiguous; the touched col slots follow B*S later: two collectives per step
+        dist.all_reduce(self._grad_flat[: 8 + n_r * self.S])
         dist.all_reduce(gc[: n_c * self.S])
-        dist.all_reduce(gs)
         self.apply_step()
 
     def _counts_for(self, step):
@@ -439,10 +445,7 @@ class GloveEngine:
         for _ in range(self.K):
             if self.dp_world > 1:
                 import torch.distributed as dist
-                if self.grad is None:
-                    f32 = dict(dtype=torch.float32, device=self.device)
-                    self.grad = (torch.zeros(self.B * self.S, **f32), torch.zeros(self.B * self.S, **f32), torch.zeros(4, **f32))
-                gr, gc, gs = self.grad
+                gr, gc, gs = self._grad_buffers()
                 check(lib.glove_grad_step(ctypes.byref(a), _ptr(gr), _ptr(gc), _ptr(gs), _stream()), "glove_grad_step")
                 dist.all_reduce(gr); dist.all_reduce(gc); dist.all_reduce(gs)
                 check(lib.glove_apply_step(ctypes.byref(a), _ptr(gr), _ptr(gc), _ptr(gs), _stream()), "glove_apply_step")

@@ -100,6 +100,16 @@ int glove_prepare_batches(void *plan, void *workspace, size_t workspace_bytes, c
                           const float *colA, const float *colB, int64_t nnz, const int64_t *sample_idx,
                           int64_t first_sample, uint32_t shuffle_key, int32_t first_step, int32_t K, int32_t B,
                           int32_t V, void *stream);
+/* Same, for row-sharded tables (n_shards owners, owner of id = id % n_shards, local row = id / n_shards): ids are
+ * remapped owner-major so that every owner's rows form one block of slots; slot positions are padded so that all
+ * owners' blocks have the same size (see glove_plan_shard_info).  n_shards = 1 is glove_prepare_batches. */
+int glove_prepare_batches_sharded(void *plan, void *workspace, size_t workspace_bytes, const int32_t *row,
+                                  const int32_t *col, const float *colA, const float *colB, int64_t nnz,
+                                  const int64_t *sample_idx, int64_t first_sample, uint32_t shuffle_key,
+                                  int32_t first_step, int32_t K, int32_t B, int32_t V, int32_t n_shards, void *stream);
+/* Host view of batch k's shard layout: out20[10*side + r] (r = 0..8) = first slot owned by shard r (entries past
+ * n_shards = number of segments), out20[10*side + 9] = padded slots per shard.  Synchronises the stream. */
+int glove_plan_shard_info(const void *plan, int32_t K, int32_t B, int32_t k, int32_t *out20, void *stream);
 /* Debug / test view of a plan: copies per-batch counts to host-visible ints: out[0..3] = {n_row_segments,
  * n_col_segments, n_row_items, n_col_items} of batch k.  Synchronises the stream. */
 int glove_plan_batch_counts(const void *plan, int32_t K, int32_t B, int32_t k, int32_t *out4, void *stream);
@@ -124,6 +134,9 @@ typedef struct glove_step_args {
     /* data-parallel: this rank only accumulates triples whose in-batch index p satisfies p / dp_block == dp_rank
      * (dp_world <= 1 disables).  See glove_grad_step / glove_apply_step. */
     int32_t dp_rank, dp_world;
+    /* row-sharded tables (n_shards > 1): this process holds the rows with id % n_shards == shard (local row id /
+     * n_shards, V_local = ceil(V / n_shards)); the plan must come from glove_prepare_batches_sharded.  0 / 1 = not sharded. */
+    int32_t n_shards, shard;
 } glove_step_args;
 
 size_t glove_step_workspace_bytes(int32_t B, int32_t d);
@@ -144,6 +157,20 @@ int glove_grad_step(const glove_step_args *args, float *grad_rows, float *grad_c
                     void *stream);
 int glove_apply_step(const glove_step_args *args, const float *grad_rows, const float *grad_cols,
                      const float *grad_scalars, void *stream);
+
+/* Row-sharded tables (cfg4): one step is
+ *   glove_shard_stage_step   stage (and replay) the OWNED rows of the batch into this shard's block of the snapshot
+ *   -- all-gather the snapshot blocks (equal-sized, see glove_plan_shard_info) --
+ *   glove_shard_grad_step    gradient partial sums of this rank's triples for every slot, dense in slot-position order
+ *   -- reduce-scatter the gradient buffers to the owners, all-reduce grad_scalars --
+ *   glove_apply_step         optimizer on the owned rows (grad_rows / grad_cols = this shard's reduced block)
+ * The snapshot lives in the step workspace: side s starts at glove_step_snapshot_offset(B, d, s) bytes and holds
+ * glove_step_snapshot_rows(B) rows of glove_table_stride(d) floats. */
+int glove_shard_stage_step(const glove_step_args *args, void *stream);
+int glove_shard_grad_step(const glove_step_args *args, float *grad_rows, float *grad_cols, float *grad_scalars,
+                          void *stream);
+int64_t glove_step_snapshot_rows(int32_t B);
+size_t glove_step_snapshot_offset(int32_t B, int32_t d, int32_t side);
 
 /* Replays the missed zero-gradient Adam steps of every row up to (not including) step to_step.  Required before the
  * tables are read from outside the step (eval, export, checkpoint) in GLOVE_ADAM_REPLAY mode; calling it after every
