@@ -756,7 +756,7 @@ int glove_train_step(const glove_step_args *args, void *stream) {
 
 int glove_catchup_step(const glove_step_args *args, int32_t step_index, void *stream) {
     StepParams p;
-    int rc = fill_params(args, p, MODE_TRAIN);
+    int rc = fill_params(args, p, args && args->n_shards > 1 ? MODE_GRAD : MODE_TRAIN);
     if (rc != GLOVE_OK) return rc;
     if (p.opt != GLOVE_OPT_ADAM || p.adam_mode != GLOVE_ADAM_REPLAY) return GLOVE_OK;
     static int grid = 0;

@@ -45,7 +45,8 @@ class GloveEngine:
     def __init__(self, vocab_size: int, embedding_size: int = 64, *, optimizer: str = "Adam",
                  learning_rate: float = 0.001, l2_reg: float = 0.01, reg_scale: float = 2.0, neg_factor: float = 1.0,
                  head: str = "glove", adam_mode: str = "replay", batch_size: int = 1024, plan_steps: int = 16,
-                 max_steps: int = 16384, device="cuda:0", dp_rank: int = 0, dp_world: int = 1, loss_cap: int = 4096):
+                 max_steps: int = 16384, device="cuda:0", dp_rank: int = 0, dp_world: int = 1, loss_cap: int = 4096,
+                 dp_mode: str = "replicated"):
         if not torch.cuda.is_available():
             raise RuntimeError("GloveEngine needs a CUDA device (sm_100a); there is no CPU fallback")
         if optimizer not in _lib.OPTIMIZERS:
@@ -60,16 +61,23 @@ class GloveEngine:
         self.optimizer, self.head, self.adam_mode = optimizer, head, adam_mode
         self.learning_rate, self.l2_reg, self.reg_scale, self.neg_factor = learning_rate, l2_reg, reg_scale, neg_factor
         self.dp_rank, self.dp_world = dp_rank, dp_world
+        if dp_mode not in ("replicated", "sharded"):
+            raise ValueError("unsupported dp_mode %r" % dp_mode)
+        # "sharded": the tables are split row-wise, rank r owns the ids with id % world == r (local row id // world)
+        self.sharded = dp_mode == "sharded" and dp_world > 1
+        self.V_global = int(vocab_size)
+        self.V_rows = (self.V_global + dp_world - 1) // dp_world if self.sharded else self.V_global  # rows held here
         self.opt_id = _lib.OPTIMIZERS[optimizer]
         self.S = lib.glove_table_stride(self.d)
         self.P = lib.glove_table_planes(self.opt_id)
         if self.S // 4 > 128:
             raise ValueError("embedding_size %d > 510 is not supported" % self.d)
         f32 = dict(dtype=torch.float32, device=self.device)
-        self.row_table = torch.empty(self.V * self.P * self.S, **f32)
-        self.col_table = torch.empty(self.V * self.P * self.S, **f32)
+        self.row_table = torch.empty(self.V_rows * self.P * self.S, **f32)
+        self.col_table = torch.empty(self.V_rows * self.P * self.S, **f32)
         for side, t in enumerate((self.row_table, self.col_table)):
-            check(lib.glove_table_init(_ptr(t), self.V, self.d, self.opt_id, side, _stream()), "glove_table_init")
+            check(lib.glove_table_init(_ptr(t), self.V_rows, self.d, self.opt_id, side, _stream()), "glove_table_init")
+        self.V = self.V_rows   # every table-shaped operation below works on the rows held here
         self.scalars = torch.zeros(8, dtype=torch.int32, device=self.device)
         if optimizer == "Adagrad":
             self._write_scalars(g_s0=0.1)
@@ -83,6 +91,7 @@ class GloveEngine:
         self.plans = [torch.empty(self.plan_bytes, **u8) for _ in range(2)]
         self.plan_first = [None, None]
         self._plan_counts = [None, None]
+        self._plan_shards = [None, None]
         self.prep_ws = torch.empty(lib.glove_prepare_workspace_bytes(self.K, self.B), **u8)
         self.step_ws = torch.zeros(lib.glove_step_workspace_bytes(self.B, self.d), **u8)   # must start zeroed
         self.coo = None
@@ -120,12 +129,23 @@ class GloveEngine:
         """Inject initial tables (reference layout: R, C [V,d]; rb, cb [V]; scalar g)."""
         self._join_side()
         for side, (table, emb, bias) in enumerate(((self.row_table, R, rb), (self.col_table, C, cb))):
+            emb, bias = np.asarray(emb, np.float32), np.asarray(bias, np.float32).reshape(-1)
+            if self.sharded and emb.shape[0] == self.V_global:      # global arrays: keep the rows this rank owns
+                emb, bias = self._local_rows(emb), self._local_rows(bias)
             e = torch.as_tensor(np.ascontiguousarray(emb, np.float32)).to(self.device)
             b = torch.as_tensor(np.ascontiguousarray(bias, np.float32).reshape(-1)).to(self.device)
             assert e.shape == (self.V, self.d) and b.shape == (self.V,)
             check(lib.glove_pack_plane(_ptr(table), self.V, self.d, self.P, 0, side, _ptr(e), _ptr(b), _stream()), "glove_pack_plane")
         self._write_scalars(g=float(g))
         torch.cuda.synchronize()
+
+    def _local_rows(self, a):
+        """Rows of a global [V, ...] array owned by this rank (id % world == rank), zero-padded to V_rows."""
+        loc = a[self.dp_rank::self.dp_world]
+        if loc.shape[0] < self.V_rows:
+            pad = np.zeros((self.V_rows - loc.shape[0],) + loc.shape[1:], loc.dtype)
+            loc = np.concatenate([loc, pad], 0)
+        return loc
 
     def set_step(self, step: int):
         """Resume at a given global_step (checkpoint restore / steady-state benchmarking)."""
@@ -161,8 +181,16 @@ class GloveEngine:
         [ref src/models/model_utils.py:7-15,39]."""
         gen = torch.Generator(device=self.device).manual_seed(seed)
         for side, table in enumerate((self.row_table, self.col_table)):
-            e = torch.empty(self.V, self.d, dtype=torch.float32, device=self.device).uniform_(-0.05, 0.05, generator=gen)
-            b = torch.empty(self.V, dtype=torch.float32, device=self.device).uniform_(-0.05, 0.05, generator=gen)
+            # the GLOBAL table is drawn (same stream on every rank) and, when sharded, only the owned rows are kept
+            e = torch.empty(self.V_global, self.d, dtype=torch.float32, device=self.device).uniform_(-0.05, 0.05, generator=gen)
+            b = torch.empty(self.V_global, dtype=torch.float32, device=self.device).uniform_(-0.05, 0.05, generator=gen)
+            if self.sharded:
+                e2 = torch.zeros(self.V, self.d, dtype=torch.float32, device=self.device)
+                b2 = torch.zeros(self.V, dtype=torch.float32, device=self.device)
+                own = e[self.dp_rank::self.dp_world]
+                e2[: own.shape[0]] = own
+                b2[: own.shape[0]] = b[self.dp_rank::self.dp_world]
+                e, b = e2, b2
             check(lib.glove_pack_plane(_ptr(table), self.V, self.d, self.P, 0, side, _ptr(e), _ptr(b), _stream()), "glove_pack_plane")
         torch.cuda.synchronize()
 
@@ -243,7 +271,8 @@ class GloveEngine:
         a.workspace, a.workspace_bytes = self.step_ws.data_ptr(), self.step_ws.numel()
         a.alpha, a.alpha_len = self.alpha.data_ptr(), self.max_steps
         a.loss_out, a.loss_cap = self.loss_out.data_ptr(), self.loss_cap
-        a.plan_K, a.V, a.d, a.B = self.K, self.V, self.d, self.B
+        a.plan_K, a.V, a.d, a.B = self.K, self.V_global, self.d, self.B
+        a.n_shards, a.shard = (self.dp_world, self.dp_rank) if self.sharded else (1, 0)
         a.head, a.optimizer = _lib.HEADS[self.head], self.opt_id
         a.adam_mode = _lib.ADAM_MODES[self.adam_mode]
         a.learning_rate, a.l2_reg, a.reg_scale, a.neg_factor = self.learning_rate, self.l2_reg, self.reg_scale, self.neg_factor
@@ -265,13 +294,15 @@ class GloveEngine:
                 chunk = torch.cat([chunk, chunk[-1:].expand(self.K - chunk.shape[0], -1)], 0)
             sidx = chunk.contiguous().view(-1)
         row, col, ca, cb = self.coo
-        check(lib.glove_prepare_batches(_ptr(self.plans[which]), _ptr(self.prep_ws), self.prep_ws.numel(), _ptr(row),
-                                        _ptr(col), _ptr(ca), _ptr(cb), self.nnz, _ptr(sidx),
-                                        int(first_step) * self.B, self.shuffle_key, int(first_step), self.K, self.B,
-                                        self.V, _stream()), "glove_prepare_batches")
+        check(lib.glove_prepare_batches_sharded(_ptr(self.plans[which]), _ptr(self.prep_ws), self.prep_ws.numel(),
+                                                _ptr(row), _ptr(col), _ptr(ca), _ptr(cb), self.nnz, _ptr(sidx),
+                                                int(first_step) * self.B, self.shuffle_key, int(first_step), self.K,
+                                                self.B, self.V_global, self.dp_world if self.sharded else 1, _stream()),
+              "glove_prepare_batches")
         self._keep[which] = sidx  # keep the index chunk alive until the stream has consumed it
         self.plan_first[which] = first_step
         self._plan_counts[which] = None
+        self._plan_shards[which] = None
         self._ev_plan[which] = None
 
     def _prefetch_plan(self, step: int):
@@ -334,6 +365,9 @@ class GloveEngine:
         ``loss_out[step % loss_cap]``."""
         if self.host_step >= self.max_steps:
             raise RuntimeError("max_steps exhausted; construct the engine with a larger max_steps")
+        if self.sharded:
+            self._step_sharded()
+            return
         which = self._plan_for(self.host_step)
         self._before_step(which)
         if self.dp_world > 1:
@@ -371,6 +405,76 @@ class GloveEngine:
         self.host_step += 1
         if self.adam_mode == "dense":
             self.flush()
+
+    # ---- row-sharded data parallel (cfg4): owner-computes ------------------------------------------------------------
+    def _shard_info(self, step):
+        """(first owned slot per shard [2][world+1], padded block size [2]) of the batch of `step` (host copy, cached)."""
+        which = self._plan_for(step)
+        if self._plan_shards[which] is None:
+            out = (ctypes.c_int32 * 20)()
+            infos = []
+            for k in range(self.K):
+                check(lib.glove_plan_shard_info(_ptr(self.plans[which]), self.K, self.B, k, out, _stream()), "glove_plan_shard_info")
+                infos.append(([list(out[0:9]), list(out[10:19])], [out[9], out[19]]))
+            self._plan_shards[which] = infos
+        return self._plan_shards[which][step - self.plan_first[which]]
+
+    def snapshot_view(self, side: int) -> torch.Tensor:
+        """float32 [snapshot_rows, S] view of the step workspace's snapshot of `side`."""
+        rows = lib.glove_step_snapshot_rows(self.B)
+        off = lib.glove_step_snapshot_offset(self.B, self.d, side)
+        return self.step_ws[off: off + rows * self.S * 4].view(torch.float32).view(rows, self.S)
+
+    def _shard_buffers(self):
+        if getattr(self, "_sgrad", None) is None:
+            rows = lib.glove_step_snapshot_rows(self.B)
+            f32 = dict(dtype=torch.float32, device=self.device)
+            self._sgrad = [torch.zeros(rows, self.S, **f32), torch.zeros(rows, self.S, **f32)]   # per slot position
+            self._sred = [torch.zeros(rows, self.S, **f32), torch.zeros(rows, self.S, **f32)]    # this shard's block
+            self._sscal = torch.zeros(4, **f32)
+        return self._sgrad, self._sred, self._sscal
+
+    def shard_stage(self):
+        which = self._plan_for(self.host_step)
+        self._before_step(which)
+        own, upad = self._shard_info(self.host_step)
+        if self.dp_world * max(upad) > lib.glove_step_snapshot_rows(self.B):
+            raise _lib.GloveError("shard blocks too unbalanced for the snapshot buffer (%d x %d rows)" % (self.dp_world, max(upad)))
+        check(lib.glove_shard_stage_step(ctypes.byref(self._args[which]), _stream()), "glove_shard_stage_step")
+        return upad
+
+    def shard_grad(self):
+        which = self._plan_for(self.host_step)
+        g, _, sc = self._shard_buffers()
+        check(lib.glove_shard_grad_step(ctypes.byref(self._args[which]), _ptr(g[0]), _ptr(g[1]), _ptr(sc), _stream()), "glove_shard_grad_step")
+
+    def shard_apply(self):
+        which = self._plan_for(self.host_step)
+        _, red, sc = self._shard_buffers()
+        check(lib.glove_apply_step(ctypes.byref(self._args[which]), _ptr(red[0]), _ptr(red[1]), _ptr(sc), _stream()), "glove_apply_step")
+        self._after_step()
+        self.host_step += 1
+        if self.adam_mode == "dense":
+            self.flush()
+
+    def _step_sharded(self):
+        """stage own rows -> all-gather snapshot blocks -> gradient partial sums of own triples -> reduce-scatter to the
+        owners (+ all-reduce of the 3 loss scalars) -> apply on own rows.  All collectives are equal-sized NCCL natives."""
+        import torch.distributed as dist
+        upad = self.shard_stage()
+        N, r = self.dp_world, self.dp_rank
+        for side in (0, 1):
+            snap, u = self.snapshot_view(side), upad[side]
+            if u:
+                dist.all_gather_into_tensor(snap[: N * u], snap[r * u:(r + 1) * u].clone())
+        self.shard_grad()
+        g, red, sc = self._shard_buffers()
+        for side in (0, 1):
+            u = upad[side]
+            if u:
+                dist.reduce_scatter_tensor(red[side][:u], g[side][: N * u])
+        dist.all_reduce(sc)
+        self.shard_apply()
 
     def _step_dp(self, which):
         import torch.distributed as dist

@@ -219,3 +219,64 @@ def test_overlap_streams_do_not_change_results():
     assert np.array_equal(out[0][0], out[1][0])
     for k in ("R", "C", "rb", "cb", "R/s0", "R/s1", "C/s0", "cb/s1"):
         assert np.array_equal(out[0][1][k], out[1][1][k]), k
+
+
+@pytest.mark.parametrize("world,adam_mode,optimizer,V", [(2, "replay", "Adam", 601), (4, "replay", "Adam", 1000),
+                                                         (3, "lazy", "Adam", 333), (2, "replay", "Adagrad", 64)])
+def test_row_sharded_tables_on_one_gpu(world, adam_mode, optimizer, V):
+    """cfg4 scheme: tables split row-wise over `world` owners (id % world), emulated as `world` engines on one
+    GPU with the three collectives (all-gather of snapshot blocks, reduce-scatter of gradient blocks, all-reduce of the
+    loss scalars) done by hand in rank order.  The union of the shards must match the single-process oracle."""
+    import torch
+    from glove_tensorflow_b200.engine import GloveEngine
+    d, B, steps, n = 40, 512 if world != 3 else 510, 14, 20000
+    coo = make_coo(V, n, 51, hot=0.1)
+    batches = np.random.default_rng(52).integers(0, n, (steps, B))
+    st = o.init_state(V, d, 53)
+    ref = st.copy()
+    ref_losses = np.array(o.train(ref, coo, batches, optimizer=optimizer, learning_rate=0.01,
+                                  adam_mode="lazy" if adam_mode == "lazy" else "keras_dense"))
+    engs = []
+    for r in range(world):
+        e = GloveEngine(V, d, optimizer=optimizer, adam_mode=adam_mode, learning_rate=0.01, batch_size=B, plan_steps=5,
+                        max_steps=steps + 8, dp_rank=r, dp_world=world, dp_mode="sharded")
+        e.load_state(st.R, st.C, st.rb, st.cb, st.g)
+        e.set_coo(coo["row"], coo["col"], coo["target"], coo["weight"])
+        e.set_batches(batches)
+        engs.append(e)
+    losses = []
+    for s in range(steps):
+        upads = [e.shard_stage() for e in engs]
+        assert all(u == upads[0] for u in upads)
+        torch.cuda.synchronize()
+        for side in (0, 1):
+            u = upads[0][side]
+            for dst in engs:                                   # all-gather of the owners' snapshot blocks
+                for q, src in enumerate(engs):
+                    if src is not dst:
+                        dst.snapshot_view(side)[q * u:(q + 1) * u].copy_(src.snapshot_view(side)[q * u:(q + 1) * u])
+        for e in engs:
+            e.shard_grad()
+        torch.cuda.synchronize()
+        for side in (0, 1):
+            u = upads[0][side]
+            for r, e in enumerate(engs):                       # reduce-scatter to the owners, rank order
+                acc = torch.zeros_like(e._sred[side][:u])
+                for src in engs:
+                    acc += src._sgrad[side][r * u:(r + 1) * u]
+                e._sred[side][:u].copy_(acc)
+        tot = torch.stack([e._sscal for e in engs]).sum(0)
+        for e in engs:
+            e._sscal.copy_(tot)
+            e.shard_apply()
+        torch.cuda.synchronize()
+        losses.append(float(engs[0].read_scalars()["loss"]))
+    got = {k: np.zeros_like(getattr(ref, k)) for k in ("R", "C", "rb", "cb")}
+    for r, e in enumerate(engs):
+        stt = e.get_state()
+        for k in got:
+            own = got[k][r::world]
+            got[k][r::world] = stt[k][: len(own)]
+    for k in got:
+        assert _rel(got[k], getattr(ref, k)) < 3e-5, (k, _rel(got[k], getattr(ref, k)))
+    assert np.max(np.abs(np.array(losses) - ref_losses) / np.abs(ref_losses)) < RTOL
