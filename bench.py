@@ -97,6 +97,13 @@ def steady_state(eng, V, B_global, seed):
     p, _ = zipf_cdf(V)
     q = -np.expm1(B_global * np.log1p(-p))                      # P(row touched in a step)
     q_t = torch.from_numpy(q.astype(np.float32)).to(dev).clamp_(1e-12, 1 - 1e-7)
+    def local(t):   # row-sharded tables: keep the rows this rank owns (id % world == rank), zero-padded
+        if not eng.sharded:
+            return t
+        own = t[eng.dp_rank::eng.dp_world]
+        out = torch.zeros((eng.V,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        out[: own.shape[0]] = own
+        return out
     for side in ("row", "col"):
         u = torch.rand(V, device=dev, generator=gen).clamp_(min=1e-12)
         gap = torch.floor(torch.log(u) / torch.log1p(-q_t))     # Geometric(q): idle steps since last touch
@@ -104,9 +111,9 @@ def steady_state(eng, V, B_global, seed):
         touched = (ls > 0).to(torch.float32)
         m = torch.randn(V, eng.d, device=dev, generator=gen) * 1e-6 * touched[:, None]
         v = torch.rand(V, eng.d, device=dev, generator=gen) * 1e-12 * touched[:, None]
-        eng.set_plane(side, 1, m, torch.randn(V, device=dev, generator=gen) * 1e-6 * touched)
-        eng.set_plane(side, 2, v, torch.rand(V, device=dev, generator=gen) * 1e-12 * touched)
-        eng.set_last_step(side, ls)
+        eng.set_plane(side, 1, local(m), local(torch.randn(V, device=dev, generator=gen) * 1e-6 * touched))
+        eng.set_plane(side, 2, local(v), local(torch.rand(V, device=dev, generator=gen) * 1e-12 * touched))
+        eng.set_last_step(side, local(ls))
         del m, v
     eng.set_step(T0)
 
@@ -184,6 +191,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cold-state", action="store_true", help="start from step 0 with empty Adam state")
+    ap.add_argument("--dp-mode", default="sharded", choices=["sharded", "replicated"],
+                    help="N>1: row-sharded tables (owner-computes) or replicated tables with gradient all-reduce")
     args = ap.parse_args()
 
     V, d, B_local, nnz = WORKLOADS[args.workload]
@@ -232,7 +241,7 @@ def main():
     total_steps = args.warmup + args.steps + 3 * K + 64
     eng = GloveEngine(V, d, optimizer="Adam", learning_rate=0.001, l2_reg=0.01, reg_scale=2.0, head="glove",
                       adam_mode=args.adam_mode, batch_size=B, plan_steps=K, max_steps=T0 + 2 * total_steps + steps,
-                      device=dev, dp_rank=rank, dp_world=N)
+                      device=dev, dp_rank=rank, dp_world=N, dp_mode=args.dp_mode)
     eng.init_uniform(seed=1)                                   # same seed on every rank: replicas start identical
     row, col, tgt, wgt = gen_coo_device(V, nnz, 1234, dev)     # replicated COO (weak scaling: B grows with N)
     eng.set_coo(row, col, tgt, wgt, shuffle_key=0xC0FFEE)
@@ -356,7 +365,8 @@ def main():
     line = {"metric": "co-occurrence updates/sec", "value": value, "unit": "updates/s", "n_gpus": N,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(config, global_batch=B, adam_mode=args.adam_mode, parallelism="dp%d" % N,
+            "config": dict(config, global_batch=B, adam_mode=args.adam_mode,
+                           parallelism=("dp%d" % N) if N == 1 else ("dp%d-%s-tables" % (N, args.dp_mode)),
                            l2_flush="inputs larger than L2 (tables+slots %.1f GB, COO %.1f GB)"
                                     % (2 * V * eng.P * eng.S * 4 / 1e9, nnz * 16 / 1e9),
                            state="cold" if args.cold_state else "steady-state emulation at step %d" % T0),

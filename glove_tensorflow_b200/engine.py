@@ -540,13 +540,19 @@ class GloveEngine:
         first = self.host_step
         which = 0
         row, col, ca, cb = self._stage_coo
-        check(lib.glove_prepare_batches(_ptr(self.plans[which]), _ptr(self.prep_ws), self.prep_ws.numel(), _ptr(row),
-                                        _ptr(col), _ptr(ca), _ptr(cb), n, _ptr(self._stage_idx), 0, 0, first, self.K,
-                                        self.B, self.V, _stream()), "glove_prepare_batches")
+        check(lib.glove_prepare_batches_sharded(_ptr(self.plans[which]), _ptr(self.prep_ws), self.prep_ws.numel(), _ptr(row),
+                                                _ptr(col), _ptr(ca), _ptr(cb), n, _ptr(self._stage_idx), 0, 0, first, self.K,
+                                                self.B, self.V_global, self.dp_world if self.sharded else 1, _stream()),
+              "glove_prepare_batches")
         self._plan_counts[which] = None
+        self._plan_shards[which] = None
         self.plan_first = [None, None]
+        self.plan_first[which] = first
         a = self._args[which]
         for _ in range(self.K):
+            if self.sharded:
+                self._step_sharded()
+                continue
             if self.dp_world > 1:
                 import torch.distributed as dist
                 gr, gc, gs = self._grad_buffers()
@@ -556,6 +562,7 @@ class GloveEngine:
             else:
                 check(lib.glove_train_step(ctypes.byref(a), _stream()), "glove_train_step")
             self.host_step += 1
+        self.plan_first = [None, None]
         idx = torch.arange(first, first + self.K, device=self.device) % self.loss_cap
         return self.loss_out[idx].cpu().numpy()      # D2H of the K losses (synchronises)
 

@@ -1,29 +1,50 @@
-import os, sys, time, json
-sys.path.insert(0, '/root/repo')
-import torch, torch.distributed as dist, numpy as np
+"""Per-phase device timings of one data-parallel step (run under torchrun): python -m torch.distributed.run ... tools/dp_profile.py [sharded|replicated]"""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch, torch.distributed as dist
 import bench
 from glove_tensorflow_b200.engine import GloveEngine
-rank=int(os.environ["RANK"]); world=int(os.environ["WORLD_SIZE"]); dev=torch.device("cuda", int(os.environ["LOCAL_RANK"]))
+mode = sys.argv[1] if len(sys.argv) > 1 else "sharded"
+rank, world, dev = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), torch.device("cuda", int(os.environ["LOCAL_RANK"]))
 torch.cuda.set_device(dev); dist.init_process_group("nccl", device_id=dev)
-V,d,Bl=400000,300,65536; B=Bl*world
-eng=GloveEngine(V,d,batch_size=B,plan_steps=16,max_steps=4096+2048,device=dev,dp_rank=rank,dp_world=world)
-eng.init_uniform(1); row,col,t,w=bench.gen_coo_device(V,1<<24,1234,dev); eng.set_coo(row,col,t,w,shuffle_key=1)
-bench.steady_state(eng,V,B,99)
+V, d, Bl = 400000, 300, 65536; B = Bl * world
+eng = GloveEngine(V, d, batch_size=B, plan_steps=16, max_steps=4096 + 2048, device=dev, dp_rank=rank, dp_world=world, dp_mode=mode)
+eng.init_uniform(1); row, col, t, w = bench.gen_coo_device(V, 1 << 24, 1234, dev); eng.set_coo(row, col, t, w, shuffle_key=1)
+bench.steady_state(eng, V, B, 99)
 for _ in range(20): eng.step()
 torch.cuda.synchronize(); dist.barrier()
-ev=[torch.cuda.Event(enable_timing=True) for _ in range(5)]
-acc=np.zeros(4); n=64
+n = 64
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(7)]
+acc = np.zeros(6)
 for _ in range(n):
-    which=eng._plan_for(eng.host_step); eng._before_step(which)
-    ev[0].record(); gr,gc,gs=eng.grad_step(); ev[1].record()
-    n_r,n_c=eng._counts_for(eng.host_step)
-    dist.all_reduce(eng._grad_flat[:8+n_r*eng.S]); dist.all_reduce(gc[:n_c*eng.S]); ev[2].record()
-    eng.apply_step(); ev[3].record()
-    torch.cuda.synchronize()
-    acc+= [ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3]), 0]
-if rank==0: print("DP breakdown ms (grad, allreduce, apply):", acc[:3]/n, "n_r,n_c", n_r, n_c)
-t0=time.perf_counter()
+    if mode == "sharded":
+        ev[0].record(); upad = eng.shard_stage(); ev[1].record()
+        N, r = world, rank
+        for side in (0, 1):
+            snap, u = eng.snapshot_view(side), upad[side]
+            dist.all_gather_into_tensor(snap[: N * u], snap[r * u:(r + 1) * u].clone())
+        ev[2].record(); eng.shard_grad(); ev[3].record()
+        g, red, sc = eng._shard_buffers()
+        for side in (0, 1):
+            u = upad[side]
+            dist.reduce_scatter_tensor(red[side][:u], g[side][: N * u])
+        dist.all_reduce(sc)
+        ev[4].record(); eng.shard_apply(); ev[5].record()
+        torch.cuda.synchronize()
+        acc[:5] += [ev[i].elapsed_time(ev[i + 1]) for i in range(5)]
+    else:
+        which = eng._plan_for(eng.host_step); eng._before_step(which)
+        ev[0].record(); gr, gc, gs = eng.grad_step(); ev[1].record()
+        n_r, n_c = eng._counts_for(eng.host_step)
+        dist.all_reduce(eng._grad_flat[:8 + n_r * eng.S]); dist.all_reduce(gc[:n_c * eng.S]); ev[2].record()
+        eng.apply_step(); ev[3].record()
+        torch.cuda.synchronize()
+        acc[:3] += [ev[i].elapsed_time(ev[i + 1]) for i in range(3)]
+if rank == 0:
+    names = ["stage", "all_gather", "grad", "reduce_scatter+all_reduce", "apply"] if mode == "sharded" else ["stage+grad", "all_reduce", "apply"]
+    print(mode, "per-phase ms:", dict(zip(names, np.round(acc / n, 4))))
+t0 = time.perf_counter()
 for _ in range(n): eng.step()
 torch.cuda.synchronize(); dist.barrier()
-if rank==0: print("pipelined ms/step", (time.perf_counter()-t0)/n*1e3)
+if rank == 0: print("pipelined ms/step", (time.perf_counter() - t0) / n * 1e3)
 dist.destroy_process_group()
