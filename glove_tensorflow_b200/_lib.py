@@ -59,7 +59,8 @@ SIGNATURES = {
     "glove_grad_step": (ctypes.c_int, [ctypes.POINTER(StepArgs), c_void, c_void, c_void, c_void]),
     "glove_apply_step": (ctypes.c_int, [ctypes.POINTER(StepArgs), c_void, c_void, c_void, c_void]),
     "glove_shard_stage_step": (ctypes.c_int, [ctypes.POINTER(StepArgs), c_void]),
-    "glove_shard_grad_step": (ctypes.c_int, [ctypes.POINTER(StepArgs), c_void, c_void, c_void, c_void]),
+    "glove_shard_update_step": (ctypes.c_int, [ctypes.POINTER(StepArgs), c_void, c_void]),
+    "glove_shard_finish_step": (ctypes.c_int, [ctypes.POINTER(StepArgs), c_void, c_void]),
     "glove_step_snapshot_rows": (c_i64, [c_i32]),
     "glove_step_snapshot_offset": (c_size, [c_i32, c_i32, c_i32]),
     "glove_flush_lazy_state": (ctypes.c_int, [c_void, c_i64, c_i32, c_i32, c_i32, c_void, c_i32, c_i32, c_f32, c_f32, c_f32,

@@ -176,6 +176,19 @@ __global__ void owners_kernel(int32_t K, int32_t n_shards, int32_t v_loc, PlanSi
         out.b_own[t] = lo - out.b_seg[k];
     }
 }
+// first work item of each shard's block: items are sorted by segment, so it is a lower bound over item_seg
+__global__ void owner_items_kernel(int32_t K, PlanSide out) {
+    for (int32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < K * (kMaxShards + 1); t += gridDim.x * blockDim.x) {
+        const int32_t k = t / (kMaxShards + 1);
+        const int32_t g = out.b_seg[k] + out.b_own[t];     // first segment of the block (or one past the last)
+        int32_t lo = out.b_item[k], hi = out.b_item[k + 1];
+        while (lo < hi) {
+            const int32_t mid = (lo + hi) >> 1;
+            if (out.item_seg[mid] < g) lo = mid + 1; else hi = mid;
+        }
+        out.b_own_item[t] = lo - out.b_item[k];
+    }
+}
 __global__ void upad_kernel(int32_t K, int32_t n_shards, PlanSide out) {
     for (int32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < K; k += gridDim.x * blockDim.x) {
         int32_t m = 0;
@@ -337,6 +350,7 @@ int glove_prepare_batches_sharded(void *plan, void *workspace, size_t workspace_
         items_kernel<<<blocks, threads, 0, stream>>>(N, B, K, ps, pv.side[s], pv.hdr, s);
         owners_kernel<<<(K * (kMaxShards + 1) + 255) / 256, 256, 0, stream>>>(K, n_shards, v_loc, pv.side[s]);
         upad_kernel<<<(K + 255) / 256, 256, 0, stream>>>(K, n_shards, pv.side[s]);
+        owner_items_kernel<<<(K * (kMaxShards + 1) + 255) / 256, 256, 0, stream>>>(K, pv.side[s]);
         slots_kernel<<<blocks, threads, 0, stream>>>(N, B, n_shards, v_loc, ps, pv.side[s]);
         itemrec_kernel<<<blocks, threads, 0, stream>>>(B, n_shards, v_loc, &pv.hdr->n_item[s], pv.side[s]);
         longrec_kernel<<<blocks, threads, 0, stream>>>(B, n_shards, v_loc, &pv.hdr->n_long[s], pv.side[s]);

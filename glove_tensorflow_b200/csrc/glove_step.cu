@@ -23,7 +23,7 @@
 
 namespace glove {
 
-enum { MODE_TRAIN = 0, MODE_GRAD = 1, MODE_APPLY = 2 };
+enum { MODE_TRAIN = 0, MODE_GRAD = 1, MODE_APPLY = 2, MODE_SHARD = 3 };  // SHARD: owner-computes update of own segments
 constexpr int kMaxWarps = 148 * 64;  // upper bound on resident warps of the update grid
 
 struct StepParams {
@@ -348,7 +348,7 @@ __device__ __forceinline__ void apply_row(const StepParams &p, float *row, float
 __device__ void finish_step(const StepParams &p, int step, const float *reduced /* MODE_APPLY */, double ld = 0.0,
                             double se = 0.0, double rg = 0.0) {
     if (reduced) { ld = reduced[0]; se = reduced[1]; rg = reduced[2]; }
-    if (p.mode == MODE_GRAD) {
+    if (p.mode == MODE_GRAD || p.mode == MODE_SHARD) {
         p.grad_scalars[0] = (float)ld; p.grad_scalars[1] = (float)se; p.grad_scalars[2] = (float)rg; p.grad_scalars[3] = 0.0f;
         p.sc->ticket = 0;
         return;
@@ -446,13 +446,17 @@ __global__ void __launch_bounds__(128, (NV <= 3 ? 4 : 3)) update_kernel(const St
     const float invB = 1.0f / (float)p.B;
     const float ce = (2.0f * p.rs * p.l2) / ((float)p.d * (float)p.B), cbias = (2.0f * p.rs * p.l2) / (float)p.B;
     const float reg_unscale = (float)p.B / (2.0f * p.rs);  // coef * reg_unscale = l2/d (embedding) | l2 (bias)
-    const bool train = p.mode == MODE_TRAIN;
+    const bool train = p.mode == MODE_TRAIN || p.mode == MODE_SHARD;
+    const int64_t id0 = (int64_t)p.shard * p.v_loc;   // first (remapped) id held by this shard
     double w_ld = 0.0, w_se = 0.0, w_rg = 0.0;   // this warp's share of the step's loss terms (fixed item order)
 
 #pragma unroll 1
     for (int s = 0; s < 2; ++s) {
         const PlanSide &ps = p.side[s];
-        const int it0 = ps.b_item[k], nI = ps.b_item[k + 1] - it0;
+        // row-sharded tables: only the work items of this shard's block of segments (contiguous in the item list)
+        const int oi0 = p.mode == MODE_SHARD ? ps.b_own_item[k * (kMaxShards + 1) + p.shard] : 0;
+        const int it0 = ps.b_item[k] + oi0;
+        const int nI = (p.mode == MODE_SHARD ? ps.b_own_item[k * (kMaxShards + 1) + p.shard + 1] : ps.b_item[k + 1] - ps.b_item[k]) - oi0;
         const float *opp_base = p.snap[1 - s];
         const int4 *rec = ps.rec;
         const int bcol = bias_col(p.d, s);
@@ -465,7 +469,7 @@ __global__ void __launch_bounds__(128, (NV <= 3 ? 4 : 3)) update_kernel(const St
             // the epilogue, so their HBM latency hides behind the whole gather loop); the next item's record.
             const int slot = ir.y, start = ir.z, n = ir.w & 0xff, part = ir.w >> 8;
             const int4 myrec = lane < n ? __ldg(rec + start + lane) : make_int4(0, 0, 0, 0);
-            float *row = p.table[s] + (int64_t)(part ? 0 : ir.x) * p.P * p.S;
+            float *row = p.table[s] + (part ? 0 : (int64_t)ir.x - id0) * p.P * p.S;
             float4 x[NV], acc[NV], bufA[NV], bufB[NV], s1[NV], s2[NV];
             load_row<NV>(x, p.snap[s] + (int64_t)slot * p.S, lane, S4);
             const bool applies = train && part == 0;
@@ -564,7 +568,7 @@ __global__ void __launch_bounds__(128, (NV <= 3 ? 4 : 3)) update_kernel(const St
                         if (!train) {
                             store_row<NV>(p.grad[s] + (int64_t)lr.y * p.S, acc, lane, S4);
                         } else {
-                            float *lrow = p.table[s] + (int64_t)lr.x * p.P * p.S;
+                            float *lrow = p.table[s] + ((int64_t)lr.x - id0) * p.P * p.S;
                             load_row<NV>(x, p.snap[s] + (int64_t)lr.y * p.S, lane, S4);
                             if (p.P >= 2) load_row<NV>(s1, lrow + p.S, lane, S4);
                             if (p.P >= 3) load_row<NV>(s2, lrow + 2 * p.S, lane, S4);
@@ -676,7 +680,7 @@ static int fill_params(const glove_step_args *a, StepParams &p, int mode) {
     p.n_shards = a->n_shards > 1 ? a->n_shards : 1;
     p.shard = p.n_shards > 1 ? a->shard : 0;
     GLOVE_REQUIRE(p.n_shards <= kMaxShards && p.shard >= 0 && p.shard < p.n_shards, "step: bad shard %d of %d", a->shard, a->n_shards);
-    GLOVE_REQUIRE(p.n_shards == 1 || mode != MODE_TRAIN, "step: row-sharded tables need the grad / apply split");
+    GLOVE_REQUIRE(p.n_shards == 1 || mode != MODE_TRAIN, "step: row-sharded tables need the stage / update / finish split");
     p.v_loc = (int32_t)((a->V + p.n_shards - 1) / p.n_shards);
     p.run_stage = p.run_update = 1;
     return GLOVE_OK;
@@ -697,7 +701,7 @@ static int launch_step(const StepParams &p, cudaStream_t stream, cudaEvent_t *ev
     if (!g_stage) g_stage = occupancy_grid(stage_kernel<false>, 256);
     if (!g_update) g_update = occupancy_grid(update_kernel<NV, GLOVE_HEAD_GLOVE, false>, 128);
     if (!g_apply) g_apply = occupancy_grid(apply_kernel<NV>, 128);
-    if (p.mode == MODE_TRAIN || p.mode == MODE_GRAD) {
+    if (p.mode == MODE_TRAIN || p.mode == MODE_GRAD || p.mode == MODE_SHARD) {
         if (ev) cudaEventRecord(ev[0], stream);
         if (p.run_stage) stage_kernel<false><<<g_stage, 256, 0, stream>>>(p, 0);
         if (ev) cudaEventRecord(ev[1], stream);
@@ -805,21 +809,31 @@ int glove_grad_step(const glove_step_args *args, float *grad_rows, float *grad_c
 
 int glove_shard_stage_step(const glove_step_args *args, void *stream) {
     StepParams p;
-    int rc = fill_params(args, p, MODE_GRAD);
+    int rc = fill_params(args, p, MODE_SHARD);
     if (rc != GLOVE_OK) return rc;
     p.run_update = 0;
     return dispatch(p, (cudaStream_t)stream);
 }
 
-int glove_shard_grad_step(const glove_step_args *args, float *grad_rows, float *grad_cols, float *grad_scalars,
-                          void *stream) {
+int glove_shard_update_step(const glove_step_args *args, float *loss_scalars, void *stream) {
     StepParams p;
-    int rc = fill_params(args, p, MODE_GRAD);
+    int rc = fill_params(args, p, MODE_SHARD);
     if (rc != GLOVE_OK) return rc;
-    GLOVE_REQUIRE(grad_rows && grad_cols && grad_scalars, "glove_shard_grad_step: null gradient buffer");
-    p.grad[0] = grad_rows; p.grad[1] = grad_cols; p.grad_scalars = grad_scalars;
+    GLOVE_REQUIRE(loss_scalars, "glove_shard_update_step: null scalar buffer");
+    p.grad_scalars = loss_scalars;
+    p.dp_world = 1;           // ownership is by segment, not by triple
     p.run_stage = 0;
     return dispatch(p, (cudaStream_t)stream);
+}
+
+int glove_shard_finish_step(const glove_step_args *args, const float *loss_scalars, void *stream) {
+    StepParams p;
+    int rc = fill_params(args, p, MODE_APPLY);
+    if (rc != GLOVE_OK) return rc;
+    GLOVE_REQUIRE(loss_scalars, "glove_shard_finish_step: null scalar buffer");
+    apply_finish_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(p, loss_scalars);
+    GLOVE_CHECK_LAUNCH();
+    return GLOVE_OK;
 }
 
 int glove_apply_step(const glove_step_args *args, const float *grad_rows, const float *grad_cols,

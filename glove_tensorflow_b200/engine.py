@@ -425,14 +425,10 @@ class GloveEngine:
         off = lib.glove_step_snapshot_offset(self.B, self.d, side)
         return self.step_ws[off: off + rows * self.S * 4].view(torch.float32).view(rows, self.S)
 
-    def _shard_buffers(self):
-        if getattr(self, "_sgrad", None) is None:
-            rows = lib.glove_step_snapshot_rows(self.B)
-            f32 = dict(dtype=torch.float32, device=self.device)
-            self._sgrad = [torch.zeros(rows, self.S, **f32), torch.zeros(rows, self.S, **f32)]   # per slot position
-            self._sred = [torch.zeros(rows, self.S, **f32), torch.zeros(rows, self.S, **f32)]    # this shard's block
-            self._sscal = torch.zeros(4, **f32)
-        return self._sgrad, self._sred, self._sscal
+    def _shard_scalars(self):
+        if getattr(self, "_sscal", None) is None:
+            self._sscal = torch.zeros(4, dtype=torch.float32, device=self.device)
+        return self._sscal
 
     def shard_stage(self):
         which = self._plan_for(self.host_step)
@@ -443,23 +439,21 @@ class GloveEngine:
         check(lib.glove_shard_stage_step(ctypes.byref(self._args[which]), _stream()), "glove_shard_stage_step")
         return upad
 
-    def shard_grad(self):
+    def shard_update(self):
         which = self._plan_for(self.host_step)
-        g, _, sc = self._shard_buffers()
-        check(lib.glove_shard_grad_step(ctypes.byref(self._args[which]), _ptr(g[0]), _ptr(g[1]), _ptr(sc), _stream()), "glove_shard_grad_step")
+        check(lib.glove_shard_update_step(ctypes.byref(self._args[which]), _ptr(self._shard_scalars()), _stream()), "glove_shard_update_step")
 
-    def shard_apply(self):
+    def shard_finish(self):
         which = self._plan_for(self.host_step)
-        _, red, sc = self._shard_buffers()
-        check(lib.glove_apply_step(ctypes.byref(self._args[which]), _ptr(red[0]), _ptr(red[1]), _ptr(sc), _stream()), "glove_apply_step")
+        check(lib.glove_shard_finish_step(ctypes.byref(self._args[which]), _ptr(self._shard_scalars()), _stream()), "glove_shard_finish_step")
         self._after_step()
         self.host_step += 1
         if self.adam_mode == "dense":
             self.flush()
 
     def _step_sharded(self):
-        """stage own rows -> all-gather snapshot blocks -> gradient partial sums of own triples -> reduce-scatter to the
-        owners (+ all-reduce of the 3 loss scalars) -> apply on own rows.  All collectives are equal-sized NCCL natives."""
+        """Owner-computes: stage own rows -> all-gather the snapshot blocks -> fused update of the own segments (in place)
+        -> all-reduce of the 3 loss scalars -> finish.  Equal-sized native NCCL collectives; no gradient exchange."""
         import torch.distributed as dist
         upad = self.shard_stage()
         N, r = self.dp_world, self.dp_rank
@@ -467,14 +461,9 @@ class GloveEngine:
             snap, u = self.snapshot_view(side), upad[side]
             if u:
                 dist.all_gather_into_tensor(snap[: N * u], snap[r * u:(r + 1) * u].clone())
-        self.shard_grad()
-        g, red, sc = self._shard_buffers()
-        for side in (0, 1):
-            u = upad[side]
-            if u:
-                dist.reduce_scatter_tensor(red[side][:u], g[side][: N * u])
-        dist.all_reduce(sc)
-        self.shard_apply()
+        self.shard_update()
+        dist.all_reduce(self._shard_scalars())
+        self.shard_finish()
 
     def _step_dp(self, which):
         import torch.distributed as dist

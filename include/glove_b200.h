@@ -158,17 +158,19 @@ int glove_grad_step(const glove_step_args *args, float *grad_rows, float *grad_c
 int glove_apply_step(const glove_step_args *args, const float *grad_rows, const float *grad_cols,
                      const float *grad_scalars, void *stream);
 
-/* Row-sharded tables (cfg4): one step is
+/* Row-sharded tables (cfg4), owner-computes.  One step on every rank is
  *   glove_shard_stage_step   stage (and replay) the OWNED rows of the batch into this shard's block of the snapshot
  *   -- all-gather the snapshot blocks (equal-sized, see glove_plan_shard_info) --
- *   glove_shard_grad_step    gradient partial sums of this rank's triples for every slot, dense in slot-position order
- *   -- reduce-scatter the gradient buffers to the owners, all-reduce grad_scalars --
- *   glove_apply_step         optimizer on the owned rows (grad_rows / grad_cols = this shard's reduced block)
+ *   glove_shard_update_step  the fused gather-loss-update of the work items of the OWNED segments (both sides), written
+ *                            in place to the local tables; loss_scalars[0..2] = this rank's {data loss, sum e, reg} sums
+ *   -- all-reduce loss_scalars (3 floats) --
+ *   glove_shard_finish_step  loss, replicated global bias, step counter (identical on every rank)
+ * No gradient ever crosses the network: the only bulk exchange is the snapshot of the touched rows.
  * The snapshot lives in the step workspace: side s starts at glove_step_snapshot_offset(B, d, s) bytes and holds
  * glove_step_snapshot_rows(B) rows of glove_table_stride(d) floats. */
 int glove_shard_stage_step(const glove_step_args *args, void *stream);
-int glove_shard_grad_step(const glove_step_args *args, float *grad_rows, float *grad_cols, float *grad_scalars,
-                          void *stream);
+int glove_shard_update_step(const glove_step_args *args, float *loss_scalars, void *stream);
+int glove_shard_finish_step(const glove_step_args *args, const float *loss_scalars, void *stream);
 int64_t glove_step_snapshot_rows(int32_t B);
 size_t glove_step_snapshot_offset(int32_t B, int32_t d, int32_t side);
 

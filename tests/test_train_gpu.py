@@ -225,8 +225,8 @@ def test_overlap_streams_do_not_change_results():
                                                          (3, "lazy", "Adam", 333), (2, "replay", "Adagrad", 64)])
 def test_row_sharded_tables_on_one_gpu(world, adam_mode, optimizer, V):
     """cfg4 scheme: tables split row-wise over `world` owners (id % world), emulated as `world` engines on one
-    GPU with the three collectives (all-gather of snapshot blocks, reduce-scatter of gradient blocks, all-reduce of the
-    loss scalars) done by hand in rank order.  The union of the shards must match the single-process oracle."""
+    GPU with the two collectives (all-gather of the owners' snapshot blocks, all-reduce of the loss scalars) done by
+    hand; every owner runs the fused update of its own segments.  The union of the shards must match the single-process oracle."""
     import torch
     from glove_tensorflow_b200.engine import GloveEngine
     d, B, steps, n = 40, 512 if world != 3 else 510, 14, 20000
@@ -256,19 +256,12 @@ def test_row_sharded_tables_on_one_gpu(world, adam_mode, optimizer, V):
                     if src is not dst:
                         dst.snapshot_view(side)[q * u:(q + 1) * u].copy_(src.snapshot_view(side)[q * u:(q + 1) * u])
         for e in engs:
-            e.shard_grad()
+            e.shard_update()                                   # owner-computes: no gradient exchange
         torch.cuda.synchronize()
-        for side in (0, 1):
-            u = upads[0][side]
-            for r, e in enumerate(engs):                       # reduce-scatter to the owners, rank order
-                acc = torch.zeros_like(e._sred[side][:u])
-                for src in engs:
-                    acc += src._sgrad[side][r * u:(r + 1) * u]
-                e._sred[side][:u].copy_(acc)
-        tot = torch.stack([e._sscal for e in engs]).sum(0)
+        tot = torch.stack([e._sscal for e in engs]).sum(0)     # all-reduce of the loss scalars
         for e in engs:
             e._sscal.copy_(tot)
-            e.shard_apply()
+            e.shard_finish()
         torch.cuda.synchronize()
         losses.append(float(engs[0].read_scalars()["loss"]))
     got = {k: np.zeros_like(getattr(ref, k)) for k in ("R", "C", "rb", "cb")}

@@ -23,13 +23,9 @@ for _ in range(n):
         for side in (0, 1):
             snap, u = eng.snapshot_view(side), upad[side]
             dist.all_gather_into_tensor(snap[: N * u], snap[r * u:(r + 1) * u].clone())
-        ev[2].record(); eng.shard_grad(); ev[3].record()
-        g, red, sc = eng._shard_buffers()
-        for side in (0, 1):
-            u = upad[side]
-            dist.reduce_scatter_tensor(red[side][:u], g[side][: N * u])
-        dist.all_reduce(sc)
-        ev[4].record(); eng.shard_apply(); ev[5].record()
+        ev[2].record(); eng.shard_update(); ev[3].record()
+        dist.all_reduce(eng._shard_scalars())
+        ev[4].record(); eng.shard_finish(); ev[5].record()
         torch.cuda.synchronize()
         acc[:5] += [ev[i].elapsed_time(ev[i + 1]) for i in range(5)]
     else:
@@ -41,7 +37,7 @@ for _ in range(n):
         torch.cuda.synchronize()
         acc[:3] += [ev[i].elapsed_time(ev[i + 1]) for i in range(3)]
 if rank == 0:
-    names = ["stage", "all_gather", "grad", "reduce_scatter+all_reduce", "apply"] if mode == "sharded" else ["stage+grad", "all_reduce", "apply"]
+    names = ["stage", "all_gather", "update(own)", "all_reduce(3 floats)", "finish"] if mode == "sharded" else ["stage+grad", "all_reduce", "apply"]
     print(mode, "per-phase ms:", dict(zip(names, np.round(acc / n, 4))))
 t0 = time.perf_counter()
 for _ in range(n): eng.step()
