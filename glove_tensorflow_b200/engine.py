@@ -460,7 +460,7 @@ class GloveEngine:
         for side in (0, 1):
             snap, u = self.snapshot_view(side), upad[side]
             if u:
-                dist.all_gather_into_tensor(snap[: N * u], snap[r * u:(r + 1) * u].clone())
+                dist.all_gather_into_tensor(snap[: N * u], snap[r * u:(r + 1) * u])   # in place (NCCL: send = recv + rank*count)
         self.shard_update()
         dist.all_reduce(self._shard_scalars())
         self.shard_finish()

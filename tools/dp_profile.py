@@ -22,7 +22,7 @@ for _ in range(n):
         N, r = world, rank
         for side in (0, 1):
             snap, u = eng.snapshot_view(side), upad[side]
-            dist.all_gather_into_tensor(snap[: N * u], snap[r * u:(r + 1) * u].clone())
+            dist.all_gather_into_tensor(snap[: N * u], snap[r * u:(r + 1) * u])
         ev[2].record(); eng.shard_update(); ev[3].record()
         dist.all_reduce(eng._shard_scalars())
         ev[4].record(); eng.shard_finish(); ev[5].record()
