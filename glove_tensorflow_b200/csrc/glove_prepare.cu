@@ -257,6 +257,43 @@ __global__ void longrec_kernel(int32_t B, int32_t n_shards, int32_t v_loc, const
     }
 }
 
+// ---- request lists of the row-sharded exchange -------------------------------------------------------------------------
+// key of sorted position q of side s: (batch, shard that owns q's segment, position of the opposite row)
+__global__ void need_keys_kernel(int32_t N, int32_t B, int32_t v_loc, int pbits, PrepSide ps, PlanSide out) {
+    for (int32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < N; q += gridDim.x * blockDim.x) {
+        const int32_t g = ps.e_seg[q] + ps.f_seg[q] - 1;
+        const uint32_t r = (uint32_t)(out.seg_id[g] / v_loc);
+        ps.keys_in[q] = ((uint32_t)(q / B) << (pbits + 3)) | (r << pbits) | (uint32_t)out.rec[q].x;
+    }
+}
+__global__ void need_compact_kernel(int32_t N, uint32_t posmask, const uint32_t *__restrict__ keys,
+                                    const int32_t *__restrict__ flag, const int32_t *__restrict__ excl, uint32_t *uniq,
+                                    int32_t *need_pos, int32_t *n_uniq) {
+    for (int32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < N; q += gridDim.x * blockDim.x) {
+        if (flag[q]) { uniq[excl[q]] = keys[q]; need_pos[excl[q]] = (int32_t)(keys[q] & posmask); }
+        if (q == N - 1) *n_uniq = excl[q] + flag[q];
+    }
+}
+__global__ void need_offsets_kernel(int32_t K, int32_t n_shards, int pbits, const uint32_t *__restrict__ uniq,
+                                    const int32_t *__restrict__ n_uniq, const int32_t *__restrict__ upad_other, int32_t *need_off) {
+    const int32_t total = K * kMaxShards * (kMaxShards + 1);
+    const int32_t nu = *n_uniq;
+    for (int32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const int32_t q = t % (kMaxShards + 1), r = (t / (kMaxShards + 1)) % kMaxShards, k = t / (kMaxShards * (kMaxShards + 1));
+        // first unique key >= (k, r, q * upad): for r or q beyond n_shards this is the end of the previous block
+        uint32_t key;
+        if (r >= n_shards) key = (uint32_t)(k + 1) << (pbits + 3);
+        else if (q >= n_shards) key = ((uint32_t)k << (pbits + 3)) | ((uint32_t)(r + 1) << pbits);
+        else key = ((uint32_t)k << (pbits + 3)) | ((uint32_t)r << pbits) | (uint32_t)(q * upad_other[k]);
+        int32_t lo = 0, hi = nu;
+        while (lo < hi) {
+            const int32_t mid = (lo + hi) >> 1;
+            if (uniq[mid] < key) lo = mid + 1; else hi = mid;
+        }
+        need_off[t] = lo;
+    }
+}
+
 __global__ void header_kernel(PlanHeader *hdr, int32_t K, int32_t B, int32_t first_step, int32_t n_shards, int32_t v_loc) {
     hdr->magic = kPlanMagic;
     hdr->K = K;
@@ -360,6 +397,37 @@ int glove_prepare_batches_sharded(void *plan, void *workspace, size_t workspace_
     for (int s = 0; s < 2; ++s)
         fill_kernel<<<blocks, threads, 0, stream>>>(N, B, w.side[s], w.side[1 - s].slot_of_p, w.A, w.Bv, pv.side[s]);
     GLOVE_CHECK_LAUNCH();
+    if (n_shards > 1) {
+        // request lists: which opposite rows does each shard need from each owner (sort + unique of (batch, shard, position))
+        int pbits = 1;
+        while ((1ll << pbits) < (int64_t)B + B / 4 + 64) ++pbits;   // positions < snapshot rows
+        GLOVE_REQUIRE(pbits + 3 + kbits <= 32, "glove_prepare_batches: K=%d x B=%d does not fit the 32-bit request keys", K, B);
+        for (int s = 0; s < 2; ++s) {
+            PrepSide &ps = w.side[s];
+            need_keys_kernel<<<blocks, threads, 0, stream>>>(N, B, v_loc, pbits, ps, pv.side[s]);
+            size_t tb = w.cub_bytes;
+            GLOVE_CHECK_CUDA(cub::DeviceRadixSort::SortKeys(w.cub_temp, tb, ps.keys_in, ps.keys_out, N, 0, pbits + 3 + kbits, stream));
+            heads_kernel<<<blocks, threads, 0, stream>>>(ps.keys_out, N, ps.f_item);
+            tb = w.cub_bytes;
+            GLOVE_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(w.cub_temp, tb, ps.f_item, ps.e_item, N, stream));
+            need_compact_kernel<<<blocks, threads, 0, stream>>>(N, (1u << pbits) - 1, ps.keys_out, ps.f_item, ps.e_item,
+                                                                ps.keys_in, pv.side[s].need_pos, ps.f_long);
+            need_offsets_kernel<<<(K * kMaxShards * (kMaxShards + 1) + 255) / 256, 256, 0, stream>>>(
+                K, n_shards, pbits, ps.keys_in, ps.f_long, pv.side[1 - s].b_upad, pv.side[s].need_off);
+        }
+        GLOVE_CHECK_LAUNCH();
+    }
+    return GLOVE_OK;
+}
+
+int glove_plan_need_info(const void *plan, int32_t K, int32_t B, int32_t *out, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    GLOVE_REQUIRE(plan && out && K > 0, "glove_plan_need_info: bad arguments");
+    PlanView pv = plan_view(const_cast<void *>(plan), K, B);
+    const size_t n = (size_t)K * kMaxShards * (kMaxShards + 1);
+    for (int s = 0; s < 2; ++s)
+        GLOVE_CHECK_CUDA(cudaMemcpyAsync(out + s * n, pv.side[s].need_off, 4 * n, cudaMemcpyDeviceToHost, stream));
+    GLOVE_CHECK_CUDA(cudaStreamSynchronize(stream));
     return GLOVE_OK;
 }
 

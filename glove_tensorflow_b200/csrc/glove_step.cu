@@ -610,6 +610,38 @@ __global__ void __launch_bounds__(128, (NV <= 3 ? 4 : 3)) update_kernel(const St
     }
 }
 
+// ---- row-sharded exchange: pack the rows other shards requested / unpack the rows this shard received ------------------
+// Layout of both buffers: for every peer (rank order) the rows of the side-0 request list followed by those of side 1.
+// PACK: peer r gets the rows of MY block that r's work items need; UNPACK: rows from owner q land at their snapshot position.
+template <bool PACK>
+__global__ void __launch_bounds__(256) exchange_kernel(const StepParams p, float *buf) {
+    int k, step;
+    if (!batch_index(p, k, step)) return;
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int S4 = p.S >> 2;
+    const int me = p.shard, N = p.n_shards;
+    constexpr int W = kMaxShards + 1;
+    int base = 0;   // first buffer row of the current (peer, side) block
+    for (int peer = 0; peer < N; ++peer) {
+        for (int s = 0; s < 2; ++s) {
+            // PACK: requester = peer, owner = me;  UNPACK: requester = me, owner = peer
+            const int r = PACK ? peer : me, q = PACK ? me : peer;
+            const int32_t *off = p.side[s].need_off + ((int64_t)k * kMaxShards + r) * W;
+            const int lo = off[q], n = off[q + 1] - lo;
+            const int32_t *pos = p.side[s].need_pos + lo;
+            float *snap = p.snap[1 - s];
+            for (int i = warp; i < n; i += nwarps) {
+                float *a = snap + (int64_t)pos[i] * p.S, *b = buf + (int64_t)(base + i) * p.S;
+                for (int f = lane; f < S4; f += 32) {
+                    if (PACK) st4(b + 4 * f, ld4(a + 4 * f)); else st4(a + 4 * f, ld4(b + 4 * f));
+                }
+            }
+            base += n;
+        }
+    }
+}
+
 // ---- DP apply: one warp per segment, gradient comes from the all-reduced dense buffer -------------------------------
 template <int NV>
 __global__ void __launch_bounds__(128) apply_kernel(const StepParams p) {
@@ -824,6 +856,26 @@ int glove_shard_update_step(const glove_step_args *args, float *loss_scalars, vo
     p.dp_world = 1;           // ownership is by segment, not by triple
     p.run_stage = 0;
     return dispatch(p, (cudaStream_t)stream);
+}
+
+int glove_shard_pack_step(const glove_step_args *args, float *send_buf, void *stream) {
+    StepParams p;
+    int rc = fill_params(args, p, MODE_SHARD);
+    if (rc != GLOVE_OK) return rc;
+    GLOVE_REQUIRE(send_buf, "glove_shard_pack_step: null buffer");
+    exchange_kernel<true><<<kNumSMs * 4, 256, 0, (cudaStream_t)stream>>>(p, send_buf);
+    GLOVE_CHECK_LAUNCH();
+    return GLOVE_OK;
+}
+
+int glove_shard_unpack_step(const glove_step_args *args, const float *recv_buf, void *stream) {
+    StepParams p;
+    int rc = fill_params(args, p, MODE_SHARD);
+    if (rc != GLOVE_OK) return rc;
+    GLOVE_REQUIRE(recv_buf, "glove_shard_unpack_step: null buffer");
+    exchange_kernel<false><<<kNumSMs * 4, 256, 0, (cudaStream_t)stream>>>(p, const_cast<float *>(recv_buf));
+    GLOVE_CHECK_LAUNCH();
+    return GLOVE_OK;
 }
 
 int glove_shard_finish_step(const glove_step_args *args, const float *loss_scalars, void *stream) {

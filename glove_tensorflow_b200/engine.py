@@ -92,6 +92,8 @@ class GloveEngine:
         self.plan_first = [None, None]
         self._plan_counts = [None, None]
         self._plan_shards = [None, None]
+        self._plan_need = [None, None]
+        self.shard_exchange = "alltoall"
         self.prep_ws = torch.empty(lib.glove_prepare_workspace_bytes(self.K, self.B), **u8)
         self.step_ws = torch.zeros(lib.glove_step_workspace_bytes(self.B, self.d), **u8)   # must start zeroed
         self.coo = None
@@ -303,6 +305,7 @@ class GloveEngine:
         self.plan_first[which] = first_step
         self._plan_counts[which] = None
         self._plan_shards[which] = None
+        self._plan_need[which] = None
         self._ev_plan[which] = None
 
     def _prefetch_plan(self, step: int):
@@ -451,16 +454,48 @@ class GloveEngine:
         if self.adam_mode == "dense":
             self.flush()
 
+    def _need_counts(self, step):
+        """(rows to send to each peer, rows to receive from each owner) of the request-only exchange of `step`."""
+        which = self._plan_for(step)
+        if self._plan_need[which] is None:
+            out = (ctypes.c_int32 * (2 * self.K * 8 * 9))()
+            check(lib.glove_plan_need_info(_ptr(self.plans[which]), self.K, self.B, out, _stream()), "glove_plan_need_info")
+            self._plan_need[which] = np.ctypeslib.as_array(out).reshape(2, self.K, 8, 9).copy()
+        need = self._plan_need[which][:, step - self.plan_first[which]]      # [side][requester][owner]
+        N, me = self.dp_world, self.dp_rank
+        send = [int(sum(need[s][r][me + 1] - need[s][r][me] for s in (0, 1))) for r in range(N)]
+        recv = [int(sum(need[s][me][q + 1] - need[s][me][q] for s in (0, 1))) for q in range(N)]
+        return send, recv
+
+    def shard_pack(self):
+        if getattr(self, "_xbuf", None) is None:
+            rows = 2 * lib.glove_step_snapshot_rows(self.B)
+            self._xbuf = [torch.empty(rows, self.S, dtype=torch.float32, device=self.device) for _ in range(2)]  # send, recv
+        which = self._plan_for(self.host_step)
+        check(lib.glove_shard_pack_step(ctypes.byref(self._args[which]), _ptr(self._xbuf[0]), _stream()), "glove_shard_pack_step")
+        return self._need_counts(self.host_step)
+
+    def shard_unpack(self):
+        which = self._plan_for(self.host_step)
+        check(lib.glove_shard_unpack_step(ctypes.byref(self._args[which]), _ptr(self._xbuf[1]), _stream()), "glove_shard_unpack_step")
+
     def _step_sharded(self):
-        """Owner-computes: stage own rows -> all-gather the snapshot blocks -> fused update of the own segments (in place)
-        -> all-reduce of the 3 loss scalars -> finish.  Equal-sized native NCCL collectives; no gradient exchange."""
+        """Owner-computes: stage own rows -> exchange snapshot rows -> fused update of the own segments (in place) ->
+        all-reduce of the 3 loss scalars -> finish.  No gradient exchange.  `shard_exchange`:
+        'alltoall' (default) sends every owner's rows only to the shards whose work items need them (request lists from the
+        plan, one all_to_all_single with uneven splits); 'allgather' sends every block to everyone (equal-sized native)."""
         import torch.distributed as dist
         upad = self.shard_stage()
         N, r = self.dp_world, self.dp_rank
-        for side in (0, 1):
-            snap, u = self.snapshot_view(side), upad[side]
-            if u:
-                dist.all_gather_into_tensor(snap[: N * u], snap[r * u:(r + 1) * u])   # in place (NCCL: send = recv + rank*count)
+        if self.shard_exchange == "alltoall":
+            send, recv = self.shard_pack()
+            dist.all_to_all_single(self._xbuf[1][: sum(recv)], self._xbuf[0][: sum(send)], recv, send)
+            self.shard_unpack()
+        else:
+            for side in (0, 1):
+                snap, u = self.snapshot_view(side), upad[side]
+                if u:
+                    dist.all_gather_into_tensor(snap[: N * u], snap[r * u:(r + 1) * u])   # in place (send = recv + rank*count)
         self.shard_update()
         dist.all_reduce(self._shard_scalars())
         self.shard_finish()
@@ -535,6 +570,7 @@ class GloveEngine:
               "glove_prepare_batches")
         self._plan_counts[which] = None
         self._plan_shards[which] = None
+        self._plan_need[which] = None
         self.plan_first = [None, None]
         self.plan_first[which] = first
         a = self._args[which]

@@ -167,8 +167,18 @@ int glove_apply_step(const glove_step_args *args, const float *grad_rows, const 
  *   glove_shard_finish_step  loss, replicated global bias, step counter (identical on every rank)
  * No gradient ever crosses the network: the only bulk exchange is the snapshot of the touched rows.
  * The snapshot lives in the step workspace: side s starts at glove_step_snapshot_offset(B, d, s) bytes and holds
- * glove_step_snapshot_rows(B) rows of glove_table_stride(d) floats. */
+ * glove_step_snapshot_rows(B) rows of glove_table_stride(d) floats.
+ *
+ * Exchange variants between stage and update: (a) all-gather of the shards' snapshot blocks (every row to every rank), or
+ * (b) all-to-all of REQUESTED rows only -- glove_shard_pack_step gathers, for every peer, the rows of this shard's block
+ * that the peer's work items need (request lists built at plan time, see glove_plan_need_info) into send_buf;
+ * all_to_all(v); glove_shard_unpack_step scatters the received rows to their snapshot positions. */
 int glove_shard_stage_step(const glove_step_args *args, void *stream);
+int glove_shard_pack_step(const glove_step_args *args, float *send_buf, void *stream);
+int glove_shard_unpack_step(const glove_step_args *args, const float *recv_buf, void *stream);
+/* Host copy of the request-list offsets of a whole plan: out[side][K][8][9] ints; the rows shard r needs from owner q in
+ * batch k (for the work items of `side`) number out[side][k][r][q+1] - out[side][k][r][q].  Synchronises the stream. */
+int glove_plan_need_info(const void *plan, int32_t K, int32_t B, int32_t *out, void *stream);
 int glove_shard_update_step(const glove_step_args *args, float *loss_scalars, void *stream);
 int glove_shard_finish_step(const glove_step_args *args, const float *loss_scalars, void *stream);
 int64_t glove_step_snapshot_rows(int32_t B);

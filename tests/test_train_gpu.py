@@ -221,9 +221,10 @@ def test_overlap_streams_do_not_change_results():
         assert np.array_equal(out[0][1][k], out[1][1][k]), k
 
 
+@pytest.mark.parametrize("exchange", ["alltoall", "allgather"])
 @pytest.mark.parametrize("world,adam_mode,optimizer,V", [(2, "replay", "Adam", 601), (4, "replay", "Adam", 1000),
                                                          (3, "lazy", "Adam", 333), (2, "replay", "Adagrad", 64)])
-def test_row_sharded_tables_on_one_gpu(world, adam_mode, optimizer, V):
+def test_row_sharded_tables_on_one_gpu(world, adam_mode, optimizer, V, exchange):
     """cfg4 scheme: tables split row-wise over `world` owners (id % world), emulated as `world` engines on one
     GPU with the two collectives (all-gather of the owners' snapshot blocks, all-reduce of the loss scalars) done by
     hand; every owner runs the fused update of its own segments.  The union of the shards must match the single-process oracle."""
@@ -249,12 +250,26 @@ def test_row_sharded_tables_on_one_gpu(world, adam_mode, optimizer, V):
         upads = [e.shard_stage() for e in engs]
         assert all(u == upads[0] for u in upads)
         torch.cuda.synchronize()
-        for side in (0, 1):
-            u = upads[0][side]
-            for dst in engs:                                   # all-gather of the owners' snapshot blocks
+        if exchange == "allgather":
+            for side in (0, 1):
+                u = upads[0][side]
+                for dst in engs:                                   # all-gather of the owners' snapshot blocks
+                    for q, src in enumerate(engs):
+                        if src is not dst:
+                            dst.snapshot_view(side)[q * u:(q + 1) * u].copy_(src.snapshot_view(side)[q * u:(q + 1) * u])
+        else:                                                      # all-to-all of the requested rows only
+            counts = [e.shard_pack() for e in engs]                # (send to each peer, receive from each owner)
+            torch.cuda.synchronize()
+            for r, dst in enumerate(engs):
+                roff = 0
                 for q, src in enumerate(engs):
-                    if src is not dst:
-                        dst.snapshot_view(side)[q * u:(q + 1) * u].copy_(src.snapshot_view(side)[q * u:(q + 1) * u])
+                    n = counts[r][1][q]
+                    assert n == counts[q][0][r]
+                    soff = sum(counts[q][0][:r])
+                    dst._xbuf[1][roff:roff + n].copy_(src._xbuf[0][soff:soff + n])
+                    roff += n
+            for e in engs:
+                e.shard_unpack()
         for e in engs:
             e.shard_update()                                   # owner-computes: no gradient exchange
         torch.cuda.synchronize()
