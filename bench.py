@@ -191,6 +191,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cold-state", action="store_true", help="start from step 0 with empty Adam state")
+    ap.add_argument("--shard-exchange", default="alltoall", choices=["alltoall", "allgather"])
     ap.add_argument("--dp-mode", default="sharded", choices=["sharded", "replicated"],
                     help="N>1: row-sharded tables (owner-computes) or replicated tables with gradient all-reduce")
     args = ap.parse_args()
@@ -242,6 +243,7 @@ def main():
     eng = GloveEngine(V, d, optimizer="Adam", learning_rate=0.001, l2_reg=0.01, reg_scale=2.0, head="glove",
                       adam_mode=args.adam_mode, batch_size=B, plan_steps=K, max_steps=T0 + 2 * total_steps + steps,
                       device=dev, dp_rank=rank, dp_world=N, dp_mode=args.dp_mode)
+    eng.shard_exchange = args.shard_exchange
     eng.init_uniform(seed=1)                                   # same seed on every rank: replicas start identical
     row, col, tgt, wgt = gen_coo_device(V, nnz, 1234, dev)     # replicated COO (weak scaling: B grows with N)
     eng.set_coo(row, col, tgt, wgt, shuffle_key=0xC0FFEE)
@@ -366,7 +368,7 @@ def main():
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict(config, global_batch=B, adam_mode=args.adam_mode,
-                           parallelism=("dp%d" % N) if N == 1 else ("dp%d-%s-tables" % (N, args.dp_mode)),
+                           parallelism=("dp%d" % N) if N == 1 else ("dp%d-%s-tables%s" % (N, args.dp_mode, "-" + args.shard_exchange if args.dp_mode == "sharded" else "")),
                            l2_flush="inputs larger than L2 (tables+slots %.1f GB, COO %.1f GB)"
                                     % (2 * V * eng.P * eng.S * 4 / 1e9, nnz * 16 / 1e9),
                            state="cold" if args.cold_state else "steady-state emulation at step %d" % T0),

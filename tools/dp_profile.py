@@ -20,9 +20,14 @@ for _ in range(n):
     if mode == "sharded":
         ev[0].record(); upad = eng.shard_stage(); ev[1].record()
         N, r = world, rank
-        for side in (0, 1):
-            snap, u = eng.snapshot_view(side), upad[side]
-            dist.all_gather_into_tensor(snap[: N * u], snap[r * u:(r + 1) * u])
+        if len(sys.argv) > 2 and sys.argv[2] == "allgather":
+            for side in (0, 1):
+                snap, u = eng.snapshot_view(side), upad[side]
+                dist.all_gather_into_tensor(snap[: N * u], snap[r * u:(r + 1) * u])
+        else:
+            send, recv = eng.shard_pack()
+            dist.all_to_all_single(eng._xbuf[1][: sum(recv)], eng._xbuf[0][: sum(send)], recv, send)
+            eng.shard_unpack()
         ev[2].record(); eng.shard_update(); ev[3].record()
         dist.all_reduce(eng._shard_scalars())
         ev[4].record(); eng.shard_finish(); ev[5].record()
@@ -37,7 +42,7 @@ for _ in range(n):
         torch.cuda.synchronize()
         acc[:3] += [ev[i].elapsed_time(ev[i + 1]) for i in range(3)]
 if rank == 0:
-    names = ["stage", "all_gather", "update(own)", "all_reduce(3 floats)", "finish"] if mode == "sharded" else ["stage+grad", "all_reduce", "apply"]
+    names = ["stage", "exchange", "update(own)", "all_reduce(3 floats)", "finish"] if mode == "sharded" else ["stage+grad", "all_reduce", "apply"]
     print(mode, "per-phase ms:", dict(zip(names, np.round(acc / n, 4))))
 t0 = time.perf_counter()
 for _ in range(n): eng.step()
