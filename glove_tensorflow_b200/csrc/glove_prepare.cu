@@ -283,7 +283,7 @@ __global__ void need_offsets_kernel(int32_t K, int32_t n_shards, int pbits, cons
         // first unique key >= (k, r, q * upad): for r or q beyond n_shards this is the end of the previous block
         uint32_t key;
         if (r >= n_shards) key = (uint32_t)(k + 1) << (pbits + 3);
-        else if (q >= n_shards) key = ((uint32_t)k << (pbits + 3)) | ((uint32_t)(r + 1) << pbits);
+        else if (q >= n_shards) key = ((uint32_t)k << (pbits + 3)) + ((uint32_t)(r + 1) << pbits);   // + : r + 1 may carry into k
         else key = ((uint32_t)k << (pbits + 3)) | ((uint32_t)r << pbits) | (uint32_t)(q * upad_other[k]);
         int32_t lo = 0, hi = nu;
         while (lo < hi) {

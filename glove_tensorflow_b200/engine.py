@@ -465,6 +465,8 @@ class GloveEngine:
         N, me = self.dp_world, self.dp_rank
         send = [int(sum(need[s][r][me + 1] - need[s][r][me] for s in (0, 1))) for r in range(N)]
         recv = [int(sum(need[s][me][q + 1] - need[s][me][q] for s in (0, 1))) for q in range(N)]
+        if min(send) < 0 or min(recv) < 0:
+            raise _lib.GloveError("corrupt request lists in the plan")
         return send, recv
 
     def shard_pack(self):

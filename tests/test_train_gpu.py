@@ -223,7 +223,8 @@ def test_overlap_streams_do_not_change_results():
 
 @pytest.mark.parametrize("exchange", ["alltoall", "allgather"])
 @pytest.mark.parametrize("world,adam_mode,optimizer,V", [(2, "replay", "Adam", 601), (4, "replay", "Adam", 1000),
-                                                         (3, "lazy", "Adam", 333), (2, "replay", "Adagrad", 64)])
+                                                         (3, "lazy", "Adam", 333), (2, "replay", "Adagrad", 64),
+                                                         (8, "replay", "Adam", 5000)])
 def test_row_sharded_tables_on_one_gpu(world, adam_mode, optimizer, V, exchange):
     """cfg4 scheme: tables split row-wise over `world` owners (id % world), emulated as `world` engines on one
     GPU with the two collectives (all-gather of the owners' snapshot blocks, all-reduce of the loss scalars) done by
