@@ -71,3 +71,121 @@ def test_dp_allreduce_equals_single_process_oracle(tmp_path):
         assert np.array_equal(r0[k], r1[k])                               # replicas stay bit-identical
         assert np.max(np.abs(r0[k] - getattr(ref, k))) <= 1e-5 * np.max(np.abs(getattr(ref, k)))
     assert abs(float(r0["g"]) - float(ref.g)) < 1e-6
+
+
+# ---- row-sharded owner-computes scheme (the default N>1 path: bench.py --dp-mode sharded) ----------------------------
+def _shard_worker(rank, world, port, tmp):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+    from conftest import make_coo
+    from glove_tensorflow_b200 import parallel as par
+    from oracle import glove_oracle as o
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    V, d, B, steps, n = 81, 6, 32, 6, 600                  # V not divisible by world: the last rank holds a pad row
+    coo = make_coo(V, n, 31)
+    batches = np.random.default_rng(32).integers(0, n, (steps, B))
+    full = o.init_state(V, d, 33)
+    alpha = o.alpha_table(0.01, steps)
+    Vl = par.shard_rows(V, world)
+    own = np.nonzero(par.shard_owner(np.arange(V), world) == rank)[0]
+
+    def a2a(send):                                         # gloo has no all-to-all: gather every rank's send lists
+        box = [None] * world
+        dist.all_gather_object(box, send)
+        return [box[k][rank] for k in range(world)]
+
+    def local(a):                                          # this rank's rows only, zero pad row at the end
+        out = np.zeros((Vl,) + a.shape[1:], np.float32)
+        out[:len(own)] = a[own]
+        return out
+    tabs = {k: local(getattr(full, k)) for k in ("R", "C", "rb", "cb")}
+    mom = {k: (np.zeros_like(v), np.zeros_like(v)) for k, v in tabs.items()}
+    g, gm, gv = np.float32(full.g), np.float32(0), np.float32(0)
+    b1, b2, eps, l2 = np.float32(0.9), np.float32(0.999), np.float32(1e-7), np.float32(0.04)
+    Bf, df = np.float32(B), np.float32(d)
+    sent_rows = 0
+    for s in range(steps):
+        gb = {k: v[batches[s]] for k, v in coo.items()}
+        snap = {k: v.copy() for k, v in tabs.items()}     # step-start snapshot of the rows held here
+        # exchange: for each side, fetch the opposite-side snapshot rows my segments reference from their owners
+        fetched = {}
+        for ids, opp, emb, bias in ((gb["row"], gb["col"], "C", "cb"), (gb["col"], gb["row"], "R", "rb")):
+            req = par.shard_requests(ids, opp, rank, world)
+            want = [torch.from_numpy(r.astype(np.int64)) for r in req]
+            asked = a2a(want)
+            reply = []
+            for k, a in enumerate(asked):                  # rows rank k asked me for: they must all be mine
+                a = a.numpy()
+                assert np.all(par.shard_owner(a, world) == rank)
+                la = par.shard_local(a, world)
+                reply.append(torch.from_numpy(np.concatenate([snap[emb][la], snap[bias][la, None]], 1)))
+                if k != rank:
+                    sent_rows += len(a)
+            rows = a2a(reply)
+            fetched[emb] = {int(i): r.numpy() for w, rr in zip(want, rows) for i, r in zip(w, rr)}
+        # forward + gradients of the segments owned here (each triple is visited once per side, on two ranks at most)
+        partial = np.zeros(3, np.float32)                  # loss sum, sum e, regulariser -- from the ROW side only
+        grads = {}
+        for side, (ids, opp, emb, bias, oemb) in enumerate(((gb["row"], gb["col"], "R", "rb", "C"), (gb["col"], gb["row"], "C", "cb", "R"))):
+            for b in np.nonzero(par.shard_owner(ids, world) == rank)[0]:
+                i, li = int(ids[b]), int(par.shard_local(ids[b], world))
+                other = fetched[oemb][int(opp[b])]
+                z = np.float32(np.dot(snap[emb][li], other[:d]) + snap[bias][li] + other[d] + g)
+                err = np.float32(z - gb["target"][b])
+                e = np.float32(2) * gb["weight"][b] * err / Bf
+                ge, gbias = grads.setdefault((emb, li), [np.zeros(d, np.float32), np.float32(0)])
+                ge += e * other[:d] + (l2 / (df * Bf)) * snap[emb][li]
+                grads[(emb, li)][1] = np.float32(gbias + e + (l2 / Bf) * snap[bias][li])
+                if side == 0:
+                    partial[0] += gb["weight"][b] * err * err / Bf
+                    partial[1] += e
+        t = torch.from_numpy(partial)
+        dist.all_reduce(t)
+        a = alpha[s]
+        for (emb, li), (ge, gbias) in grads.items():
+            bias = "rb" if emb == "R" else "cb"
+            for name, grad in ((emb, ge), (bias, gbias)):
+                m, v = mom[name]
+                m[li] = b1 * m[li] + (np.float32(1) - b1) * grad
+                v[li] = b2 * v[li] + (np.float32(1) - b2) * grad * grad
+                tabs[name][li] = snap[name][li] - a * m[li] / (np.sqrt(v[li]) + eps)
+        # rows not in the batch still decay under dense Adam (legacy OptimizerV2): m, v shrink, x moves
+        for name in tabs:
+            touched = np.zeros(Vl, bool)
+            touched[[li for (e_, li) in grads if e_ == ("R" if name in ("R", "rb") else "C")]] = True
+            m, v = mom[name]
+            idle = ~touched
+            m[idle] = b1 * m[idle]
+            v[idle] = b2 * v[idle]
+            tabs[name][idle] = tabs[name][idle] - a * m[idle] / (np.sqrt(v[idle]) + eps)
+        dg = np.float32(partial[1] + l2 * g)
+        gm = b1 * gm + (np.float32(1) - b1) * dg
+        gv = b2 * gv + (np.float32(1) - b2) * dg * dg
+        g = np.float32(g - a * gm / (np.sqrt(gv) + eps))
+    np.savez(os.path.join(tmp, "shard%d.npz" % rank), own=own, g=g, sent=sent_rows, **tabs)
+    dist.destroy_process_group()
+
+
+def test_sharded_owner_computes_equals_single_process_oracle(tmp_path):
+    import torch.multiprocessing as mp
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import make_coo
+    from oracle import glove_oracle as o
+    world, port = 2, 30100 + os.getpid() % 500
+    mp.spawn(_shard_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    V, d, B, steps, n = 81, 6, 32, 6, 600
+    coo = make_coo(V, n, 31)
+    batches = np.random.default_rng(32).integers(0, n, (steps, B))
+    ref = o.init_state(V, d, 33)
+    o.train(ref, coo, batches, learning_rate=0.01)
+    parts = [np.load(tmp_path / ("shard%d.npz" % r)) for r in range(world)]
+    for k in ("R", "C", "rb", "cb"):
+        got = np.zeros_like(getattr(ref, k))
+        for p in parts:
+            got[p["own"]] = p[k][:len(p["own"])]
+        assert np.max(np.abs(got - getattr(ref, k))) <= 1e-5 * np.max(np.abs(getattr(ref, k))), k
+    assert abs(float(parts[0]["g"]) - float(ref.g)) < 1e-6 and float(parts[0]["g"]) == float(parts[1]["g"])
+    assert all(int(p["sent"]) > 0 for p in parts)          # the exchange really moved remote rows
