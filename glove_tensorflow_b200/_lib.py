@@ -32,6 +32,12 @@ class StepArgs(ctypes.Structure):
                 ("epsilon", c_f32), ("dp_rank", c_i32), ("dp_world", c_i32), ("n_shards", c_i32), ("shard", c_i32)]
 
 
+class CsvSchema(ctypes.Structure):
+    _fields_ = [("n_cols", c_i32), ("column", c_i32 * 4), ("kind", c_i32 * 4)]
+
+
+CSV_TOKEN, CSV_INT, CSV_FLOAT = 0, 1, 2
+
 # name -> (restype, argtypes); every symbol include/glove_b200.h declares
 SIGNATURES = {
     "glove_last_error": (ctypes.c_char_p, []),
@@ -80,6 +86,14 @@ SIGNATURES = {
     "glove_topk_flagged": (ctypes.c_int, [c_void, c_i64, c_i32, c_i32, c_i32, ctypes.POINTER(c_i32), c_void]),
     "glove_topk_cosine_fp32": (ctypes.c_int, [c_void, c_i64, c_i32, c_i32, c_void, c_void, c_i32, c_i32, c_void,
                                               c_void, c_void, c_size, c_void]),
+    "glove_vocab_slots": (c_i64, [c_i64]),
+    "glove_vocab_build": (ctypes.c_int, [c_void, c_i64, c_void, c_void, c_i64, c_void]),
+    "glove_csv_workspace_bytes": (c_size, [c_i64]),
+    "glove_csv_index": (ctypes.c_int, [c_void, c_i64, c_void, c_size, ctypes.POINTER(c_i64), c_void]),
+    "glove_csv_parse": (ctypes.c_int, [c_void, c_i64, c_i32, c_void, c_size, ctypes.POINTER(CsvSchema), c_void, c_i64,
+                                       c_void, c_void, c_i64, c_void, c_void, c_void, c_void, c_void, c_i64, c_i64,
+                                       ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), c_void]),
+    "glove_parse_float32": (ctypes.c_int, [ctypes.c_char_p, c_i32, ctypes.POINTER(c_f32)]),
     "glove_host_staging_bytes": (c_size, [c_i32, c_i32]),
     "glove_train_steps_host": (ctypes.c_int, [ctypes.POINTER(StepArgs), c_void, c_void, c_size, c_void, c_size, c_void,
                                               c_void, c_void, c_void, c_i32, c_void, c_void]),

@@ -1,9 +1,12 @@
-"""Input side of the drop-in: interaction.csv + vocab.txt -> COO arrays.
+"""Input side of the drop-in: interaction.csv + vocab.txt -> device-resident COO arrays.
 
 Replaces ``get_csv_input_fn`` (tf.data ``make_csv_dataset`` with select_columns, ref src/models/data_utils.py:4-26) and
 the per-step ``StaticHashTable`` string->id lookup (ref src/models/model_utils.py:121-127, src/models/estimator.py:26-28):
-the csv is parsed ONCE, token strings are resolved to vocab line numbers once (missing -> 0, the table's default), and
-the result is uploaded as the device-resident COO triple buffer.  A binary sidecar (<csv>.coo.npz) caches the parse."""
+the csv bytes are streamed to the GPU in chunks and parsed ONCE by the CUDA ingest kernels (csrc/glove_ingest.cu: record
+index, field split, token -> vocab line number with default 0, decimal text -> float32), and the result is the
+device-resident COO triple buffer the trainer shuffles and batches from.  A binary sidecar (<csv>.coo.npz) caches the
+parse.  The host only reads the header record and moves bytes."""
+import ctypes
 import os
 
 import numpy as np
@@ -24,45 +27,184 @@ def file_lines(fname):
     return i + 1
 
 
-def lookup_ids(tokens, vocab):
-    """string -> id with default 0, like tf.lookup.StaticHashTable(..., default_value=0)."""
-    table = {}
-    for i, tok in enumerate(vocab):
-        table.setdefault(tok, i)  # TextFileInitializer rejects duplicate keys; first occurrence is the safe reading
-    return np.fromiter((table.get(t, 0) for t in tokens), dtype=np.int32, count=len(tokens))
+def vocab_blob(vocab_txt):
+    """vocab.txt as the ingest kernels want it: every line followed by one '\\n', plus the n+1 line offsets."""
+    with open(vocab_txt, "rb") as f:
+        lines = f.read().split(b"\n")
+    blob = b"".join(t + b"\n" for t in lines)
+    off = np.zeros(len(lines) + 1, np.int64)
+    np.cumsum([len(t) + 1 for t in lines], out=off[1:])
+    return blob, off
+
+
+def read_header(train_csv, limit=1 << 20):
+    """Column names of the header record and the byte offset of the first data record."""
+    import csv
+    import io
+    with open(train_csv, "rb") as f:
+        head = f.read(limit)
+    quoted, end = False, None
+    for i, b in enumerate(head):
+        if b == 0x22:
+            quoted = not quoted
+        elif b == 0x0A and not quoted:
+            end = i
+            break
+    if end is None:
+        if len(head) == limit:
+            raise ValueError("%s: no header record in the first %d bytes" % (train_csv, limit))
+        end = len(head)
+    line = head[:end].rstrip(b"\r").decode("utf8")
+    names = next(csv.reader(io.StringIO(line, newline="")))
+    return names, min(end + 1, len(head))
+
+
+def make_schema(names, row_name, col_name, value_names):
+    from . import _lib
+    sc = _lib.CsvSchema()
+    sc.n_cols = len(names)
+    for c, name in enumerate((row_name, col_name) + tuple(value_names)):
+        if name not in names:
+            raise ValueError("column %r not in the csv header %r" % (name, names))
+        sc.column[c] = names.index(name)
+        sc.kind[c] = _lib.CSV_FLOAT if c >= 2 else (_lib.CSV_INT if name.endswith("_id") else _lib.CSV_TOKEN)
+    return sc
+
+
+_HEAD = 1 << 20   # room in front of every chunk for the unterminated tail of the previous one
+
+
+class _ChunkReader:
+    """Fills pinned host buffers from the file with a few threads (os.preadv releases the GIL), one chunk ahead of the
+    GPU.  Chunk k lands at buf[k % 2][_HEAD : _HEAD + n]."""
+
+    def __init__(self, path, offset, size, chunk, bufs, threads=8, piece=8 << 20):
+        from concurrent.futures import ThreadPoolExecutor
+        self.fd = os.open(path, os.O_RDONLY)
+        self.offset, self.size, self.chunk, self.bufs, self.piece = offset, size, chunk, bufs, piece
+        self.pool = ThreadPoolExecutor(max_workers=threads)
+        self.pending = {}
+
+    def n_chunks(self):
+        return (self.size + self.chunk - 1) // self.chunk
+
+    def _read(self, view, pos):
+        done = 0
+        while done < len(view):
+            got = os.preadv(self.fd, [view[done:]], pos + done)
+            if got <= 0:
+                raise IOError("short read at byte %d" % (pos + done))
+            done += got
+
+    def start(self, k):
+        if k >= self.n_chunks():
+            return
+        lo = k * self.chunk
+        n = min(self.chunk, self.size - lo)
+        view = memoryview(self.bufs[k % 2])[_HEAD:_HEAD + n]
+        self.pending[k] = (n, [self.pool.submit(self._read, view[o:min(o + self.piece, n)], self.offset + lo + o)
+                               for o in range(0, n, self.piece)])
+
+    def wait(self, k):
+        n, futs = self.pending.pop(k)
+        for f in futs:
+            f.result()
+        return n
+
+    def close(self):
+        self.pool.shutdown(wait=True)
+        os.close(self.fd)
+
+
+def ingest_csv(train_csv, vocab_txt, row_name="row_token", col_name="col_token",
+               value_names=("glove_value", "glove_weight"), device="cuda:0", chunk_bytes=64 << 20):
+    """Streams the file through the CUDA ingest kernels.  Returns device tensors
+    {'row': i32[n], 'col': i32[n], <value_name>: f32[n] ...} in file order.
+
+    Host side: reader threads fill pinned chunk k+1 while the GPU indexes and parses chunk k; the unterminated tail of a
+    chunk is copied in front of the next one (padded to 16-byte alignment with '\n', which the indexer skips as blank
+    lines)."""
+    import torch
+    from . import _lib
+    lib, check = _lib.lib, _lib.check
+    if len(value_names) != 2:
+        raise ValueError("exactly two value columns are read (target, weight) / (pos, neg)")
+    dev = torch.device(device)
+    names, data_off = read_header(train_csv)
+    schema = make_schema(names, row_name, col_name, value_names)
+    size = os.path.getsize(train_csv) - data_off
+    parts = {k: [] for k in ("row", "col", "a", "b")}
+    with torch.cuda.device(dev):
+        st = torch.cuda.current_stream().cuda_stream
+        blob, off = vocab_blob(vocab_txt)
+        n_vocab = len(off) - 1
+        vb = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(dev)
+        voff = torch.from_numpy(off).to(dev)
+        slots = lib.glove_vocab_slots(n_vocab)
+        table = torch.empty(slots, dtype=torch.int32, device=dev)
+        check(lib.glove_vocab_build(table.data_ptr(), slots, vb.data_ptr(), voff.data_ptr(), n_vocab, st), "glove_vocab_build")
+        chunk = int(max(1 << 16, min(chunk_bytes, size))) // 16 * 16
+        pinned = [torch.empty(_HEAD + chunk, dtype=torch.uint8, pin_memory=True) for _ in range(2 if size > chunk else 1)]
+        host = [t.numpy() for t in pinned]
+        text = torch.empty(_HEAD + chunk, dtype=torch.uint8, device=dev)
+        ws = torch.empty(lib.glove_csv_workspace_bytes(_HEAD + chunk), dtype=torch.uint8, device=dev)
+        reader = _ChunkReader(train_csv, data_off, max(size, 0), chunk, host * (2 // len(host)))
+        try:
+            n_chunks, carry, n_total = reader.n_chunks(), 0, 0
+            reader.start(0)
+            for k in range(n_chunks):
+                n_new = reader.wait(k)
+                reader.start(k + 1)
+                final = k == n_chunks - 1
+                begin = (_HEAD - carry) // 16 * 16
+                host[k % 2][begin:_HEAD - carry] = 0x0A
+                fill = _HEAD + n_new - begin
+                text[:fill].copy_(pinned[k % 2][begin:_HEAD + n_new], non_blocking=True)
+                n_rec = ctypes.c_int64()
+                check(lib.glove_csv_index(text.data_ptr(), fill, ws.data_ptr(), ws.numel(), ctypes.byref(n_rec), st), "glove_csv_index")
+                cap = n_rec.value + 1
+                ends = torch.empty(cap, dtype=torch.int64, device=dev)
+                row = torch.empty(cap, dtype=torch.int32, device=dev)
+                col = torch.empty(cap, dtype=torch.int32, device=dev)
+                a = torch.empty(cap, dtype=torch.float32, device=dev)
+                b = torch.empty(cap, dtype=torch.float32, device=dev)
+                n_rows, consumed = ctypes.c_int64(), ctypes.c_int64()
+                check(lib.glove_csv_parse(text.data_ptr(), fill, int(final), ws.data_ptr(), ws.numel(), ctypes.byref(schema),
+                                          table.data_ptr(), slots, vb.data_ptr(), voff.data_ptr(), n_vocab, ends.data_ptr(),
+                                          row.data_ptr(), col.data_ptr(), a.data_ptr(), b.data_ptr(), cap, n_total,
+                                          ctypes.byref(n_rows), ctypes.byref(consumed), st), "glove_csv_parse")
+                n = n_rows.value
+                for key, t in (("row", row), ("col", col), ("a", a), ("b", b)):
+                    parts[key].append(t[:n])
+                n_total += n
+                carry = fill - consumed.value
+                if carry > _HEAD - 16:
+                    raise ValueError("%s: a record is longer than %d bytes" % (train_csv, _HEAD - 16))
+                if carry:   # the tail goes in front of the next chunk (which is being read into the other buffer)
+                    host[(k + 1) % 2][_HEAD - carry:_HEAD] = host[k % 2][begin + consumed.value:begin + fill]
+        finally:
+            reader.close()
+        empty = {"row": torch.int32, "col": torch.int32, "a": torch.float32, "b": torch.float32}
+        cat = {k: (torch.cat(v) if len(v) > 1 else v[0]) if v else torch.empty(0, dtype=empty[k], device=dev)
+               for k, v in parts.items()}
+    return {"row": cat["row"], "col": cat["col"], value_names[0]: cat["a"], value_names[1]: cat["b"]}
 
 
 def load_interaction_csv(train_csv, vocab_txt, row_name="row_token", col_name="col_token",
-                         value_names=("glove_value", "glove_weight"), cache=True):
-    """Returns {'row': i32[n], 'col': i32[n], <value_name>: f32[n] ...} in file order.
+                         value_names=("glove_value", "glove_weight"), cache=True, device="cuda:0"):
+    """Returns {'row': i32[n], 'col': i32[n], <value_name>: f32[n] ...} in file order (numpy, from the sidecar cache when
+    it is current, else parsed on the GPU by ``ingest_csv``).
 
-    ``row_name`` / ``col_name`` may name string columns (resolved through vocab.txt) or integer id columns
-    (``row_token_id``: equal by construction).  keep_default_na=False: tokens like 'na' / 'null' / 'nan' are
-    ordinary vocabulary words (ref README.md:54)."""
-    import pandas as pd
-
+    ``row_name`` / ``col_name`` may name string columns (resolved through vocab.txt, missing -> 0) or integer id columns
+    (``row_token_id``: equal by construction).  Tokens like 'na' / 'null' / 'nan' are ordinary vocabulary
+    words (ref README.md:54)."""
     key = "|".join([row_name, col_name] + list(value_names))
     side = train_csv + ".coo.npz"
     if cache and os.path.exists(side) and os.path.getmtime(side) >= os.path.getmtime(train_csv):
         z = np.load(side, allow_pickle=False)
         if str(z["key"]) == key:
             return {k: z[k] for k in z.files if k != "key"}
-    cols = [row_name, col_name] + list(value_names)
-    df = pd.read_csv(train_csv, usecols=cols, keep_default_na=False,
-                     dtype={row_name: str, col_name: str, **{v: np.float32 for v in value_names}})
-    vocab = read_vocab(vocab_txt)
-    out = {}
-    for name, src in (("row", row_name), ("col", col_name)):
-        vals = df[src].to_numpy()
-        if src.endswith("_id"):
-            ids = vals.astype(np.int64)
-            if ids.min() < 0 or ids.max() >= len(vocab):
-                raise ValueError("%s out of range [0, %d)" % (src, len(vocab)))
-            out[name] = ids.astype(np.int32)
-        else:
-            out[name] = lookup_ids(vals, vocab)
-    for v in value_names:
-        out[v] = df[v].to_numpy(np.float32)
+    out = {k: v.cpu().numpy() for k, v in ingest_csv(train_csv, vocab_txt, row_name, col_name, value_names, device).items()}
     if cache:
         try:
             np.savez(side, key=np.array(key), **out)

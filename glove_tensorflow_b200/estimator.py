@@ -12,7 +12,7 @@ def build_engine(params, head=HEAD, value_names=None):
     from .engine import GloveEngine
     value_names = value_names or (params["target_name"], params["weight_name"])
     coo = data_utils.load_interaction_csv(params["train_csv"], params["vocab_txt"], params["row_name"],
-                                          params["col_name"], value_names)
+                                          params["col_name"], value_names, device=params.get("device", "cuda:0"))
     vocab_size = data_utils.file_lines(params["vocab_txt"])
     reg_scale = params.get("reg_scale")
     if reg_scale is None:

@@ -224,6 +224,42 @@ int glove_topk_cosine_fp32(const float *table, int64_t V, int32_t d, int32_t pla
                            const int32_t *query_ids, int32_t n_queries, int32_t k, float *out_sim, int32_t *out_idx,
                            void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---- INGEST: interaction.csv text -> device COO -----------------------------------------------------
+ * Replaces tf.data make_csv_dataset(select_columns=...) [ref src/models/data_utils.py:4-26] and the per-step
+ * StaticHashTable(TextFileInitializer(vocab.txt), default_value=0) lookup [ref src/models/model_utils.py:121-127,
+ * src/models/estimator.py:26-28].  The caller uploads the file bytes (after the header record) chunk by chunk; every
+ * chunk must start at a record boundary.  RFC-4180 quoting, "" escapes, \r\n and blank lines are handled on the
+ * device; float columns are converted with ONE rounding, decimal text -> float32 (as DecodeCSV does), empty field -> 0. */
+enum { GLOVE_CSV_TOKEN = 0, GLOVE_CSV_INT = 1, GLOVE_CSV_FLOAT = 2 };
+typedef struct glove_csv_schema {
+    int32_t n_cols;      /* fields per record (from the header) */
+    int32_t column[4];   /* index of the row, col, colA, colB columns */
+    int32_t kind[4];     /* row / col: GLOVE_CSV_TOKEN (string resolved through the vocab table, missing -> 0) or
+                          * GLOVE_CSV_INT (a *_token_id column, checked against [0, n_vocab)); colA / colB: GLOVE_CSV_FLOAT */
+} glove_csv_schema;
+/* Device hash table over the lines of vocab.txt [ref src/data/text8.py:149-150]: vocab_bytes holds every line followed
+ * by one '\n', vocab_off[v] .. vocab_off[v+1]-1 delimit line v (n_vocab + 1 offsets).  A duplicated line keeps the
+ * lowest line number.  slots = glove_vocab_slots(n_vocab) int32 entries. */
+int64_t glove_vocab_slots(int64_t n_vocab);
+int glove_vocab_build(int32_t *table, int64_t slots, const uint8_t *vocab_bytes, const int64_t *vocab_off,
+                      int64_t n_vocab, void *stream);
+size_t glove_csv_workspace_bytes(int64_t nbytes);
+/* Pass 1 over a chunk (text: device, 16-byte aligned): number of non-empty TERMINATED records -> *n_records_host.
+ * Synchronises the stream.  glove_csv_parse on the same (text, nbytes, workspace) must follow. */
+int glove_csv_index(const uint8_t *text, int64_t nbytes, void *workspace, size_t workspace_bytes,
+                    int64_t *n_records_host, void *stream);
+/* Pass 2 + parse: fills row/col/colA/colB[0 .. *n_rows_host) in file order.  capacity >= n_records + 1 entries in
+ * row_ends (scratch) and the four outputs.  final_chunk: an unterminated last record counts; otherwise its bytes are
+ * left to the next chunk (*consumed_host = bytes of this chunk that were parsed).  first_record numbers the records
+ * in error messages.  Any malformed record fails the call (GLOVE_EINVAL, lowest record reported). Synchronises. */
+int glove_csv_parse(const uint8_t *text, int64_t nbytes, int32_t final_chunk, void *workspace, size_t workspace_bytes,
+                    const glove_csv_schema *schema, const int32_t *vocab_table, int64_t vocab_slots,
+                    const uint8_t *vocab_bytes, const int64_t *vocab_off, int64_t n_vocab, int64_t *row_ends,
+                    int32_t *row, int32_t *col, float *colA, float *colB, int64_t capacity, int64_t first_record,
+                    int64_t *n_rows_host, int64_t *consumed_host, void *stream);
+/* Host entry to the decimal -> float32 routine the parse kernel uses (one field, no blanks); for tests and tools. */
+int glove_parse_float32(const char *text, int32_t n, float *out);
+
 /* ---- HOST-buffer boundary (end to end): what a non-torch caller of the reference's training path would bind ----- */
 /* Copies K*B explicit triples from HOST memory (pinned recommended), builds the plan and runs K train steps, then
  * copies the K losses back to host_losses.  Device state (tables, scalars, plan, workspaces) stays caller-owned.

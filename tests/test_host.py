@@ -42,26 +42,89 @@ def test_init_params_writes_params_json_and_copies_vocab(tmp_path):
     assert p2["job_dir"].startswith(str(tmp_path / "j2") + "-20")    # datetime suffix %Y%m%d-%H%M%S
 
 
-def test_csv_ingest_resolves_tokens_like_the_hash_table(tmp_path):
+def test_csv_oracle_resolves_tokens_like_the_reference_preprocessor():
+    """Pins the ingest oracle on the reference's own preprocessor output: the *_token_id columns it wrote must be what
+    the vocab lookup of the token columns gives (tokens 'na' / 'null' / 'nan' included)."""
     import pandas as pd
-    from glove_tensorflow_b200 import data_utils
+    from oracle import csv_oracle
     csv, voc = os.path.join(GOLD, "interaction.csv"), os.path.join(GOLD, "vocab.txt")
     df = pd.read_csv(csv, keep_default_na=False)
-    coo = data_utils.load_interaction_csv(csv, voc, cache=False)
+    data, vocab = open(csv, "rb").read(), csv_oracle.read_vocab(voc)
+    coo = csv_oracle.parse_interaction_csv(data, vocab, "row_token", "col_token", ("glove_value", "glove_weight"))
     assert np.array_equal(coo["row"], df["row_token_id"]) and np.array_equal(coo["col"], df["col_token_id"])
-    np.testing.assert_allclose(coo["glove_value"], df["glove_value"].astype(np.float32))
-    by_id = data_utils.load_interaction_csv(csv, voc, "row_token_id", "col_token_id", ("value", "neg_weight"), cache=False)
+    np.testing.assert_allclose(coo["glove_value"], df["glove_value"].astype(np.float32), rtol=1e-7)
+    by_id = csv_oracle.parse_interaction_csv(data, vocab, "row_token_id", "col_token_id", ("value", "neg_weight"))
     assert np.array_equal(by_id["row"], coo["row"]) and by_id["value"].dtype == np.float32
-    assert data_utils.file_lines(voc) == len(data_utils.read_vocab(voc)) == 61
-    # out-of-vocabulary -> 0, the StaticHashTable default (ref model_utils.py:121-127)
-    assert list(data_utils.lookup_ids(["w5", "not-a-token", "nan"], data_utils.read_vocab(voc))) == \
-        [data_utils.read_vocab(voc).index("w5"), 0, data_utils.read_vocab(voc).index("nan")]
-    # sidecar cache round trip
+    # out-of-vocabulary -> 0, the StaticHashTable default (ref model_utils.py:121-127); quoting; blank lines; CRLF
+    tricky = b'a,row_token,col_token,glove_value,glove_weight\r\n1,w5,not-a-token,1.5,0.25\r\n\r\n2,"nan","w,x",-2e-3,\n'
+    t = csv_oracle.parse_interaction_csv(tricky, vocab + [b"w,x"], "row_token", "col_token", ("glove_value", "glove_weight"))
+    assert list(t["row"]) == [vocab.index(b"w5"), vocab.index(b"nan")] and list(t["col"]) == [0, len(vocab)]
+    assert list(t["glove_value"]) == [np.float32(1.5), np.float32(-2e-3)] and list(t["glove_weight"]) == [0.25, 0.0]
+
+
+def test_decimal_to_float32_is_correctly_rounded():
+    """The host entry of the kernels' decimal -> float32 routine against exact rational rounding (one rounding, like
+    DecodeCSV; NOT text -> double -> float)."""
+    import ctypes
+    import random
+    from fractions import Fraction
+    from glove_tensorflow_b200._lib import lib
+    from oracle.csv_oracle import f32_exact
+
+    def parse(s):
+        out = ctypes.c_float()
+        rc = lib.glove_parse_float32(s, len(s), ctypes.byref(out))
+        return rc, np.float32(out.value)
+    rng = random.Random(7)
+    cases = [b"0", b"-0", b"1", b"-1.5", b"3.5596246182566738", b"1e38", b"3.4028235e38", b"3.4028236e38", b"1e39", b"1e-45",
+             b"7e-46", b"7.1e-46", b"1.17549435e-38", b"1.1754942e-38", b"16777217", b"16777219", b"9007199791611905",
+             b"1E+5", b"+2.5e-3", b".5", b"5.", b"1e-64", b"1e-65", b"12345678901234567890", b"8388609.5", b"8388610.5",
+             b"inf", b"-Infinity", b"", b"0.000000000000000000000000000000000000000000001"]
+    for _ in range(20000):
+        cases.append(repr(rng.lognormvariate(0, 8) * rng.choice((1, -1))).encode())        # what pandas writes
+        f = np.array([rng.getrandbits(31)], np.uint32).view(np.float32)[0]                   # float32 midpoints
+        with np.errstate(invalid="ignore", over="ignore"):
+            g = np.nextafter(f, np.float32(np.inf))
+        if np.isfinite(f) and np.isfinite(g) and f > 0:
+            mid = (Fraction(float(f)) + Fraction(float(g))) / 2
+            digits = rng.choice((9, 12, 17, 19))
+            e = len(str(mid.numerator // mid.denominator)) - 1 if mid >= 1 else -len(str(mid.denominator // mid.numerator))
+            w = mid / Fraction(10) ** (e - digits + 1)
+            cases.append(b"%de%d" % (w.numerator // w.denominator + rng.choice((0, 0, 1)), e - digits + 1))
+        cases.append(b"%de%d" % (rng.randint(0, 10 ** rng.randint(1, 19) - 1), rng.randint(-70, 45)))
+    for s in cases:
+        rc, got = parse(s)
+        assert rc == 0, s
+        assert got.view(np.uint32) == f32_exact(s).view(np.uint32), s
+    assert np.isnan(parse(b"nan")[1])
+    for s in (b"abc", b"1e", b"--1", b"1.2.3", b"1 ", b" 1", b"e5", b".", b"+", b"infx", b"1e+"):
+        assert parse(s)[0] != 0, s
+    assert parse(b"1.00000005960464477539062500000")[0] != 0   # > 19 digits AND the tail decides: refused, never guessed
+
+
+def test_ingest_host_helpers(tmp_path):
+    from glove_tensorflow_b200 import _lib, data_utils
+    csv, voc = os.path.join(GOLD, "interaction.csv"), os.path.join(GOLD, "vocab.txt")
+    names, off = data_utils.read_header(csv)
+    assert names[:2] == ["row_token_id", "col_token_id"] and open(csv, "rb").read()[off - 1:off] == b"\n"
+    sc = data_utils.make_schema(names, "row_token", "col_token_id", ("glove_value", "glove_weight"))
+    assert sc.n_cols == 9 and list(sc.column) == [4, 1, 8, 7] and list(sc.kind) == [_lib.CSV_TOKEN, _lib.CSV_INT, _lib.CSV_FLOAT, _lib.CSV_FLOAT]
+    with pytest.raises(ValueError):
+        data_utils.make_schema(names, "row_token", "nope", ("glove_value", "glove_weight"))
+    blob, offs = data_utils.vocab_blob(voc)
+    vocab = data_utils.read_vocab(voc)
+    assert data_utils.file_lines(voc) == len(vocab) == len(offs) - 1 == 61
+    assert [blob[offs[i]:offs[i + 1] - 1].decode() for i in range(61)] == vocab
+    q = tmp_path / "q.csv"
+    q.write_bytes(b'"a ""x""","b\nc",d\r\n1,2,3\n')
+    assert data_utils.read_header(str(q)) == (['a "x"', "b\nc", "d"], 19)
+    # sidecar cache: a current <csv>.coo.npz with the same column key is returned without touching the GPU
     c2 = tmp_path / "i.csv"
-    c2.write_text(open(csv).read())
-    first = data_utils.load_interaction_csv(str(c2), voc)
-    again = data_utils.load_interaction_csv(str(c2), voc)
-    assert os.path.exists(str(c2) + ".coo.npz") and np.array_equal(first["row"], again["row"])
+    c2.write_text("x\n")
+    np.savez(str(c2) + ".coo.npz", key=np.array("r|c|a|b"), row=np.arange(3, dtype=np.int32), col=np.arange(3, dtype=np.int32),
+             a=np.ones(3, np.float32), b=np.ones(3, np.float32))
+    got = data_utils.load_interaction_csv(str(c2), voc, "r", "c", ("a", "b"))
+    assert list(got["row"]) == [0, 1, 2]
 
 
 def test_export_embeddings_format(tmp_path):
