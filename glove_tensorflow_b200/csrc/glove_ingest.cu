@@ -151,18 +151,15 @@ __global__ void __launch_bounds__(kTileThreads) row_ends_kernel(const uint8_t *_
     if (base >= nbytes) return;
     uint32_t par = before.flip;
     int64_t r = before.n_out;
-    int64_t last = -1;
 #pragma unroll
     for (int i = 0; i < kThreadBytes; ++i) {
         const uint8_t b = span_byte(v, i);
         if (b == '"') par ^= 1u;
         else if (b == '\n' && !par && !empty_record(text, base + i)) {
             if (r < capacity) row_ends[r] = base + i;
-            last = base + i;
             ++r;
         }
     }
-    if (last >= 0) atomicMax(&status->last_end, (long long)last);
     if (base + kThreadBytes >= nbytes) status->open_quote = par;
 }
 
@@ -210,12 +207,18 @@ struct Schema {
     int32_t sel[4];    // column index of row, col, colA, colB
     int32_t kind[4];   // GLOVE_CSV_TOKEN / _INT / _FLOAT
 };
-struct Field { int64_t b, e; int32_t esc; };   // content bytes [b, e); esc: contains "" escapes
+struct Field { int32_t b, e, esc; };   // content bytes [b, e); esc: contains "" escapes
+
+// the bytes of one record, addressed relative to its first byte (32-bit offsets keep the address arithmetic short)
+struct Bytes {
+    const uint8_t *p;
+    __device__ __forceinline__ uint8_t operator[](int i) const { return __ldg(p + i); }
+};
 
 // logical bytes of a field (collapses "" to ")
 struct FieldBytes {
-    const uint8_t *text;
-    int64_t i, e;
+    const Bytes &text;
+    int i, e;
     bool esc;
     __device__ __forceinline__ bool next(uint8_t &c) {
         if (i >= e) return false;
@@ -225,10 +228,10 @@ struct FieldBytes {
     }
 };
 
-__device__ int32_t lookup_token(const uint8_t *__restrict__ text, const Field &f, const int32_t *__restrict__ table,
+__device__ int32_t lookup_token(const Bytes &text, const Field &f, const int32_t *__restrict__ table,
                                 int64_t slots, const uint8_t *__restrict__ vb, const int64_t *__restrict__ voff) {
     uint64_t h = kFnvSeed;
-    int64_t len = 0;
+    int len = 0;
     {
         FieldBytes it = {text, f.b, f.e, f.esc != 0};
         uint8_t c;
@@ -242,7 +245,7 @@ __device__ int32_t lookup_token(const uint8_t *__restrict__ text, const Field &f
         if (voff[v + 1] - 1 - o0 == len) {
             FieldBytes it = {text, f.b, f.e, f.esc != 0};
             uint8_t c;
-            int64_t k = 0;
+            int k = 0;
             bool same = true;
             while (same && it.next(c)) same = vb[o0 + k++] == c;
             if (same) return v;
@@ -255,7 +258,7 @@ __device__ __forceinline__ void report(CsvStatus *st, int64_t record, int code) 
     atomicMin(&st->first_error, ((unsigned long long)record << 8) | (unsigned)code);
 }
 
-__global__ void __launch_bounds__(128) parse_rows_kernel(const uint8_t *__restrict__ text, int64_t nbytes, int32_t final_chunk,
+__global__ void __launch_bounds__(128) parse_rows_kernel(const uint8_t *__restrict__ text_bytes, int64_t nbytes, int32_t final_chunk,
                                                          const int64_t *__restrict__ row_ends, CsvStatus *st, Schema sc,
                                                          const int32_t *__restrict__ table, int64_t slots,
                                                          const uint8_t *__restrict__ vb, const int64_t *__restrict__ voff,
@@ -264,16 +267,22 @@ __global__ void __launch_bounds__(128) parse_rows_kernel(const uint8_t *__restri
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t n_terms = st->n_terms;
     if (r > n_terms || r >= capacity || (r == n_terms && !final_chunk)) return;
-    int64_t pos = r ? row_ends[r - 1] + 1 : 0;
-    int64_t end = r < n_terms ? row_ends[r] : nbytes;
+    int64_t pos0 = r ? row_ends[r - 1] + 1 : 0;
+    int64_t end0 = r < n_terms ? row_ends[r] : nbytes;
+    if (r == n_terms - 1) st->last_end = end0;
     // skipped empty records in front of this one
-    while (pos < end && (text[pos] == '\n' || (text[pos] == '\r' && pos + 1 < end && text[pos + 1] == '\n'))) ++pos;
-    if (end > pos && text[end - 1] == '\r') --end;
+    while (pos0 < end0 && (text_bytes[pos0] == '\n' || (text_bytes[pos0] == '\r' && pos0 + 1 < end0 && text_bytes[pos0 + 1] == '\n')))
+        ++pos0;
+    if (end0 > pos0 && text_bytes[end0 - 1] == '\r') --end0;
     if (r == n_terms) {              // unterminated last record of the file
-        if (pos >= end) return;
+        if (pos0 >= end0) return;
         if (st->open_quote) { report(st, record0 + r, CSV_EQUOTE); return; }
         st->tail_valid = 1;
     }
+    if (end0 - pos0 > 0x3fffffff) { report(st, record0 + r, CSV_EFIELDS); return; }
+    const Bytes text = {text_bytes + pos0};
+    int pos = 0;
+    const int end = (int)(end0 - pos0);
     Field sel[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) sel[c] = Field{0, 0, 0};
@@ -320,7 +329,8 @@ __global__ void __launch_bounds__(128) parse_rows_kernel(const uint8_t *__restri
         if (sc.kind[c] == GLOVE_CSV_TOKEN) {
             ids[c & 1] = lookup_token(text, f, table, slots, vb, voff);
         } else if (sc.kind[c] == GLOVE_CSV_INT) {
-            int64_t i = f.b, v = 0;
+            int i = f.b;
+            int64_t v = 0;
             bool neg = false, ok = f.e > f.b && !f.esc;
             if (ok && (text[i] == '-' || text[i] == '+')) { neg = text[i] == '-'; ++i; ok = i < f.e; }
             for (; ok && i < f.e; ++i) {
@@ -334,8 +344,8 @@ __global__ void __launch_bounds__(128) parse_rows_kernel(const uint8_t *__restri
             ids[c & 1] = (int32_t)v;
         } else {
             uint32_t bits;
-            const uint8_t *p = text + f.b;
-            const int rc = f.esc ? (int)STRTOF_BAD : parse_f32([p](int i) { return (int)p[i]; }, (int)(f.e - f.b), bits);
+            const Bytes fb = {text.p + f.b};
+            const int rc = f.esc ? (int)STRTOF_BAD : parse_f32([fb](int i) { return (int)fb[i]; }, f.e - f.b, bits);
             if (rc != STRTOF_OK) { report(st, record0 + r, rc == STRTOF_TOO_LONG ? CSV_EDIGITS : CSV_EFLOAT); return; }
             vals[c & 1] = __uint_as_float(bits);
         }
