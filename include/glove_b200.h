@@ -260,6 +260,32 @@ int glove_csv_parse(const uint8_t *text, int64_t nbytes, int32_t final_chunk, vo
 /* Host entry to the decimal -> float32 routine the parse kernel uses (one field, no blanks); for tests and tools. */
 int glove_parse_float32(const char *text, int32_t n, float *out);
 
+/* ---- PREPROCESS: token-id stream -> symmetric co-occurrence table with the GloVe columns ------------
+ * create_interaction_dataframe + create_glove_dataframe of the reference preprocessor [ref src/data/text8.py:84-139].
+ * Partial tables are (keys u64[n] sorted unique, agg i64[2n] = {count, numer} per key) with numer = sum over the pairs of
+ * lcm(1..context)/distance, i.e. the reference's sum of 1/distance carried exactly.  All pointers are device memory.
+ * workspace: glove_cooc_workspace_bytes(n_items), n_items = the largest of n_positions*context (chunk), n_a+n_b (merge),
+ * 2*n (finish).  Every call synchronises the stream. */
+size_t glove_cooc_workspace_bytes(int64_t n_items);
+/* Pairs (id[p], id[p+k]), p in [0, n_positions), k = 1..context, p + k < n_tokens (token_ids holds n_tokens >= n_positions
+ * entries: the chunk plus its look-ahead), equal ids dropped [ref text8.py:90-95,98-102]. */
+int glove_cooc_chunk(const int32_t *token_ids, int64_t n_positions, int64_t n_tokens, int32_t V, int32_t context,
+                     void *workspace, size_t workspace_bytes, uint64_t *out_keys, int64_t *out_agg, int64_t capacity,
+                     int64_t *n_unique_host, void *stream);
+/* Union of two partial tables, summed per key.  capacity >= n_a + n_b. */
+int glove_cooc_merge(const uint64_t *keys_a, const int64_t *agg_a, int64_t n_a, const uint64_t *keys_b, const int64_t *agg_b,
+                     int64_t n_b, int32_t V, void *workspace, size_t workspace_bytes, uint64_t *out_keys, int64_t *out_agg,
+                     int64_t capacity, int64_t *n_unique_host, void *stream);
+/* Union with the transposed table [ref text8.py:105-110], count >= count_min [ref text8.py:129], columns
+ * [ref text8.py:113-117,130-139]: value = numer / lcm (one rounding), neg_weight = vocab_count[row] * (vocab_count[col] /
+ * total_tokens), glove_weight = clip((count/100)^0.75, 0, 1), glove_value = log(value).  Records come out in the order
+ * of a keyed 64-bit hash of (row, col) (the reference uses Python's salted hash() of the token pair: a random order).
+ * *n_out_host is set even when it exceeds capacity (the call then fails and can be repeated with larger outputs). */
+int glove_cooc_finish(const uint64_t *keys, const int64_t *agg, int64_t n, int32_t V, int32_t context, int64_t count_min,
+                      const int64_t *vocab_count, int64_t total_tokens, uint64_t order_key, void *workspace,
+                      size_t workspace_bytes, int32_t *row, int32_t *col, int64_t *count, double *value, double *neg_weight,
+                      double *glove_weight, double *glove_value, int64_t capacity, int64_t *n_out_host, void *stream);
+
 /* ---- HOST-buffer boundary (end to end): what a non-torch caller of the reference's training path would bind ----- */
 /* Copies K*B explicit triples from HOST memory (pinned recommended), builds the plan and runs K train steps, then
  * copies the K losses back to host_losses.  Device state (tables, scalars, plan, workspaces) stays caller-owned.

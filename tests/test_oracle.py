@@ -217,3 +217,37 @@ def test_eval_metrics_definition():
     w, y = coo["weight"].astype(np.float64), coo["target"].astype(np.float64)
     assert abs(m["average_loss"] - np.sum(w * (z - y) ** 2) / np.sum(w)) < 1e-9
     assert abs(m["label/mean"] - np.sum(w * y) / np.sum(w)) < 1e-9
+
+
+def test_cooc_oracle_is_pinned_on_the_reference_preprocessor_output():
+    """oracle/cooc_oracle.py against tests/golden/text8_small (written by the reference's src/data/text8.py, unmodified):
+    ids and counts exact, float64 columns to 1e-15 (the reference evaluates them through pandas/numexpr)."""
+    import os
+    import pandas as pd
+    from oracle import cooc_oracle
+    gold = os.path.join(os.path.dirname(__file__), "golden", "text8_small")
+    voc = pd.read_csv(os.path.join(gold, "vocab.csv"), keep_default_na=False)
+    tokens = open(os.path.join(gold, "corpus.txt")).read().split()
+    ids = cooc_oracle.token_ids(tokens, list(voc["token"]))
+    got = cooc_oracle.interaction_table(ids, voc["count"].to_numpy(), 5, 10)
+    ref = pd.read_csv(os.path.join(gold, "interaction.csv"), keep_default_na=False)
+    ref = ref.sort_values(["row_token_id", "col_token_id"]).reset_index(drop=True)
+    assert len(got) == len(ref) == 2746
+    for k in ("row_token_id", "col_token_id", "count"):
+        assert np.array_equal(got[k].to_numpy(), ref[k].to_numpy()), k
+    for k in ("value", "neg_weight", "glove_weight", "glove_value"):
+        np.testing.assert_allclose(got[k].to_numpy(), ref[k].to_numpy(), rtol=1e-15, atol=0, err_msg=k)
+
+
+def test_host_vocabulary_matches_the_reference_preprocessor_output():
+    import os
+    import pandas as pd
+    from glove_tensorflow_b200 import text8
+    gold = os.path.join(os.path.dirname(__file__), "golden", "text8_small")
+    ref = pd.read_csv(os.path.join(gold, "vocab.csv"), keep_default_na=False)
+    tokens = open(os.path.join(gold, "corpus.txt")).read().split()
+    got = text8.create_vocabulary(tokens, 60, 0.9)
+    assert list(got["token"]) == list(ref["token"]) and list(got["count"]) == list(ref["count"])
+    np.testing.assert_allclose(got["proportion"], ref["proportion"], rtol=1e-15)
+    ids = text8.token_ids(tokens, got["token"].to_numpy())
+    assert ids.dtype == np.int32 and ids.max() == len(got) - 1 and np.bincount(ids)[0] > got["count"][0]   # unknown -> row 0
