@@ -103,6 +103,7 @@ SIGNATURES = {
                                          c_size, c_void, c_void, c_void, c_void, c_void, c_void, c_void, c_i64,
                                          ctypes.POINTER(c_i64), c_void]),
     "glove_host_staging_bytes": (c_size, [c_i32, c_i32]),
+    "glove_host_plan_bytes": (c_size, [c_i32, c_i32]),
     "glove_train_steps_host": (ctypes.c_int, [ctypes.POINTER(StepArgs), c_void, c_void, c_size, c_void, c_size, c_void,
                                               c_void, c_void, c_void, c_i32, c_void, c_void]),
 }

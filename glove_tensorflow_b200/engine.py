@@ -536,17 +536,21 @@ class GloveEngine:
         return tuple(ms)
 
     def train_steps_host(self, host_row, host_col, host_a, host_b, host_losses):
-        """End-to-end boundary: K = plan_steps TRAIN steps on K*B explicit triples held in HOST (pinned) tensors;
-        H2D copies, plan build, steps and the D2H loss read all happen inside the call (glove_train_steps_host)."""
+        """End-to-end boundary: n * plan_steps TRAIN steps on the explicit triples held in HOST (pinned) tensors
+        (numel = steps * B); H2D copies, plan builds, steps and the D2H loss read all happen inside ONE C-ABI call
+        (glove_train_steps_host), pipelined chunk against chunk."""
         if getattr(self, "_host_staging", None) is None:
             self._host_staging = torch.empty(lib.glove_host_staging_bytes(self.K, self.B), dtype=torch.uint8, device=self.device)
-        assert host_row.numel() == self.K * self.B and not host_row.is_cuda
+            self._host_plans = torch.empty(lib.glove_host_plan_bytes(self.K, self.B), dtype=torch.uint8, device=self.device)
+        steps = host_row.numel() // self.B
+        assert steps * self.B == host_row.numel() and steps % self.K == 0 and not host_row.is_cuda
+        assert host_losses.numel() >= steps
         self._join_side()
-        check(lib.glove_train_steps_host(ctypes.byref(self._args[0]), _ptr(self.plans[0]), _ptr(self.prep_ws),
+        check(lib.glove_train_steps_host(ctypes.byref(self._args[0]), _ptr(self._host_plans), _ptr(self.prep_ws),
                                          self.prep_ws.numel(), _ptr(self._host_staging), self._host_staging.numel(),
-                                         _ptr(host_row), _ptr(host_col), _ptr(host_a), _ptr(host_b), self.K,
+                                         _ptr(host_row), _ptr(host_col), _ptr(host_a), _ptr(host_b), steps,
                                          _ptr(host_losses), _stream()), "glove_train_steps_host")
-        self.host_step += self.K
+        self.host_step += steps
         self.plan_first = [None, None]
 
     def train_chunk_from_host(self, host_row, host_col, host_a, host_b):

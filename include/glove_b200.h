@@ -287,10 +287,14 @@ int glove_cooc_finish(const uint64_t *keys, const int64_t *agg, int64_t n, int32
                       double *glove_weight, double *glove_value, int64_t capacity, int64_t *n_out_host, void *stream);
 
 /* ---- HOST-buffer boundary (end to end): what a non-torch caller of the reference's training path would bind ----- */
-/* Copies K*B explicit triples from HOST memory (pinned recommended), builds the plan and runs K train steps, then
- * copies the K losses back to host_losses.  Device state (tables, scalars, plan, workspaces) stays caller-owned.
- * staging: device scratch of glove_host_staging_bytes(K, B). Synchronises the stream before returning. */
-size_t glove_host_staging_bytes(int32_t K, int32_t B);
+/* Runs K TRAIN steps (K a multiple of args->plan_K, at most 4096) on K*B explicit triples held in HOST memory (pinned
+ * recommended) and copies the K losses back to host_losses.  Internally a pipeline over the chunks of plan_K steps:
+ * H2D + plan construction of chunk c+1 on a helper stream while the steps of chunk c run on `stream`, and (exact-replay
+ * Adam) the catch-up of step s+1 on a second helper stream while step s runs.  Device state (tables, scalars, plans,
+ * workspaces) stays caller-owned: `plan` holds glove_host_plan_bytes(plan_K, B) bytes (two plans), `staging`
+ * glove_host_staging_bytes(plan_K, B).  Synchronises the stream on entry and before returning. */
+size_t glove_host_staging_bytes(int32_t plan_K, int32_t B);
+size_t glove_host_plan_bytes(int32_t plan_K, int32_t B);
 int glove_train_steps_host(const glove_step_args *args, void *plan, void *prepare_ws, size_t prepare_ws_bytes,
                            void *staging, size_t staging_bytes, const int32_t *host_row, const int32_t *host_col,
                            const float *host_colA, const float *host_colB, int32_t K, float *host_losses,

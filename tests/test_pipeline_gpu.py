@@ -126,3 +126,41 @@ def test_host_entry_point_matches_device_path():
     assert np.max(np.abs(got - want) / np.abs(want)) < 1e-5
     state = eng.get_state()
     assert np.max(np.abs(state["R"] - ref.R)) / np.max(np.abs(ref.R)) < 1e-5
+
+
+def test_host_entry_pipelined_call_is_bit_identical_to_chunked_calls():
+    """One glove_train_steps_host call over 6 plan chunks (H2D + plan of chunk c+1 and the Adam catch-up overlap the
+    steps in flight) == 6 calls of one chunk each == the device-resident path, bit for bit; and == the oracle to 1e-5."""
+    import torch
+    from glove_tensorflow_b200.engine import GloveEngine
+    V, d, n, B, K, chunks = 3000, 40, 6 * 5 * 512, 512, 5, 6
+    coo = make_coo(V, n, 31)
+    st = o.init_state(V, d, 32)
+    pin = {k: torch.from_numpy(coo[k].copy()).pin_memory() for k in ("row", "col", "target", "weight")}
+
+    def run(calls):
+        eng = GloveEngine(V, d, learning_rate=0.01, batch_size=B, plan_steps=K, max_steps=64)
+        eng.load_state(st.R, st.C, st.rb, st.cb, st.g)
+        per = chunks // calls * K * B
+        losses = []
+        for c in range(calls):
+            hl = torch.empty(per // B, dtype=torch.float32).pin_memory()
+            eng.train_steps_host(*[pin[k][c * per:(c + 1) * per] for k in ("row", "col", "target", "weight")], hl)
+            losses.append(hl.numpy().copy())
+        return np.concatenate(losses), eng.get_state()
+    l1, s1 = run(1)
+    l6, s6 = run(6)
+    l2, s2 = run(2)
+    assert np.array_equal(l1, l6) and np.array_equal(l1, l2)
+    for k in ("R", "C", "rb", "cb"):
+        assert np.array_equal(s1[k], s6[k]) and np.array_equal(s1[k], s2[k]), k
+    dev = GloveEngine(V, d, learning_rate=0.01, batch_size=B, plan_steps=K, max_steps=64)
+    dev.load_state(st.R, st.C, st.rb, st.cb, st.g)
+    dev.set_coo(coo["row"], coo["col"], coo["target"], coo["weight"])
+    dev.set_batches(np.arange(chunks * K * B).reshape(chunks * K, B))
+    ld = dev.train(chunks * K)
+    assert np.array_equal(ld, l1) and np.array_equal(dev.get_state()["R"], s1["R"])
+    ref = st.copy()
+    want = np.array(o.train(ref, coo, np.arange(chunks * K * B).reshape(chunks * K, B), learning_rate=0.01))
+    assert np.max(np.abs(l1 - want) / np.abs(want)) < 1e-5
+    assert np.max(np.abs(s1["R"] - ref.R)) / np.max(np.abs(ref.R)) < 1e-5
