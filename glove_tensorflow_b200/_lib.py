@@ -94,6 +94,11 @@ SIGNATURES = {
                                        c_void, c_void, c_i64, c_void, c_void, c_void, c_void, c_void, c_i64, c_i64,
                                        ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), c_void]),
     "glove_parse_float32": (ctypes.c_int, [ctypes.c_char_p, c_i32, ctypes.POINTER(c_f32)]),
+    "glove_tokens_workspace_bytes": (c_size, [c_i64, c_i64]),
+    "glove_tokens_scan": (ctypes.c_int, [c_void, c_i64, c_void, c_size, c_void, c_void, c_i64, ctypes.POINTER(c_i64), c_void]),
+    "glove_tokens_count": (ctypes.c_int, [c_void, c_i64, c_void, c_i64, c_void, c_size, c_void, c_void, c_void, c_i64,
+                                          ctypes.POINTER(c_i64), c_void]),
+    "glove_tokens_lookup": (ctypes.c_int, [c_void, c_void, c_void, c_i64, c_void, c_i64, c_void, c_void, c_void, c_void]),
     "glove_cooc_workspace_bytes": (c_size, [c_i64]),
     "glove_cooc_chunk": (ctypes.c_int, [c_void, c_i64, c_i64, c_i32, c_i32, c_void, c_size, c_void, c_void, c_i64,
                                         ctypes.POINTER(c_i64), c_void]),

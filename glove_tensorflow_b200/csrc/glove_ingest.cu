@@ -17,6 +17,7 @@
 //
 // HBM-bound byte work: no tensor cores.  Errors never fall back to the host: the lowest offending record is reported.
 #include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
 
 #include "glove_common.cuh"
 #include "glove_strtof.cuh"
@@ -356,6 +357,130 @@ __global__ void __launch_bounds__(128) parse_rows_kernel(const uint8_t *__restri
     out_b[r] = vals[1];
 }
 
+
+// ---- corpus text -> token stream (front half of the preprocessor) -------------------------------------
+// str.split() of the reference [ref src/data/text8.py:47]: tokens are maximal runs of non-whitespace.  ASCII whitespace
+// only (space, \t \n \v \f \r, 0x1c-0x1f); the UTF-8 encodings of the other Unicode separators str.split() knows are
+// detected and refused, never mis-split.
+__device__ __forceinline__ bool is_space(uint8_t b) { return b == 0x20 || (b >= 0x09 && b <= 0x0d) || (b >= 0x1c && b <= 0x1f); }
+__device__ __forceinline__ bool unicode_space_at(const uint8_t *t, int64_t i, int64_t n) {
+    const uint8_t b = t[i];
+    if (b == 0xc2) return i + 1 < n && (t[i + 1] == 0x85 || t[i + 1] == 0xa0);
+    if (i + 2 >= n) return false;
+    const uint8_t c = t[i + 1], d = t[i + 2];
+    if (b == 0xe1) return c == 0x9a && d == 0x80;
+    if (b == 0xe2) return (c == 0x80 && ((d >= 0x80 && d <= 0x8a) || d == 0xa8 || d == 0xa9 || d == 0xaf)) || (c == 0x81 && d == 0x9f);
+    if (b == 0xe3) return c == 0x80 && d == 0x80;
+    return false;
+}
+__global__ void __launch_bounds__(256) token_flags_kernel(const uint8_t *__restrict__ text, int64_t nbytes, uint8_t *flags,
+                                                          int32_t *bad) {
+    const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    if (i0 >= nbytes) return;
+    uint8_t b[17];
+    b[0] = i0 ? text[i0 - 1] : (uint8_t)' ';
+#pragma unroll
+    for (int k = 0; k < 16; ++k) b[k + 1] = i0 + k < nbytes ? text[i0 + k] : (uint8_t)' ';
+    uint8_t f[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        f[k] = (i0 + k < nbytes) && !is_space(b[k + 1]) && is_space(b[k]);
+        if (b[k + 1] >= 0xc2 && i0 + k < nbytes && unicode_space_at(text, i0 + k, nbytes)) *bad = 1;
+    }
+    if (i0 + 16 <= nbytes) *(uint4 *)(flags + i0) = *(const uint4 *)f;
+    else
+        for (int k = 0; i0 + k < nbytes; ++k) flags[i0 + k] = f[k];
+}
+// length and 64-bit hash of the token that starts at starts[i]
+__global__ void __launch_bounds__(256) token_hash_kernel(const uint8_t *__restrict__ text, int64_t nbytes,
+                                                         const int64_t *__restrict__ starts, int64_t n, int32_t *lens,
+                                                         uint64_t *hash, uint32_t *idx) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t s = starts[i];
+    uint64_t h = kFnvSeed;
+    int64_t e = s;
+    while (e < nbytes && !is_space(text[e])) h = fnv1a(h, text[e++]);
+    lens[i] = (int32_t)(e - s);
+    if (hash) {
+        h ^= h >> 29; h *= 0xbf58476d1ce4e5b9ull; h ^= h >> 32;
+        hash[i] = h;
+        idx[i] = (uint32_t)i;
+    }
+}
+// equal hashes must be equal tokens (adjacent elements of the sorted order are compared: equality is transitive)
+__global__ void __launch_bounds__(256) token_verify_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__ starts,
+                                                           const int32_t *__restrict__ lens, const uint64_t *__restrict__ hash,
+                                                           const uint32_t *__restrict__ idx, int64_t n, int32_t *bad) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 1 || i >= n || hash[i] != hash[i - 1]) return;
+    const uint32_t a = idx[i], b = idx[i - 1];
+    bool same = lens[a] == lens[b];
+    for (int k = 0; same && k < lens[a]; ++k) same = text[starts[a] + k] == text[starts[b] + k];
+    if (!same) *bad = 1;
+}
+__global__ void __launch_bounds__(256) token_runs_kernel(const uint32_t *__restrict__ idx, const int64_t *__restrict__ starts,
+                                                         const int32_t *__restrict__ lens, const int32_t *__restrict__ run_len,
+                                                         const int32_t *__restrict__ run_off, int64_t n_runs,
+                                                         int64_t *first_start, int32_t *first_len, int64_t *count) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_runs) return;
+    const uint32_t head = idx[run_off[r]];      // stable sort: the first element of a run is the first occurrence
+    first_start[r] = starts[head];
+    first_len[r] = lens[head];
+    count[r] = run_len[r];
+}
+__global__ void __launch_bounds__(256) token_lookup_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__ starts,
+                                                           const int32_t *__restrict__ lens, int64_t n,
+                                                           const int32_t *__restrict__ table, int64_t slots,
+                                                           const uint8_t *__restrict__ vb, const int64_t *__restrict__ voff,
+                                                           int32_t *ids) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Bytes t = {text + starts[i]};
+    const Field f = {0, lens[i], 0};
+    ids[i] = lookup_token(t, f, table, slots, vb, voff);
+}
+
+struct TokWs {
+    uint8_t *flags;
+    uint64_t *hash[2];
+    uint32_t *idx[2];
+    int32_t *run_len, *run_off;
+    long long *n_out;
+    int32_t *bad;
+    void *cub_temp;
+    size_t cub_bytes, bytes;
+};
+static TokWs tok_ws_view(void *base, int64_t nbytes, int64_t n_tokens) {
+    TokWs w;
+    char *p = (char *)base;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { char *r = p ? p + off : nullptr; off += align_up(bytes); return r; };
+    const int64_t n = n_tokens < 1 ? 1 : n_tokens;
+    w.flags = (uint8_t *)take(nbytes + 16);
+    for (int i = 0; i < 2; ++i) w.hash[i] = (uint64_t *)take(8 * n);
+    for (int i = 0; i < 2; ++i) w.idx[i] = (uint32_t *)take(4 * n);
+    w.run_len = (int32_t *)take(4 * n);
+    w.run_off = (int32_t *)take(4 * n);
+    w.n_out = (long long *)take(8);
+    w.bad = (int32_t *)take(4);
+    size_t a = 0, b = 0, c = 0, d = 0, e = 0;
+    cub::DeviceReduce::Sum(nullptr, e, (uint8_t *)nullptr, (long long *)nullptr, (int)(nbytes < 1 ? 1 : nbytes));
+    cub::DeviceSelect::Flagged(nullptr, a, thrust::counting_iterator<int64_t>(0), (uint8_t *)nullptr, (int64_t *)nullptr,
+                               (long long *)nullptr, (int)(nbytes < 1 ? 1 : nbytes));
+    cub::DeviceRadixSort::SortPairs(nullptr, b, (uint64_t *)nullptr, (uint64_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, (int)n);
+    cub::DeviceRunLengthEncode::Encode(nullptr, c, (uint64_t *)nullptr, (uint64_t *)nullptr, (int32_t *)nullptr, (long long *)nullptr, (int)n);
+    cub::DeviceScan::ExclusiveSum(nullptr, d, (int32_t *)nullptr, (int32_t *)nullptr, (int)n);
+    w.cub_bytes = a > b ? a : b;
+    if (c > w.cub_bytes) w.cub_bytes = c;
+    if (d > w.cub_bytes) w.cub_bytes = d;
+    if (e > w.cub_bytes) w.cub_bytes = e;
+    w.cub_temp = take(w.cub_bytes);
+    w.bytes = off;
+    return w;
+}
+
 }  // namespace glove
 
 using namespace glove;
@@ -454,6 +579,100 @@ int glove_csv_parse(const uint8_t *text, int64_t nbytes, int32_t final_chunk, vo
         return set_error(GLOVE_EINVAL, "interaction csv: unterminated quoted field at end of file");
     *n_rows_host = st.n_terms + st.tail_valid;
     *consumed_host = final_chunk ? nbytes : st.last_end + 1;
+    return GLOVE_OK;
+}
+
+size_t glove_tokens_workspace_bytes(int64_t nbytes, int64_t n_tokens) {
+    return tok_ws_view(nullptr, nbytes < 1 ? 1 : nbytes, n_tokens).bytes;
+}
+
+int glove_tokens_scan(const uint8_t *text, int64_t nbytes, void *workspace, size_t workspace_bytes, int64_t *starts,
+                      int32_t *lens, int64_t capacity, int64_t *n_tokens_host, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    GLOVE_REQUIRE(text && workspace && starts && lens && n_tokens_host, "glove_tokens_scan: null pointer");
+    GLOVE_REQUIRE(nbytes > 0 && nbytes < (1ll << 31), "glove_tokens_scan: chunk must hold 1 .. 2^31-1 bytes");
+    const TokWs w = tok_ws_view(workspace, nbytes, 0);
+    if (workspace_bytes < w.bytes)
+        return set_error(GLOVE_EWORKSPACE, "glove_tokens_scan: workspace %zu < required %zu", workspace_bytes, w.bytes);
+    GLOVE_CHECK_CUDA(cudaMemsetAsync(w.bad, 0, 4, stream));
+    token_flags_kernel<<<(unsigned)((nbytes + 4095) / 4096), 256, 0, stream>>>(text, nbytes, w.flags, w.bad);
+    GLOVE_CHECK_LAUNCH();
+    size_t tb = w.cub_bytes;
+    // capacity is checked after the count is known: select into the caller's buffer only if it fits
+    long long n = 0;
+    {
+        // first pass: count (sum of the flags) -- cheap, and it lets us refuse before writing past `capacity`
+        size_t rb = w.cub_bytes;
+        GLOVE_CHECK_CUDA(cub::DeviceReduce::Sum(w.cub_temp, rb, w.flags, w.n_out, (int)nbytes, stream));
+        int32_t bad = 0;
+        GLOVE_CHECK_CUDA(cudaMemcpyAsync(&bad, w.bad, 4, cudaMemcpyDeviceToHost, stream));
+        GLOVE_CHECK_CUDA(cudaMemcpyAsync(&n, w.n_out, 8, cudaMemcpyDeviceToHost, stream));
+        GLOVE_CHECK_CUDA(cudaStreamSynchronize(stream));
+        if (bad) return set_error(GLOVE_EUNSUPPORTED, "corpus holds non-ASCII Unicode whitespace, which str.split() would split on");
+    }
+    *n_tokens_host = n;
+    if (n > capacity) return set_error(GLOVE_EINVAL, "glove_tokens_scan: %lld tokens > capacity %lld", n, (long long)capacity);
+    if (n == 0) return GLOVE_OK;
+    GLOVE_CHECK_CUDA(cub::DeviceSelect::Flagged(w.cub_temp, tb, thrust::counting_iterator<int64_t>(0), w.flags, starts, w.n_out,
+                                                (int)nbytes, stream));
+    token_hash_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(text, nbytes, starts, n, lens, nullptr, nullptr);
+    GLOVE_CHECK_LAUNCH();
+    GLOVE_CHECK_CUDA(cudaStreamSynchronize(stream));
+    return GLOVE_OK;
+}
+
+int glove_tokens_count(const uint8_t *text, int64_t nbytes, const int64_t *starts, int64_t n_tokens, void *workspace,
+                       size_t workspace_bytes, int64_t *first_start, int32_t *first_len, int64_t *count, int64_t capacity,
+                       int64_t *n_distinct_host, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    GLOVE_REQUIRE(text && starts && workspace && first_start && first_len && count && n_distinct_host,
+                  "glove_tokens_count: null pointer");
+    GLOVE_REQUIRE(n_tokens > 0 && n_tokens < (1ll << 31) && nbytes > 0, "glove_tokens_count: bad sizes");
+    const TokWs w = tok_ws_view(workspace, nbytes, n_tokens);
+    if (workspace_bytes < w.bytes)
+        return set_error(GLOVE_EWORKSPACE, "glove_tokens_count: workspace %zu < required %zu", workspace_bytes, w.bytes);
+    const unsigned g = (unsigned)((n_tokens + 255) / 256);
+    int32_t *lens = w.run_off;   // token lengths live here until the run offsets are needed
+    GLOVE_CHECK_CUDA(cudaMemsetAsync(w.bad, 0, 4, stream));
+    token_hash_kernel<<<g, 256, 0, stream>>>(text, nbytes, starts, n_tokens, lens, w.hash[0], w.idx[0]);
+    GLOVE_CHECK_LAUNCH();
+    size_t tb = w.cub_bytes;
+    GLOVE_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_temp, tb, w.hash[0], w.hash[1], w.idx[0], w.idx[1], (int)n_tokens, 0, 64,
+                                                     stream));
+    token_verify_kernel<<<g, 256, 0, stream>>>(text, starts, lens, w.hash[1], w.idx[1], n_tokens, w.bad);
+    GLOVE_CHECK_LAUNCH();
+    tb = w.cub_bytes;
+    GLOVE_CHECK_CUDA(cub::DeviceRunLengthEncode::Encode(w.cub_temp, tb, w.hash[1], w.hash[0], w.run_len, w.n_out, (int)n_tokens,
+                                                        stream));
+    long long runs = 0;
+    int32_t bad = 0;
+    GLOVE_CHECK_CUDA(cudaMemcpyAsync(&bad, w.bad, 4, cudaMemcpyDeviceToHost, stream));
+    GLOVE_CHECK_CUDA(cudaMemcpyAsync(&runs, w.n_out, 8, cudaMemcpyDeviceToHost, stream));
+    GLOVE_CHECK_CUDA(cudaStreamSynchronize(stream));
+    if (bad) return set_error(GLOVE_EUNSUPPORTED, "glove_tokens_count: two different tokens share a 64-bit hash");
+    *n_distinct_host = runs;
+    if (runs > capacity)
+        return set_error(GLOVE_EINVAL, "glove_tokens_count: %lld distinct tokens > capacity %lld", runs, (long long)capacity);
+    // first occurrence of every run: the lengths move to idx[0] (free now) so that run_off can hold the offsets
+    int32_t *lens2 = (int32_t *)w.idx[0];
+    GLOVE_CHECK_CUDA(cudaMemcpyAsync(lens2, lens, 4 * n_tokens, cudaMemcpyDeviceToDevice, stream));
+    tb = w.cub_bytes;
+    GLOVE_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(w.cub_temp, tb, w.run_len, w.run_off, (int)runs, stream));
+    token_runs_kernel<<<(unsigned)((runs + 255) / 256), 256, 0, stream>>>(w.idx[1], starts, lens2, w.run_len, w.run_off, runs,
+                                                                           first_start, first_len, count);
+    GLOVE_CHECK_LAUNCH();
+    GLOVE_CHECK_CUDA(cudaStreamSynchronize(stream));
+    return GLOVE_OK;
+}
+
+int glove_tokens_lookup(const uint8_t *text, const int64_t *starts, const int32_t *lens, int64_t n_tokens,
+                        const int32_t *vocab_table, int64_t vocab_slots, const uint8_t *vocab_bytes, const int64_t *vocab_off,
+                        int32_t *ids, void *stream) {
+    GLOVE_REQUIRE(text && starts && lens && vocab_table && vocab_bytes && vocab_off && ids && n_tokens > 0 && vocab_slots > 0,
+                  "glove_tokens_lookup: bad arguments");
+    token_lookup_kernel<<<(unsigned)((n_tokens + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        text, starts, lens, n_tokens, vocab_table, vocab_slots, vocab_bytes, vocab_off, ids);
+    GLOVE_CHECK_LAUNCH();
     return GLOVE_OK;
 }
 

@@ -46,17 +46,8 @@ def load_data(src_dir=DATA_DIR):
 def create_vocabulary(text_tokens, vocab_size=VOCAB_SIZE, coverage=COVERAGE):
     """Frame (token, count, proportion): '<UNK>' plus at most ``vocab_size`` tokens whose count reaches the cut-off at
     which the cumulative token share passes ``coverage``; ordered by count (ref text8.py:61-81)."""
-    import pandas as pd
-    freq = Counter(text_tokens)
-    by_count = np.sort(np.fromiter(freq.values(), np.int64, len(freq)))[::-1]
-    total = int(by_count.sum())
-    cutoff = by_count[np.searchsorted(np.cumsum(by_count) / total, coverage)]
-    logger.info("count cufoff: %s; token coverage: %s.", cutoff, coverage)
-    kept = [(tok, n) for tok, n in freq.most_common(vocab_size) if n >= cutoff]
-    counts = [n for _, n in kept]
-    frame = pd.DataFrame({"token": ["<UNK>"] + [tok for tok, _ in kept], "count": [total - int(np.sum(counts))] + counts})
-    frame["proportion"] = frame["count"] / total
-    return frame.sort_values("count", ascending=False).reset_index(drop=True)
+    freq = Counter(text_tokens)                    # insertion order = order of first occurrence
+    return _frame_from_counts(list(freq.keys()), np.fromiter(freq.values(), np.int64, len(freq)), vocab_size, coverage)
 
 
 def token_ids(text_tokens, vocab_tokens):
@@ -64,6 +55,89 @@ def token_ids(text_tokens, vocab_tokens):
     lut = {t: i for i, t in enumerate(vocab_tokens)}
     get = lut.get
     return np.fromiter((get(t, 0) for t in text_tokens), np.int32, len(text_tokens))
+
+
+def _frame_from_counts(tokens, counts, vocab_size, coverage):
+    """The vocabulary frame from (token, count) pairs listed in order of first occurrence -- the part of
+    create_vocabulary that comes after Counter (ref text8.py:64-81)."""
+    import pandas as pd
+    counts = np.asarray(counts, np.int64)
+    by_count = np.sort(counts)[::-1]
+    total = int(by_count.sum())
+    cutoff = by_count[np.searchsorted(np.cumsum(by_count) / total, coverage)]
+    logger.info("count cufoff: %s; token coverage: %s.", cutoff, coverage)
+    top = np.argsort(-counts, kind="stable")[:vocab_size]        # most_common: by count, ties in order of first occurrence
+    top = top[counts[top] >= cutoff]
+    kept = counts[top].tolist()
+    frame = pd.DataFrame({"token": ["<UNK>"] + [tokens[i] for i in top], "count": [total - int(np.sum(kept))] + kept})
+    frame["proportion"] = frame["count"] / total
+    return frame.sort_values("count", ascending=False).reset_index(drop=True)
+
+
+class DeviceCorpus:
+    """Corpus text resident on the GPU with its token index (glove_tokens_scan): what ``text8.split()`` is to the
+    reference (ref text8.py:47), without materialising Python strings."""
+
+    def __init__(self, text, device="cuda:0"):
+        import torch
+        from . import _lib
+        self.lib, self.check = _lib.lib, _lib.check
+        self.dev = torch.device(device)
+        raw = text.encode("utf8") if isinstance(text, str) else bytes(text)
+        if not 0 < len(raw) < (1 << 31):
+            raise ValueError("corpus must hold 1 .. 2^31-1 bytes (split larger corpora at whitespace)")
+        self.raw, self.nbytes = raw, len(raw)
+        with torch.cuda.device(self.dev):
+            self.st = torch.cuda.current_stream().cuda_stream
+            self.text = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(self.dev)
+            ws = torch.empty(self.lib.glove_tokens_workspace_bytes(self.nbytes, 0), dtype=torch.uint8, device=self.dev)
+            cap = self.nbytes // 2 + 1
+            starts = torch.empty(cap, dtype=torch.int64, device=self.dev)
+            lens = torch.empty(cap, dtype=torch.int32, device=self.dev)
+            n = ctypes.c_int64()
+            self.check(self.lib.glove_tokens_scan(self.text.data_ptr(), self.nbytes, ws.data_ptr(), ws.numel(), starts.data_ptr(),
+                                                  lens.data_ptr(), cap, ctypes.byref(n), self.st), "glove_tokens_scan")
+            self.n_tokens = n.value
+            self.starts, self.lens = starts[:self.n_tokens].clone(), lens[:self.n_tokens].clone()
+
+    def distinct(self):
+        """(tokens, counts) of the distinct tokens in order of first occurrence -- Counter(text.split()) (ref text8.py:62)."""
+        import torch
+        with torch.cuda.device(self.dev):
+            n = self.n_tokens
+            ws = torch.empty(self.lib.glove_tokens_workspace_bytes(self.nbytes, n), dtype=torch.uint8, device=self.dev)
+            first = torch.empty(n, dtype=torch.int64, device=self.dev)
+            flen = torch.empty(n, dtype=torch.int32, device=self.dev)
+            cnt = torch.empty(n, dtype=torch.int64, device=self.dev)
+            m = ctypes.c_int64()
+            self.check(self.lib.glove_tokens_count(self.text.data_ptr(), self.nbytes, self.starts.data_ptr(), n, ws.data_ptr(),
+                                                   ws.numel(), first.data_ptr(), flen.data_ptr(), cnt.data_ptr(), n,
+                                                   ctypes.byref(m), self.st), "glove_tokens_count")
+            first, flen, cnt = (t[:m.value].cpu().numpy() for t in (first, flen, cnt))
+        order = np.argsort(first, kind="stable")
+        tokens = [self.raw[s:s + l].decode("utf8") for s, l in zip(first[order].tolist(), flen[order].tolist())]
+        return tokens, cnt[order]
+
+    def ids(self, vocab_tokens):
+        """Device int32 id of every token: row of the vocabulary frame, unknown -> 0 (ref text8.py:85-86)."""
+        import torch
+        lines = [t.encode("utf8") for t in vocab_tokens]
+        blob = b"".join(t + b"\n" for t in lines)
+        off = np.zeros(len(lines) + 1, np.int64)
+        np.cumsum([len(t) + 1 for t in lines], out=off[1:])
+        with torch.cuda.device(self.dev):
+            vb = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(self.dev)
+            voff = torch.from_numpy(off).to(self.dev)
+            slots = self.lib.glove_vocab_slots(len(lines))
+            table = torch.empty(slots, dtype=torch.int32, device=self.dev)
+            self.check(self.lib.glove_vocab_build(table.data_ptr(), slots, vb.data_ptr(), voff.data_ptr(), len(lines), self.st),
+                       "glove_vocab_build")
+            out = torch.empty(self.n_tokens, dtype=torch.int32, device=self.dev)
+            self.check(self.lib.glove_tokens_lookup(self.text.data_ptr(), self.starts.data_ptr(), self.lens.data_ptr(),
+                                                    self.n_tokens, table.data_ptr(), slots, vb.data_ptr(), voff.data_ptr(),
+                                                    out.data_ptr(), self.st), "glove_tokens_lookup")
+            torch.cuda.current_stream().synchronize()
+        return out
 
 
 def cooccurrence_table(ids, vocab_count, context_size=CONTEXT_SIZE, count_minimum=10, device="cuda:0",
@@ -79,7 +153,10 @@ def cooccurrence_table(ids, vocab_count, context_size=CONTEXT_SIZE, count_minimu
         raise ValueError("need at least two tokens")
     with torch.cuda.device(dev):
         st = torch.cuda.current_stream().cuda_stream
-        d_ids = torch.as_tensor(np.array(ids, np.int32)).to(dev)
+        if torch.is_tensor(ids):
+            d_ids = ids.to(device=dev, dtype=torch.int32).contiguous()
+        else:
+            d_ids = torch.as_tensor(np.array(ids, np.int32)).to(dev)
         d_vc = torch.as_tensor(np.array(vocab_count, np.int64)).to(dev)
         total = int(np.asarray(vocab_count, np.int64).sum())
         chunk = int(min(chunk_positions, T, ((1 << 31) - 1) // context_size))
@@ -137,19 +214,33 @@ def create_interaction_dataframe(text_tokens, df_vocab, context_size=CONTEXT_SIZ
     vocab_tokens = df_vocab["token"].to_numpy()
     ids = token_ids(text_tokens, vocab_tokens)
     t = cooccurrence_table(ids, df_vocab["count"].to_numpy(), context_size, count_minimum, device)
-    frame = pd.DataFrame({"row_token_id": t["row_token_id"], "col_token_id": t["col_token_id"], "count": t["count"],
-                          "value": t["value"], "row_token": vocab_tokens[t["row_token_id"]],
-                          "col_token": vocab_tokens[t["col_token_id"]], "neg_weight": t["neg_weight"],
-                          "glove_weight": t["glove_weight"], "glove_value": t["glove_value"]})
+    frame = interaction_frame(t, vocab_tokens)
     logger.info("dataframe shape: %s.", frame.shape)
     return frame
 
 
+def interaction_frame(table, vocab_tokens):
+    """The reference's interaction.csv columns, in its order, from the numeric table (ref text8.py:113-114 for the tokens)."""
+    import pandas as pd
+    vocab_tokens = np.asarray(vocab_tokens, dtype=object)
+    return pd.DataFrame({"row_token_id": table["row_token_id"], "col_token_id": table["col_token_id"], "count": table["count"],
+                         "value": table["value"], "row_token": vocab_tokens[table["row_token_id"]],
+                         "col_token": vocab_tokens[table["col_token_id"]], "neg_weight": table["neg_weight"],
+                         "glove_weight": table["glove_weight"], "glove_value": table["glove_value"]})
+
+
 def process_data(text8, vocab_size=VOCAB_SIZE, coverage=COVERAGE, context_size=CONTEXT_SIZE, device="cuda:0"):
-    tokens = text8.split()
-    df_vocab = create_vocabulary(tokens, int(vocab_size), coverage)
+    """ref text8.py:46-58, with the token stream kept on the GPU from the split to the table: tokenise, count distinct
+    tokens, (host: pick the vocabulary among them), map tokens to ids, count pairs, write the columns."""
+    corpus = DeviceCorpus(text8, device)
+    tokens, counts = corpus.distinct()
+    df_vocab = _frame_from_counts(tokens, counts, int(vocab_size), coverage)
     logger.info("vocab created, size: %s.", df_vocab.shape[0])
-    return {"vocabulary": df_vocab, "interaction": create_interaction_dataframe(tokens, df_vocab, context_size, device=device)}
+    vocab_tokens = df_vocab["token"].to_numpy()
+    table = cooccurrence_table(corpus.ids(vocab_tokens), df_vocab["count"].to_numpy(), context_size, 10, device)
+    frame = interaction_frame(table, vocab_tokens)
+    logger.info("dataframe shape: %s.", frame.shape)
+    return {"vocabulary": df_vocab, "interaction": frame}
 
 
 def save_data(data, save_dir=DATA_DIR):

@@ -260,6 +260,26 @@ int glove_csv_parse(const uint8_t *text, int64_t nbytes, int32_t final_chunk, vo
 /* Host entry to the decimal -> float32 routine the parse kernel uses (one field, no blanks); for tests and tools. */
 int glove_parse_float32(const char *text, int32_t n, float *out);
 
+/* ---- TOKENS: corpus text -> token stream, the front half of the preprocessor ------------------------
+ * text8.split() [ref src/data/text8.py:47], Counter(text_tokens) [ref :62], token2id.get(token, 0) [ref :85-86].
+ * Tokens are maximal runs of non-whitespace bytes (ASCII whitespace; the UTF-8 encodings of the other separators that
+ * str.split() knows are refused with GLOVE_EUNSUPPORTED).  text: device, < 2^31 bytes per call. */
+size_t glove_tokens_workspace_bytes(int64_t nbytes, int64_t n_tokens);
+/* starts[i] / lens[i] of every token, in text order; *n_tokens_host is set even when it exceeds capacity.  Workspace:
+ * glove_tokens_workspace_bytes(nbytes, 0).  Synchronises. */
+int glove_tokens_scan(const uint8_t *text, int64_t nbytes, void *workspace, size_t workspace_bytes, int64_t *starts,
+                      int32_t *lens, int64_t capacity, int64_t *n_tokens_host, void *stream);
+/* Distinct tokens (radix sort of a 64-bit hash of the bytes, verified byte-wise: a collision fails the call): for each,
+ * the start and length of its FIRST occurrence and its count; order = by hash.  Workspace:
+ * glove_tokens_workspace_bytes(nbytes, n_tokens).  Synchronises. */
+int glove_tokens_count(const uint8_t *text, int64_t nbytes, const int64_t *starts, int64_t n_tokens, void *workspace,
+                       size_t workspace_bytes, int64_t *first_start, int32_t *first_len, int64_t *count, int64_t capacity,
+                       int64_t *n_distinct_host, void *stream);
+/* ids[i] = line of token i in the vocab table built by glove_vocab_build, missing -> 0.  Asynchronous. */
+int glove_tokens_lookup(const uint8_t *text, const int64_t *starts, const int32_t *lens, int64_t n_tokens,
+                        const int32_t *vocab_table, int64_t vocab_slots, const uint8_t *vocab_bytes, const int64_t *vocab_off,
+                        int32_t *ids, void *stream);
+
 /* ---- PREPROCESS: token-id stream -> symmetric co-occurrence table with the GloVe columns ------------
  * create_interaction_dataframe + create_glove_dataframe of the reference preprocessor [ref src/data/text8.py:84-139].
  * Partial tables are (keys u64[n] sorted unique, agg i64[2n] = {count, numer} per key) with numer = sum over the pairs of
