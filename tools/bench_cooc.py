@@ -52,6 +52,36 @@ def main():
     order = np.lexsort((small["col_token_id"], small["row_token_id"]))
     ok = (np.array_equal(small["count"][order], ref["count"].to_numpy())
           and np.allclose(small["value"][order], ref["value"].to_numpy(), rtol=1e-14, atol=0))
+    # ---- whole preprocessor from corpus TEXT (SURVEY cfg1 shape: Zipf over 253,854 types "w<id>"), stage by stage
+    types = 253_854
+    pt = 1.0 / np.arange(1, types + 1)
+    tid = np.searchsorted(np.cumsum(pt / pt.sum()), rng.random(T)).clip(0, types - 1)
+    names = np.array(["w%d" % i for i in range(types)], dtype=object)
+    text = " ".join(names[tid].tolist())
+    del tid
+    stages = {}
+    text8.process_data(text[:2_000_000], 10000, 0.9, K)         # warm-up
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    corpus = text8.DeviceCorpus(text)
+    torch.cuda.synchronize(); stages["encode + H2D + tokenise"] = time.perf_counter() - t0; t1 = time.perf_counter()
+    toks, cnts = corpus.distinct()
+    torch.cuda.synchronize(); stages["distinct tokens (sort by hash, verify, D2H, decode %d strings)" % len(toks)] = time.perf_counter() - t1; t1 = time.perf_counter()
+    dfv = text8._frame_from_counts(toks, cnts, 10000, 0.9)
+    stages["vocabulary frame (host, pandas)"] = time.perf_counter() - t1; t1 = time.perf_counter()
+    dids = corpus.ids(dfv["token"].to_numpy())
+    torch.cuda.synchronize(); stages["token -> id"] = time.perf_counter() - t1; t1 = time.perf_counter()
+    tab = text8.cooccurrence_table(dids, dfv["count"].to_numpy(), K, 10, as_numpy=False)
+    torch.cuda.synchronize(); stages["co-occurrence table"] = time.perf_counter() - t1
+    text_s = time.perf_counter() - t0
+    # host equivalents of the front half on a sample (what the reference does in Python: split, Counter, dict lookups)
+    sample = text[:len(text) // 16]
+    t1 = time.perf_counter()
+    stoks = sample.split()
+    from collections import Counter
+    Counter(stoks)
+    text8.token_ids(stoks, dfv["token"].to_numpy())
+    host_front_s = time.perf_counter() - t1
     # algorithmic bytes: read the ids once, write the table once
     alg = 4 * T + n_out * (4 + 4 + 8 + 4 * 8)
     print(json.dumps({
@@ -59,6 +89,10 @@ def main():
         "parity_on_cpu_sample": bool(ok),
         "gpu": {"s": gpu_s, "tokens_per_s": T / gpu_s, "pairs_per_s": pairs / gpu_s, "includes": "H2D of the ids, chunk/merge/finish kernels, all syncs"},
         "cpu_port": {"s": cpu_s, "tokens": n_cpu, "tokens_per_s": n_cpu / cpu_s, "kind": "port (pandas groupby restatement of ref src/data/text8.py:84-139)"},
+        "from_text": {"s": text_s, "bytes": len(text), "tokens_per_s": T / text_s, "records": int(tab["count"].numel()),
+                      "vocab_rows": int(len(dfv)), "stages_s": stages},
+        "host_front_half_sample": {"s": host_front_s, "tokens": len(stoks), "tokens_per_s": len(stoks) / host_front_s,
+                                   "what": "str.split + Counter + dict lookups (ref text8.py:47,62,85-86)"},
         "algorithmic_bytes": alg, "sorted_bytes_per_pair": 9}))
 
 
