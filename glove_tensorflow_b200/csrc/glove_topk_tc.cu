@@ -1,13 +1,15 @@
-// Tensor-core candidate pass of the cosine top-k (the only tensor-core path of the trainer): for a tile of 128 query
-// rows, stream the normalised bf16 table through tcgen05.mma (accumulators in TMEM, operands staged in shared memory by
+// Tensor-core candidate pass of the cosine top-k (the only tensor-core path of the trainer): for a tile of 256 query
+// rows (two M = 128 halves that share every table tile: the pass is bound by streaming the table, so operand reuse is
+// what counts), stream the normalised bf16 table through tcgen05.mma (accumulators in TMEM, operands staged in shared memory by
 // TMA with 128-byte swizzle) and keep, per query row, the KP best approximate similarities in a fused epilogue that
 // reads the accumulator straight out of TMEM.  The candidates are re-scored exactly in fp32 (same routine as the fp32
 // scan) and a query whose k-th exact score is not safely above the bf16 cut-off of the candidate lists is sent through the
 // exact scan, so the returned ids are the exact fp32 top-k in every case
 // [replaces cosine_similarity + tf.math.top_k, ref src/models/utils.py:12-19, src/models/model_utils.py:97-99].
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane),
-// warps 2..5 = epilogue (each owns one 32-lane quarter of TMEM; thread = one query row).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane),
+// warps 2..9 = epilogue (warps 2-5 drain the accumulators of query half 0, warps 6-9 those of half 1; each owns the
+// 32-lane quarter of TMEM given by warp % 4; thread = one query row).
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <cuda_bf16.h>
@@ -16,15 +18,17 @@
 
 namespace glove {
 
-constexpr int TC_M = 128;     // query rows per CTA  (UMMA M)
-constexpr int TC_N = 256;     // table rows per accumulator tile (UMMA N)
+constexpr int TC_M = 128;     // UMMA M
+constexpr int TC_MQ = 256;    // query rows per CTA = 2 x UMMA M
+constexpr int TC_N = 128;     // table rows per accumulator tile (UMMA N)
 constexpr int TC_KC = 64;     // bf16 elements per K chunk = 128 bytes = one SWIZZLE_128B row
 constexpr int TC_STAGES = 3;  // B-operand pipeline depth
 constexpr int TC_KP = 32;     // candidates kept per (query, table slice)
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;
 constexpr int TC_MAX_KCH = 5;  // Kp <= 320
-constexpr uint32_t TC_A_CHUNK_BYTES = TC_M * TC_KC * 2;  // 16 KB
-constexpr uint32_t TC_B_STAGE_BYTES = TC_N * TC_KC * 2;  // 32 KB
+constexpr uint32_t TC_A_HALF_BYTES = TC_M * TC_KC * 2;    // 16 KB
+constexpr uint32_t TC_A_CHUNK_BYTES = TC_MQ * TC_KC * 2;  // 32 KB: rows 0-127 then rows 128-255
+constexpr uint32_t TC_B_STAGE_BYTES = TC_N * TC_KC * 2;   // 16 KB
 constexpr float TC_DELTA = 4.0e-3f;  // bound on |bf16 similarity - fp32 similarity| for unit vectors (2^-8 + slack)
 
 // ---- PTX wrappers ----------------------------------------------------------------------------------------------------
@@ -76,15 +80,13 @@ __device__ __forceinline__ uint64_t sw128_desc(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
     return d;
 }
-// kind::f16: D = F32, A = B = BF16, both K-major, M = 128, N = 256
+// kind::f16: D = F32, A = B = BF16, both K-major, M = 128, N = 128
 constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 
 struct TcSmem {  // offsets inside the 1024-byte aligned dynamic shared memory
     static constexpr uint32_t A = 0;
     static constexpr uint32_t B = TC_MAX_KCH * TC_A_CHUNK_BYTES;
-    static constexpr uint32_t LIST_VAL = B + TC_STAGES * TC_B_STAGE_BYTES;
-    static constexpr uint32_t LIST_IDX = LIST_VAL + TC_KP * TC_M * 4;
-    static constexpr uint32_t BARS = LIST_IDX + TC_KP * TC_M * 4;
+    static constexpr uint32_t BARS = B + TC_STAGES * TC_B_STAGE_BYTES;
     static constexpr uint32_t TOTAL = BARS + 128;
 };
 
@@ -111,10 +113,10 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     if (threadIdx.x == 0) {
         mbar_init(bar_a, 1);
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull(b), 1); mbar_init(bar_tempty(b), 4); }
+        for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull(b), 1); mbar_init(bar_tempty(b), 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {  // TMEM: all 512 columns (two 128 x 256 fp32 accumulators)
+    if (warp == 1) {  // TMEM: all 512 columns (2 buffers x 2 query halves of 128 x 128 fp32 accumulators)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -127,7 +129,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         // ===== TMA producer =====
         if (lane == 0) {
             mbar_expect_tx(bar_a, kch * TC_A_CHUNK_BYTES);
-            for (int kc = 0; kc < kch; ++kc) tma_load_2d(base + TcSmem::A + kc * TC_A_CHUNK_BYTES, &map_q, bar_a, kc * TC_KC, qt * TC_M);
+            for (int kc = 0; kc < kch; ++kc) tma_load_2d(base + TcSmem::A + kc * TC_A_CHUNK_BYTES, &map_q, bar_a, kc * TC_KC, qt * TC_MQ);
             int stage = 0;
             uint32_t phase = 0;
             for (int t = t0; t < t1; ++t) {
@@ -150,15 +152,18 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                 const int buf = j & 1;
                 mbar_wait(bar_tempty(buf), ((j >> 1) & 1) ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + buf * TC_N;
                 for (int kc = 0; kc < kch; ++kc) {
                     mbar_wait(bar_full(stage), phase);
                     tc_fence_after();
-                    const uint64_t adesc = sw128_desc(base + TcSmem::A + kc * TC_A_CHUNK_BYTES);
                     const uint64_t bdesc = sw128_desc(base + TcSmem::B + stage * TC_B_STAGE_BYTES);
 #pragma unroll
-                    for (int kk = 0; kk < TC_KC / 16; ++kk)  // UMMA_K = 16 bf16 = 32 bytes: +2 in the address field
-                        tc_mma_bf16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, TC_IDESC, (kc | kk) != 0);
+                    for (int h = 0; h < 2; ++h) {            // both query halves consume the same table tile
+                        const uint32_t d_tmem = tmem_base + (buf * 2 + h) * TC_N;
+                        const uint64_t adesc = sw128_desc(base + TcSmem::A + kc * TC_A_CHUNK_BYTES + h * TC_A_HALF_BYTES);
+#pragma unroll
+                        for (int kk = 0; kk < TC_KC / 16; ++kk)  // UMMA_K = 16 bf16 = 32 bytes: +2 in the address field
+                            tc_mma_bf16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, TC_IDESC, (kc | kk) != 0);
+                    }
                     tc_commit(bar_empty(stage));  // frees the stage when these MMAs have read it
                     if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -168,11 +173,16 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     } else {
         // ===== epilogue: thread = one query row; running top-KP of the approximate similarities =====
         const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
-        const int row = quarter * 32 + lane;
-        float *lval = reinterpret_cast<float *>(gen + TcSmem::LIST_VAL) + row;     // entry e at lval[e * TC_M]
-        int32_t *lidx = reinterpret_cast<int32_t *>(gen + TcSmem::LIST_IDX) + row;
-        int cnt = 0, minpos = 0;
-        float thr = -INFINITY;                        // KP-th best so far once the list is full
+        const int half = (warp - 2) >> 2;             // query half whose accumulators this warp drains
+        const int row = half * TC_M + quarter * 32 + lane;
+        // the running top-KP list lives in registers, sorted (descending): inserting is one pass of compare-and-swap over
+        // statically indexed registers, the cut-off is the last entry.  No memory traffic until the list is published.
+        const int64_t q = (int64_t)qt * TC_MQ + row;
+        float lv[TC_KP];
+        int32_t li[TC_KP];
+#pragma unroll
+        for (int e = 0; e < TC_KP; ++e) { lv[e] = -INFINITY; li[e] = -1; }
+        float thr = -INFINITY;                        // KP-th best so far (-inf until the list is full)
         for (int j = 0; j < n_tiles; ++j) {
             const int buf = j & 1;
             mbar_wait(bar_tfull(buf), (j >> 1) & 1);
@@ -181,7 +191,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 #pragma unroll 1
             for (int c = 0; c < TC_N / 32; ++c) {
                 uint32_t r[32];
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * TC_N + c * 32;
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (buf * 2 + half) * TC_N + c * 32;
                 asm volatile(
                     "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                     "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -195,23 +205,31 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                 float m = __uint_as_float(r[0]);
 #pragma unroll
                 for (int e = 1; e < 32; ++e) m = fmaxf(m, __uint_as_float(r[e]));
-                if (cnt < TC_KP || m > thr) {
+                if (m > thr) {
+                    const int64_t g0 = tile_row0 + c * 32;
+                    uint32_t hits = 0;                             // entries of this chunk that beat the cut-off
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) {
-                        const float v = __uint_as_float(r[e]);
-                        const int64_t gi = tile_row0 + c * 32 + e;
-                        if (gi < V && (cnt < TC_KP || v > thr)) {
-                            const int pos = cnt < TC_KP ? cnt : minpos;
-                            lval[pos * TC_M] = v;
-                            lidx[pos * TC_M] = (int32_t)gi;
-                            if (cnt < TC_KP) ++cnt;
-                            if (cnt == TC_KP) {  // (re)locate the minimum = cut-off
-                                thr = lval[0]; minpos = 0;
-                                for (int u = 1; u < TC_KP; ++u) {
-                                    const float w = lval[u * TC_M];
-                                    if (w < thr) { thr = w; minpos = u; }
-                                }
+                    for (int e = 0; e < 32; ++e) hits |= (uint32_t)(__uint_as_float(r[e]) > thr) << e;
+                    while (hits) {
+                        const int e = __ffs(hits) - 1;
+                        hits &= hits - 1;
+                        // r[] is statically indexed only in fully unrolled code: pick entry e with a select chain
+                        float v = -INFINITY;
+#pragma unroll
+                        for (int u = 0; u < 32; ++u) v = (u == e) ? __uint_as_float(r[u]) : v;
+                        if (v > thr && g0 + e < V) {
+                            int32_t vi = (int32_t)(g0 + e);
+#pragma unroll
+                            for (int u = 0; u < TC_KP; ++u) {      // ties keep the earlier (lower) table row in front
+                                const bool up = v > lv[u];
+                                const float tv = lv[u];
+                                const int32_t ti = li[u];
+                                lv[u] = up ? v : tv;
+                                li[u] = up ? vi : ti;
+                                v = up ? tv : v;
+                                vi = up ? ti : vi;
                             }
+                            thr = lv[TC_KP - 1];
                         }
                     }
                 }
@@ -221,13 +239,13 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             if (lane == 0) mbar_arrive(bar_tempty(buf));
         }
         // publish the candidate list of this (query, slice)
-        const int64_t q = (int64_t)qt * TC_M + row;
         const int64_t o = (q * n_slices + slice) * TC_KP;
+#pragma unroll
         for (int e = 0; e < TC_KP; ++e) {
-            cand_val[o + e] = e < cnt ? lval[e * TC_M] : -INFINITY;
-            cand_idx[o + e] = e < cnt ? lidx[e * TC_M] : -1;
+            cand_val[o + e] = lv[e];
+            cand_idx[o + e] = li[e];
         }
-        cutoff[q * n_slices + slice] = cnt == TC_KP ? thr : -INFINITY;
+        cutoff[q * n_slices + slice] = thr;
     }
     tc_fence_before();
     __syncthreads();
@@ -339,9 +357,19 @@ static TcWs tc_ws_view(void *base, int64_t V, int32_t d, int32_t nq, int32_t k) 
     auto take = [&](size_t bytes) { char *r = p ? p + off : nullptr; off += align_up(bytes); return r; };
     const int32_t Kp = glove_topk_kpad(d);
     const int64_t tiles = glove_topk_vpad(V) / TC_N;
-    w.nq_pad = (nq + TC_M - 1) / TC_M * TC_M;
-    const int q_tiles = w.nq_pad / TC_M;
+    w.nq_pad = (nq + TC_MQ - 1) / TC_MQ * TC_MQ;
+    const int q_tiles = w.nq_pad / TC_MQ;
+    // one CTA per SM: at least one full wave, and among 1..8 x that the slice count that wastes least of its last wave
     int slices = (kNumSMs + q_tiles - 1) / q_tiles;
+    {
+        const int lo = slices;
+        double best = -1.0;
+        for (int s = lo; s <= 8 * lo && s <= lo + 7; ++s) {
+            const int ctas = q_tiles * s, waves = (ctas + kNumSMs - 1) / kNumSMs;
+            const double eff = (double)ctas / ((double)waves * kNumSMs);
+            if (eff > best + 0.02) { best = eff; slices = s; }
+        }
+    }
     if (slices > tiles) slices = (int)tiles;
     if (slices < 1) slices = 1;
     w.tiles_per_slice = (int32_t)((tiles + slices - 1) / slices);
@@ -413,13 +441,13 @@ int glove_topk_cosine(const float *table, int64_t V, int32_t d, int32_t planes, 
                                                            w.nq_pad, w.qn);
     GLOVE_CHECK_LAUNCH();
     CUtensorMap map_q, map_t;
-    int rc = make_map(&map_q, w.qn, (uint64_t)w.nq_pad, (uint64_t)Kp, TC_M);
+    int rc = make_map(&map_q, w.qn, (uint64_t)w.nq_pad, (uint64_t)Kp, TC_MQ);
     if (rc != GLOVE_OK) return rc;
     rc = make_map(&map_t, norm_bf16, (uint64_t)Vp, (uint64_t)Kp, TC_N);
     if (rc != GLOVE_OK) return rc;
     const size_t smem = TcSmem::TOTAL + 1024;
     GLOVE_CHECK_CUDA(cudaFuncSetAttribute(topk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(w.nq_pad / TC_M, w.n_slices);
+    dim3 grid(w.nq_pad / TC_MQ, w.n_slices);
     topk_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(map_q, map_t, V, kch, (int32_t)(Vp / TC_N), w.tiles_per_slice,
                                                        w.cand_val, w.cand_idx, w.cutoff);
     GLOVE_CHECK_LAUNCH();
