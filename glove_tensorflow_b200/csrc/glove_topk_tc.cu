@@ -10,6 +10,8 @@
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane),
 // warps 2..9 = epilogue (warps 2-5 drain the accumulators of query half 0, warps 6-9 those of half 1; each owns the
 // 32-lane quarter of TMEM given by warp % 4; thread = one query row).
+#include <stdlib.h>
+
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <cuda_bf16.h>
@@ -369,6 +371,10 @@ static TcWs tc_ws_view(void *base, int64_t V, int32_t d, int32_t nq, int32_t k) 
             const double eff = (double)ctas / ((double)waves * kNumSMs);
             if (eff > best + 0.02) { best = eff; slices = s; }
         }
+    }
+    if (const char *e = getenv("GLOVE_TOPK_SLICES")) {   // tuning aid
+        const int n = atoi(e);
+        if (n > 0) slices = n;
     }
     if (slices > tiles) slices = (int)tiles;
     if (slices < 1) slices = 1;
