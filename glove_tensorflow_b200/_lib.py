@@ -83,6 +83,9 @@ SIGNATURES = {
     "glove_topk_workspace_bytes": (c_size, [c_i64, c_i32, c_i32, c_i32]),
     "glove_topk_cosine": (ctypes.c_int, [c_void, c_i64, c_i32, c_i32, c_void, c_void, c_void, c_i32, c_i32, c_void,
                                          c_void, c_void, c_size, c_void]),
+    "glove_topk_cosine_queries": (ctypes.c_int, [c_void, c_i64, c_i32, c_i32, c_void, c_void, c_void, c_i32, c_void, c_void,
+                                                 c_i32, c_i32, c_void, c_void, c_void, c_size, c_void]),
+    "glove_topk_merge": (ctypes.c_int, [c_void, c_void, c_i32, c_i32, c_i32, c_void, c_void, c_void]),
     "glove_topk_flagged": (ctypes.c_int, [c_void, c_i64, c_i32, c_i32, c_i32, ctypes.POINTER(c_i32), c_void]),
     "glove_topk_cosine_fp32": (ctypes.c_int, [c_void, c_i64, c_i32, c_i32, c_void, c_void, c_i32, c_i32, c_void,
                                               c_void, c_void, c_size, c_void]),

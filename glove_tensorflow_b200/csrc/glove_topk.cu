@@ -40,6 +40,7 @@ __global__ void __launch_bounds__(256) normalize_kernel(const float *__restrict_
 template <int NV>
 __global__ void __launch_bounds__(256) scan_fp32_kernel(const float *__restrict__ table, int64_t V, int32_t d, int32_t S,
                                                         int32_t P, const float *__restrict__ inv_norm,
+                                                        const float *__restrict__ qtable, int32_t qP,
                                                         const int32_t *__restrict__ query_ids, int32_t nq, int32_t k,
                                                         const int32_t *__restrict__ only_flagged, int64_t rows_per_slice,
                                                         float *cand_sim, int32_t *cand_idx) {
@@ -53,7 +54,7 @@ __global__ void __launch_bounds__(256) scan_fp32_kernel(const float *__restrict_
     }
     for (int t = wid; t < kScanQT; t += 8) {
         const int q = q0 + t;
-        const float *row = table + (int64_t)(q < nq ? query_ids[q] : 0) * P * S;
+        const float *row = qtable + (int64_t)(q < nq ? query_ids[q] : 0) * qP * S;   // queries may live in another table
         const float rn = q < nq ? row_inv_norm(row, d, lane) : 0.0f;
         for (int c = lane; c < S; c += 32) qn[t * S + c] = (q < nq && c < d) ? row[c] * rn : 0.0f;
     }
@@ -119,8 +120,9 @@ __global__ void __launch_bounds__(256) merge_kernel(const float *__restrict__ ca
 }
 
 int scan_fp32_launch(const float *table, int64_t V, int32_t d, int32_t planes, const float *inv_norm,
-                     const int32_t *query_ids, int32_t nq, int32_t k, const int32_t *only_flagged, float *out_sim,
-                     int32_t *out_idx, void *workspace, size_t workspace_bytes, cudaStream_t stream) {
+                     const float *qtable, int32_t qplanes, const int32_t *query_ids, int32_t nq, int32_t k,
+                     const int32_t *only_flagged, float *out_sim, int32_t *out_idx, void *workspace, size_t workspace_bytes,
+                     cudaStream_t stream) {
     const int32_t S = table_stride(d);
     const int nv = (S / 4 + 31) / 32;
     const int q_tiles = (nq + kScanQT - 1) / kScanQT;
@@ -138,8 +140,8 @@ int scan_fp32_launch(const float *table, int64_t V, int32_t d, int32_t planes, c
     const size_t smem = sizeof(float) * kScanQT * S;
     dim3 grid(q_tiles, slices);
 #define LAUNCH_SCAN(NV)                                                                                              \
-    scan_fp32_kernel<NV><<<grid, 256, smem, stream>>>(table, V, d, S, planes, inv_norm, query_ids, nq, k, only_flagged, \
-                                                      rows_per_slice, cand_sim, cand_idx)
+    scan_fp32_kernel<NV><<<grid, 256, smem, stream>>>(table, V, d, S, planes, inv_norm, qtable, qplanes, query_ids, nq, k, \
+                                                      only_flagged, rows_per_slice, cand_sim, cand_idx)
     switch (nv) {
         case 1: LAUNCH_SCAN(1); break;
         case 2: LAUNCH_SCAN(2); break;
@@ -184,8 +186,20 @@ int glove_topk_cosine_fp32(const float *table, int64_t V, int32_t d, int32_t pla
     GLOVE_REQUIRE(table && inv_norm && query_ids && out_sim && out_idx && workspace, "glove_topk_cosine_fp32: null pointer");
     GLOVE_REQUIRE(V > 0 && d > 0 && planes >= 1 && n_queries > 0, "glove_topk_cosine_fp32: bad sizes");
     if (k < 1 || k > 32 || k > V) return set_error(GLOVE_EUNSUPPORTED, "topk: k=%d not in [1, min(32, V)]", k);
-    return scan_fp32_launch(table, V, d, planes, inv_norm, query_ids, n_queries, k, nullptr, out_sim, out_idx, workspace,
-                            workspace_bytes, (cudaStream_t)stream);
+    return scan_fp32_launch(table, V, d, planes, inv_norm, table, planes, query_ids, n_queries, k, nullptr, out_sim, out_idx,
+                            workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+// Merge n_cand candidates per query (idx < 0 = empty) into the k best: descending similarity, ties -> lower id.  The last
+// step of a row-sharded top-k: every shard contributes the top-k of its own rows (ids already made global).
+int glove_topk_merge(const float *cand_sim, const int32_t *cand_idx, int32_t n_queries, int32_t n_cand, int32_t k,
+                     float *out_sim, int32_t *out_idx, void *stream) {
+    GLOVE_REQUIRE(cand_sim && cand_idx && out_sim && out_idx && n_queries > 0 && n_cand > 0, "glove_topk_merge: bad arguments");
+    if (k < 1 || k > 32) return set_error(GLOVE_EUNSUPPORTED, "topk: k=%d not in [1, 32]", k);
+    merge_kernel<<<(n_queries + 7) / 8, 256, 0, (cudaStream_t)stream>>>(cand_sim, cand_idx, n_queries, n_cand, k, nullptr,
+                                                                         out_sim, out_idx);
+    GLOVE_CHECK_LAUNCH();
+    return GLOVE_OK;
 }
 
 }  // extern "C"

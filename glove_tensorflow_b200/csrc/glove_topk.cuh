@@ -59,8 +59,9 @@ struct LaneTopK {
 };
 
 int scan_fp32_launch(const float *table, int64_t V, int32_t d, int32_t planes, const float *inv_norm,
-                     const int32_t *query_ids, int32_t nq, int32_t k, const int32_t *only_flagged, float *out_sim,
-                     int32_t *out_idx, void *workspace, size_t workspace_bytes, cudaStream_t stream);
+                     const float *qtable, int32_t qplanes, const int32_t *query_ids, int32_t nq, int32_t k,
+                     const int32_t *only_flagged, float *out_sim, int32_t *out_idx, void *workspace, size_t workspace_bytes,
+                     cudaStream_t stream);
 size_t scan_fp32_workspace(int32_t nq, int32_t k);
 
 }  // namespace glove

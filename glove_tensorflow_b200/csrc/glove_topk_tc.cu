@@ -271,7 +271,8 @@ __global__ void gather_queries_kernel(const __nv_bfloat16 *__restrict__ tn, int3
 // exact fp32 re-score of the candidates (one warp per query) + guarantee check
 template <int NV>
 __global__ void __launch_bounds__(256) rescore_kernel(const float *__restrict__ table, int32_t d, int32_t S, int32_t P,
-                                                      const float *__restrict__ inv_norm, const int32_t *__restrict__ query_ids,
+                                                      const float *__restrict__ inv_norm, const float *__restrict__ qtable,
+                                                      int32_t qP, const int32_t *__restrict__ query_ids,
                                                       int32_t nq, int32_t k, const int32_t *__restrict__ cand_idx,
                                                       const float *__restrict__ cutoff, int32_t n_slices, float *out_sim,
                                                       int32_t *out_idx, int32_t *flags) {
@@ -281,7 +282,7 @@ __global__ void __launch_bounds__(256) rescore_kernel(const float *__restrict__ 
     if (q >= nq) return;
     float *qn = qn_all + wid * S;
     {
-        const float *row = table + (int64_t)query_ids[q] * P * S;
+        const float *row = qtable + (int64_t)query_ids[q] * qP * S;
         const float rn = row_inv_norm(row, d, lane);
         for (int c = lane; c < S; c += 32) qn[c] = c < d ? row[c] * rn : 0.0f;
     }
@@ -426,11 +427,13 @@ size_t glove_topk_workspace_bytes(int64_t V, int32_t d, int32_t n_queries, int32
     return tc_ws_view(nullptr, V, d, n_queries, k).bytes;
 }
 
-int glove_topk_cosine(const float *table, int64_t V, int32_t d, int32_t planes, const void *norm_bf16,
-                      const float *inv_norm, const int32_t *query_ids, int32_t n_queries, int32_t k, float *out_sim,
-                      int32_t *out_idx, void *workspace, size_t workspace_bytes, void *stream_) {
+int glove_topk_cosine_queries(const float *table, int64_t V, int32_t d, int32_t planes, const void *norm_bf16,
+                              const float *inv_norm, const float *qtable, int32_t qplanes, const void *qnorm_bf16,
+                              const int32_t *query_ids, int32_t n_queries, int32_t k, float *out_sim, int32_t *out_idx,
+                              void *workspace, size_t workspace_bytes, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    GLOVE_REQUIRE(table && inv_norm && query_ids && out_sim && out_idx && workspace, "glove_topk_cosine: null pointer");
+    GLOVE_REQUIRE(table && inv_norm && query_ids && out_sim && out_idx && workspace && qtable && qplanes >= 1,
+                  "glove_topk_cosine: null pointer");
     GLOVE_REQUIRE(V > 0 && d > 0 && planes >= 1 && n_queries > 0, "glove_topk_cosine: bad sizes");
     if (k < 1 || k > 32 || k > V) return set_error(GLOVE_EUNSUPPORTED, "topk: k=%d not in [1, min(32, V)]", k);
     const int32_t Kp = glove_topk_kpad(d), S = table_stride(d);
@@ -439,11 +442,11 @@ int glove_topk_cosine(const float *table, int64_t V, int32_t d, int32_t planes, 
     if (workspace_bytes < w.bytes)
         return set_error(GLOVE_EWORKSPACE, "glove_topk_cosine: workspace %zu < required %zu", workspace_bytes, w.bytes);
     // shapes the tensor-core pass does not cover go straight to the exact scan
-    if (!norm_bf16 || kch > TC_MAX_KCH || k > TC_KP - 8 || V < 4 * TC_N)
-        return scan_fp32_launch(table, V, d, planes, inv_norm, query_ids, n_queries, k, nullptr, out_sim, out_idx,
-                                w.scan_ws, w.scan_bytes, stream);
+    if (!norm_bf16 || !qnorm_bf16 || kch > TC_MAX_KCH || k > TC_KP - 8 || V < 1024)
+        return scan_fp32_launch(table, V, d, planes, inv_norm, qtable, qplanes, query_ids, n_queries, k, nullptr, out_sim,
+                                out_idx, w.scan_ws, w.scan_bytes, stream);
     const int64_t Vp = glove_topk_vpad(V);
-    gather_queries_kernel<<<kNumSMs * 4, 256, 0, stream>>>((const __nv_bfloat16 *)norm_bf16, Kp, query_ids, n_queries,
+    gather_queries_kernel<<<kNumSMs * 4, 256, 0, stream>>>((const __nv_bfloat16 *)qnorm_bf16, Kp, query_ids, n_queries,
                                                            w.nq_pad, w.qn);
     GLOVE_CHECK_LAUNCH();
     CUtensorMap map_q, map_t;
@@ -461,8 +464,9 @@ int glove_topk_cosine(const float *table, int64_t V, int32_t d, int32_t planes, 
     const size_t rs_smem = sizeof(float) * 8 * S;
     const int rs_blocks = (n_queries + 7) / 8;
 #define LAUNCH_RESCORE(NV)                                                                                            \
-    rescore_kernel<NV><<<rs_blocks, 256, rs_smem, stream>>>(table, d, S, planes, inv_norm, query_ids, n_queries, k,   \
-                                                            w.cand_idx, w.cutoff, w.n_slices, out_sim, out_idx, w.flags)
+    rescore_kernel<NV><<<rs_blocks, 256, rs_smem, stream>>>(table, d, S, planes, inv_norm, qtable, qplanes, query_ids,  \
+                                                            n_queries, k, w.cand_idx, w.cutoff, w.n_slices, out_sim,  \
+                                                            out_idx, w.flags)
     switch (nv) {
         case 1: LAUNCH_RESCORE(1); break;
         case 2: LAUNCH_RESCORE(2); break;
@@ -472,8 +476,15 @@ int glove_topk_cosine(const float *table, int64_t V, int32_t d, int32_t planes, 
 #undef LAUNCH_RESCORE
     GLOVE_CHECK_LAUNCH();
     // guarantee fallback: flagged queries (none in the common case; the scan kernel exits at once for unflagged tiles)
-    return scan_fp32_launch(table, V, d, planes, inv_norm, query_ids, n_queries, k, w.flags, out_sim, out_idx, w.scan_ws,
-                            w.scan_bytes, stream);
+    return scan_fp32_launch(table, V, d, planes, inv_norm, qtable, qplanes, query_ids, n_queries, k, w.flags, out_sim,
+                            out_idx, w.scan_ws, w.scan_bytes, stream);
+}
+
+int glove_topk_cosine(const float *table, int64_t V, int32_t d, int32_t planes, const void *norm_bf16,
+                      const float *inv_norm, const int32_t *query_ids, int32_t n_queries, int32_t k, float *out_sim,
+                      int32_t *out_idx, void *workspace, size_t workspace_bytes, void *stream) {
+    return glove_topk_cosine_queries(table, V, d, planes, norm_bf16, inv_norm, table, planes, norm_bf16, query_ids, n_queries,
+                                     k, out_sim, out_idx, workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

@@ -626,10 +626,31 @@ class GloveEngine:
     def topk(self, query_ids, k: int, exact_fp32: bool = False):
         """Cosine top-k of the ROW embeddings of ``query_ids`` against the whole row table
         (get_predictions, ref src/models/model_utils.py:81-110).  Returns (sim [n,k] f32, idx [n,k] i32) as numpy:
-        similarities descending, ties -> lower id.  ``exact_fp32`` forces the CUDA-core scan."""
+        similarities descending, ties -> lower id.  ``exact_fp32`` forces the CUDA-core scan.
+
+        Row-sharded tables: every rank runs the same call with the same global ``query_ids``; the query rows are
+        gathered from their owners (one all-reduce), each rank ranks ALL queries against its own rows, and the per-rank
+        top-k lists are all-gathered and merged (ties -> lower global id)."""
+        if self.sharded:
+            import torch.distributed as dist
+            qrows = self.topk_shard_query_rows(query_ids)
+            dist.all_reduce(qrows)
+            sim, idx = self.topk_shard_local(qrows, k, exact_fp32)
+            n, kk = sim.shape
+            all_sim = torch.empty(self.dp_world * n * kk, dtype=torch.float32, device=self.device)
+            all_idx = torch.empty(self.dp_world * n * kk, dtype=torch.int32, device=self.device)
+            dist.all_gather_into_tensor(all_sim, sim.reshape(-1))
+            dist.all_gather_into_tensor(all_idx, idx.reshape(-1))
+            return self.topk_shard_merge(all_sim.view(self.dp_world, n, kk), all_idx.view(self.dp_world, n, kk), k)
         self.flush()
         q = torch.as_tensor(np.ascontiguousarray(query_ids, np.int32)).to(self.device)
         n = int(q.numel())
+        inv, nb = self._normalised_table()
+        sim, idx = self._topk_call(inv, nb, self.row_table, self.P, nb, q, n, k, exact_fp32)
+        torch.cuda.synchronize()
+        return sim.cpu().numpy().reshape(n, k), idx.cpu().numpy().reshape(n, k)
+
+    def _normalised_table(self):
         if self._norm_cache is None or self._norm_cache[0] != self.host_step:
             Kp, Vp = lib.glove_topk_kpad(self.d), lib.glove_topk_vpad(self.V)
             inv = torch.empty(self.V, dtype=torch.float32, device=self.device)
@@ -637,20 +658,65 @@ class GloveEngine:
             check(lib.glove_normalize_rows(_ptr(self.row_table), self.V, self.d, self.P, _ptr(nb), _ptr(inv), _stream()),
                   "glove_normalize_rows")
             self._norm_cache = (self.host_step, inv, nb)
-        _, inv, nb = self._norm_cache
+        return self._norm_cache[1], self._norm_cache[2]
+
+    def _topk_call(self, inv, nb, qtable, qplanes, qnb, q, n, k, exact_fp32):
         sim = torch.empty(n * k, dtype=torch.float32, device=self.device)
         idx = torch.empty(n * k, dtype=torch.int32, device=self.device)
         ws = torch.empty(max(lib.glove_topk_workspace_bytes(self.V, self.d, n, k), 256), dtype=torch.uint8, device=self.device)
-        if exact_fp32:
-            check(lib.glove_topk_cosine_fp32(_ptr(self.row_table), self.V, self.d, self.P, _ptr(inv), _ptr(q), n, k,
-                                             _ptr(sim), _ptr(idx), _ptr(ws), ws.numel(), _stream()), "glove_topk_cosine_fp32")
-        else:
-            check(lib.glove_topk_cosine(_ptr(self.row_table), self.V, self.d, self.P, _ptr(nb), _ptr(inv), _ptr(q), n, k,
-                                        _ptr(sim), _ptr(idx), _ptr(ws), ws.numel(), _stream()), "glove_topk_cosine")
-            if self.tc_path_covers(k):
-                cnt = ctypes.c_int32(0)
-                check(lib.glove_topk_flagged(_ptr(ws), self.V, self.d, n, k, ctypes.byref(cnt), _stream()), "glove_topk_flagged")
-                self.last_topk_fallbacks = int(cnt.value)
+        use_tc = not exact_fp32
+        check(lib.glove_topk_cosine_queries(_ptr(self.row_table), self.V, self.d, self.P, _ptr(nb) if use_tc else None, _ptr(inv),
+                                            _ptr(qtable), qplanes, _ptr(qnb) if use_tc else None, _ptr(q), n, k, _ptr(sim),
+                                            _ptr(idx), _ptr(ws), ws.numel(), _stream()), "glove_topk_cosine")
+        if use_tc and self.tc_path_covers(k):
+            cnt = ctypes.c_int32(0)
+            check(lib.glove_topk_flagged(_ptr(ws), self.V, self.d, n, k, ctypes.byref(cnt), _stream()), "glove_topk_flagged")
+            self.last_topk_fallbacks = int(cnt.value)
+        return sim, idx
+
+    # ---- row-sharded top-k, in the three phases between which the collectives sit (topk() strings them together) -----
+    def topk_shard_query_rows(self, query_ids):
+        """[n, S] fp32: the packed plane-0 rows of the queries this rank owns, zero elsewhere (sum over ranks = all rows)."""
+        self.flush()
+        q = torch.as_tensor(np.ascontiguousarray(query_ids, np.int64)).to(self.device)
+        out = torch.zeros(q.numel(), self.S, dtype=torch.float32, device=self.device)
+        mine = (q % self.dp_world) == self.dp_rank
+        rows = self.row_table.view(self.V, self.P, self.S)[:, 0, :]
+        out[mine] = rows[q[mine] // self.dp_world]
+        return out
+
+    def topk_shard_local(self, qrows, k: int, exact_fp32: bool = False):
+        """Top-k of every query (rows of ``qrows``) against the rows held here; ids are returned GLOBAL, pad rows removed.
+        One spare candidate is kept when this shard holds a pad row, so that dropping it cannot cost a real one."""
+        n = int(qrows.shape[0])
+        has_pad = self.V * self.dp_world > self.V_global
+        kk = min(k + 1, 32, self.V) if has_pad else min(k, self.V)
+        inv, nb = self._normalised_table()
+        Kp = lib.glove_topk_kpad(self.d)
+        qnb = torch.empty(lib.glove_topk_vpad(n) * Kp, dtype=torch.bfloat16, device=self.device)
+        qrows = qrows.contiguous()
+        check(lib.glove_normalize_rows(_ptr(qrows), n, self.d, 1, _ptr(qnb), None, _stream()), "glove_normalize_rows")
+        ids = torch.arange(n, dtype=torch.int32, device=self.device)
+        sim, idx = self._topk_call(inv, nb, qrows, 1, qnb, ids, n, kk, exact_fp32)
+        sim, idx = sim.view(n, kk), idx.view(n, kk)
+        gid = idx.to(torch.int64) * self.dp_world + self.dp_rank
+        bad = (idx < 0) | (gid >= self.V_global)
+        sim = torch.where(bad, torch.full_like(sim, float("-inf")), sim)
+        gid = torch.where(bad, torch.full_like(gid, -1), gid).to(torch.int32)
+        if kk < k + 1:                                                   # same list width on every rank
+            pad = k + 1 - kk
+            sim = torch.cat([sim, torch.full((n, pad), float("-inf"), device=self.device)], 1)
+            gid = torch.cat([gid, torch.full((n, pad), -1, dtype=torch.int32, device=self.device)], 1)
+        return sim.contiguous(), gid.contiguous()
+
+    def topk_shard_merge(self, all_sim, all_idx, k: int):
+        """[world, n, kk] candidate lists -> (sim [n,k], idx [n,k]) numpy."""
+        world, n, kk = all_sim.shape
+        cs = all_sim.permute(1, 0, 2).reshape(n, world * kk).contiguous()
+        ci = all_idx.permute(1, 0, 2).reshape(n, world * kk).contiguous()
+        sim = torch.empty(n * k, dtype=torch.float32, device=self.device)
+        idx = torch.empty(n * k, dtype=torch.int32, device=self.device)
+        check(lib.glove_topk_merge(_ptr(cs), _ptr(ci), n, world * kk, k, _ptr(sim), _ptr(idx), _stream()), "glove_topk_merge")
         torch.cuda.synchronize()
         return sim.cpu().numpy().reshape(n, k), idx.cpu().numpy().reshape(n, k)
 

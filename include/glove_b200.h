@@ -214,6 +214,17 @@ size_t glove_topk_workspace_bytes(int64_t V, int32_t d, int32_t n_queries, int32
 int glove_topk_cosine(const float *table, int64_t V, int32_t d, int32_t planes, const void *norm_bf16,
                       const float *inv_norm, const int32_t *query_ids, int32_t n_queries, int32_t k, float *out_sim,
                       int32_t *out_idx, void *workspace, size_t workspace_bytes, void *stream);
+/* Same, with the query vectors taken from ANOTHER packed table (qtable, qplanes, its normalised bf16 copy qnorm_bf16;
+ * query_ids index qtable): what a shard of a row-sharded table runs on the gathered query rows.  Candidate ids are rows
+ * of `table`. */
+int glove_topk_cosine_queries(const float *table, int64_t V, int32_t d, int32_t planes, const void *norm_bf16,
+                              const float *inv_norm, const float *qtable, int32_t qplanes, const void *qnorm_bf16,
+                              const int32_t *query_ids, int32_t n_queries, int32_t k, float *out_sim, int32_t *out_idx,
+                              void *workspace, size_t workspace_bytes, void *stream);
+/* k best of n_cand candidates per query (cand_idx < 0 = empty slot): descending similarity, ties -> lower id.  Last step
+ * of a row-sharded top-k (every shard contributes the top-k of its rows with ids made global). */
+int glove_topk_merge(const float *cand_sim, const int32_t *cand_idx, int32_t n_queries, int32_t n_cand, int32_t k,
+                     float *out_sim, int32_t *out_idx, void *stream);
 /* Diagnostics: number of queries of the last glove_topk_cosine call on `workspace` that failed the candidate guarantee
  * check and were recomputed by the exact scan (0 in the common case).  Synchronises. */
 int glove_topk_flagged(const void *workspace, int64_t V, int32_t d, int32_t n_queries, int32_t k, int32_t *host_count,

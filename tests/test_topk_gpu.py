@@ -85,3 +85,33 @@ def test_topk_rejects_unsupported_k():
     eng.init_uniform(0)
     with pytest.raises(GloveError):
         eng.topk(np.array([1], np.int32), 33, exact_fp32=True)
+
+
+@pytest.mark.parametrize("world,V,d,k,exact", [(2, 3001, 64, 10, False), (2, 3001, 64, 10, True), (4, 2601, 300, 20, False),
+                                               (3, 4000, 40, 31, True), (8, 9001, 300, 10, False)])
+def test_row_sharded_topk_matches_oracle(world, V, d, k, exact):
+    """Row-sharded tables (owner = id % world), emulated as `world` engines on one GPU: the three phases of
+    GloveEngine.topk with the collectives done by hand (sum of the partial query rows; stacking of the per-shard lists).
+    Ties across shards must still go to the lower GLOBAL id; the pad row of the short shards must never surface."""
+    import torch
+    from glove_tensorflow_b200.engine import GloveEngine
+    T = _table(V, d, 4)
+    T[V - 2] = T[3]                                            # a tie that straddles two shards
+    engs = []
+    for r in range(world):
+        e = GloveEngine(V, d, batch_size=64, plan_steps=1, max_steps=4, dp_rank=r, dp_world=world, dp_mode="sharded")
+        e.load_state(T, T[::-1].copy(), np.zeros(V, np.float32) + 0.3, np.zeros(V, np.float32))
+        engs.append(e)
+    q = np.array([7, V // 2, V - 1, 0, 11, 3, V - 2] + list(range(20, 20 + 90)), np.int32) % V
+    qrows = sum(e.topk_shard_query_rows(q) for e in engs)     # == dist.all_reduce
+    parts = [e.topk_shard_local(qrows, k, exact) for e in engs]
+    all_sim = torch.stack([p[0] for p in parts])               # == dist.all_gather_into_tensor
+    all_idx = torch.stack([p[1] for p in parts])
+    assert int(all_idx.max()) < V
+    sim, idx = engs[0].topk_shard_merge(all_sim, all_idx, k)
+    _check(sim, idx, T, q, k)
+    # and it is the same answer as the unsharded engine gives
+    one = GloveEngine(V, d, batch_size=64, plan_steps=1, max_steps=4)
+    one.load_state(T, T[::-1].copy(), np.zeros(V, np.float32) + 0.3, np.zeros(V, np.float32))
+    sim1, idx1 = one.topk(q, k, exact_fp32=True)
+    assert np.array_equal(idx, idx1) or np.allclose(sim, sim1, atol=5e-7)
