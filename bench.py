@@ -209,7 +209,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        steps = max(1, min(args.steps, 8 if V >= 100_000 else 64))   # bounded sample: a few steps of the same shape
+        steps = max(1, min(args.steps, 96 if V >= 100_000 else 1024))   # bounded sample (about 10 s) of the same shape
         warm = 1 if args.warmup else 0
         ups, dt, cores = cpu_reference(V, d, B_local, steps, warm)
         line = {"metric": "co-occurrence updates/sec", "value": ups, "unit": "updates/s", "n_gpus": 0, "steps": steps,
@@ -361,7 +361,7 @@ def main():
 
     cpu = None
     if not args.no_cpu_baseline and N == 1:
-        csteps = 4 if V >= 100_000 else 32
+        csteps = 96 if V >= 100_000 else 1024                      # about 10 s of CPU work on the box's host cores
         ups, dt, cores = cpu_reference(V, d, B_local, csteps, 1)
         cpu = {"value": ups, "unit": "updates/s", "cores": cores, "kind": "port",
                "sample": "%d TRAIN steps of B=%d (%.1f s), C port of the oracle with OpenMP, legacy-Keras dense Adam"
