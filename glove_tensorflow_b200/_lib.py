@@ -29,7 +29,8 @@ class StepArgs(ctypes.Structure):
                 ("loss_out", c_void), ("loss_cap", c_i32), ("plan_K", c_i32), ("V", c_i64), ("d", c_i32), ("B", c_i32),
                 ("head", c_i32), ("optimizer", c_i32), ("adam_mode", c_i32), ("learning_rate", c_f32),
                 ("l2_reg", c_f32), ("reg_scale", c_f32), ("neg_factor", c_f32), ("beta1", c_f32), ("beta2", c_f32),
-                ("epsilon", c_f32), ("dp_rank", c_i32), ("dp_world", c_i32), ("n_shards", c_i32), ("shard", c_i32)]
+                ("epsilon", c_f32), ("dp_rank", c_i32), ("dp_world", c_i32), ("n_shards", c_i32), ("shard", c_i32),
+                ("peer_gather", c_i32)]
 
 
 class CsvSchema(ctypes.Structure):
@@ -64,6 +65,7 @@ SIGNATURES = {
     "glove_train_step_profiled": (ctypes.c_int, [ctypes.POINTER(StepArgs), c_void, ctypes.POINTER(c_f32)]),
     "glove_grad_step": (ctypes.c_int, [ctypes.POINTER(StepArgs), c_void, c_void, c_void, c_void]),
     "glove_apply_step": (ctypes.c_int, [ctypes.POINTER(StepArgs), c_void, c_void, c_void, c_void]),
+    "glove_shard_set_peers": (ctypes.c_int, [ctypes.POINTER(StepArgs), ctypes.POINTER(c_void), c_i32, c_void]),
     "glove_shard_stage_step": (ctypes.c_int, [ctypes.POINTER(StepArgs), c_void]),
     "glove_shard_pack_step": (ctypes.c_int, [ctypes.POINTER(StepArgs), c_void, c_void]),
     "glove_shard_unpack_step": (ctypes.c_int, [ctypes.POINTER(StepArgs), c_void, c_void]),

@@ -48,6 +48,9 @@ struct StepParams {
     int32_t dp_rank, dp_world, dp_block;
     int32_t n_shards, shard, v_loc;   // row-sharded tables (n_shards = 1: everything is owned by shard 0)
     int32_t run_stage, run_update;
+    // peer gather (row-sharded tables, NVLink): peer_snap[side * kMaxShards + owner] = snapshot base of side `side` in the
+    // step workspace of rank `owner` (peer-mapped device memory); nullptr = opposite rows come from the local snapshot
+    const float *const *peer_snap;
 };
 
 struct StepWs {
@@ -56,6 +59,7 @@ struct StepWs {
     int32_t *long_cnt[2];
     int32_t *chunk_cnt[2];
     double *warp_out;
+    const float **peer_tab;   // [2][kMaxShards] snapshot bases of the peers (glove_shard_set_peers)
     size_t bytes;
 };
 static inline int64_t snapshot_rows(int32_t B) { return (int64_t)B + B / 4 + 64; }  // room for padded shard blocks
@@ -72,6 +76,7 @@ static StepWs step_ws_view(void *base, int32_t B, int32_t d) {
     for (int s = 0; s < 2; ++s) w.long_cnt[s] = (int32_t *)take(sizeof(int32_t) * (size_t)(B / kItemMax + 2));
     for (int s = 0; s < 2; ++s) w.chunk_cnt[s] = (int32_t *)take(sizeof(int32_t) * (size_t)max_parts_per_batch(B));
     w.warp_out = (double *)take(sizeof(double) * 3 * kMaxWarps);
+    w.peer_tab = (const float **)take(sizeof(float *) * 2 * kMaxShards);
     w.bytes = off;
     return w;
 }
@@ -458,6 +463,22 @@ __global__ void __launch_bounds__(128, (NV <= 3 ? 4 : 3)) update_kernel(const St
         const int it0 = ps.b_item[k] + oi0;
         const int nI = (p.mode == MODE_SHARD ? ps.b_own_item[k * (kMaxShards + 1) + p.shard + 1] : ps.b_item[k + 1] - ps.b_item[k]) - oi0;
         const float *opp_base = p.snap[1 - s];
+        // peer gather: position pos of the opposite snapshot lives in the block of owner pos / upad, i.e. in THAT rank's
+        // snapshot (same layout on every rank), read straight over NVLink
+        const float *const *peer = p.peer_snap ? p.peer_snap + (1 - s) * kMaxShards : nullptr;
+        const int upad_opp = peer ? max(p.side[1 - s].b_upad[k], 1) : 1;
+        auto load_opp = [&](float4 (&buf)[NV], int pos) {
+            if (peer) {
+                const float *base = reinterpret_cast<const float *>(__ldg(reinterpret_cast<const unsigned long long *>(peer + pos / upad_opp))) + (int64_t)pos * p.S;
+#pragma unroll
+                for (int r = 0; r < NV; ++r) {
+                    const int f = lane + 32 * r;
+                    buf[r] = (r < NV - 1 || f < S4) ? __ldcg(reinterpret_cast<const float4 *>(base + 4 * f)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            } else {
+                load_row_nc<NV>(buf, opp_base + (int64_t)pos * p.S, lane, S4);
+            }
+        };
         const int4 *rec = ps.rec;
         const int bcol = bias_col(p.d, s);
         int itl = warp;
@@ -483,11 +504,11 @@ __global__ void __launch_bounds__(128, (NV <= 3 ? 4 : 3)) update_kernel(const St
             int n_eff = 0;
 
             // ---- memory round 2: opposite snapshot rows, two triples per iteration with ping-pong buffers
-            load_row_nc<NV>(bufA, opp_base + (int64_t)__shfl_sync(0xffffffffu, myrec.x, 0) * p.S, lane, S4);
+            load_opp(bufA, __shfl_sync(0xffffffffu, myrec.x, 0));
 #pragma unroll 1
             for (int q = 0; q < n; q += 2) {
                 const bool hasB = q + 1 < n;
-                if (hasB) load_row_nc<NV>(bufB, opp_base + (int64_t)__shfl_sync(0xffffffffu, myrec.x, q + 1) * p.S, lane, S4);
+                if (hasB) load_opp(bufB, __shfl_sync(0xffffffffu, myrec.x, q + 1));
                 {
                     const float a = __int_as_float(__shfl_sync(0xffffffffu, myrec.y, q));
                     const float b = __int_as_float(__shfl_sync(0xffffffffu, myrec.z, q));
@@ -501,7 +522,7 @@ __global__ void __launch_bounds__(128, (NV <= 3 ? 4 : 3)) update_kernel(const St
                     axpy_row<NV>(acc, e, bufA);
                 }
                 if (hasB) {
-                    if (q + 2 < n) load_row_nc<NV>(bufA, opp_base + (int64_t)__shfl_sync(0xffffffffu, myrec.x, q + 2) * p.S, lane, S4);
+                    if (q + 2 < n) load_opp(bufA, __shfl_sync(0xffffffffu, myrec.x, q + 2));
                     const float a = __int_as_float(__shfl_sync(0xffffffffu, myrec.y, q + 1));
                     const float b = __int_as_float(__shfl_sync(0xffffffffu, myrec.z, q + 1));
                     float e, l;
@@ -715,6 +736,7 @@ static int fill_params(const glove_step_args *a, StepParams &p, int mode) {
     GLOVE_REQUIRE(p.n_shards == 1 || mode != MODE_TRAIN, "step: row-sharded tables need the stage / update / finish split");
     p.v_loc = (int32_t)((a->V + p.n_shards - 1) / p.n_shards);
     p.run_stage = p.run_update = 1;
+    p.peer_snap = (a->peer_gather && p.n_shards > 1) ? w.peer_tab : nullptr;
     return GLOVE_OK;
 }
 
@@ -781,6 +803,25 @@ size_t glove_step_snapshot_offset(int32_t B, int32_t d, int32_t side) {
     if (B <= 0 || d <= 0 || side < 0 || side > 1) return 0;
     StepWs w = step_ws_view((void *)256, B, d);   // any non-null base: offsets are relative to it
     return (size_t)((char *)w.snap[side] - (char *)256);
+}
+
+// Row-sharded tables, peer gather: records where every rank's snapshot lives.  peer_workspaces[r] = base of rank r's step
+// workspace as mapped in THIS process (symmetric / IPC memory; entry `shard` is the local one), same B and d everywhere.
+int glove_shard_set_peers(const glove_step_args *args, const void *const *peer_workspaces, int32_t n_peers, void *stream) {
+    GLOVE_REQUIRE(args && args->workspace && peer_workspaces && n_peers > 1 && n_peers <= kMaxShards,
+                  "glove_shard_set_peers: bad arguments");
+    StepWs w = step_ws_view(args->workspace, args->B, args->d);
+    if (args->workspace_bytes < w.bytes)
+        return set_error(GLOVE_EWORKSPACE, "glove_shard_set_peers: workspace %zu < required %zu", args->workspace_bytes, w.bytes);
+    const float *tab[2 * kMaxShards] = {};
+    for (int r = 0; r < n_peers; ++r) {
+        GLOVE_REQUIRE(peer_workspaces[r], "glove_shard_set_peers: null workspace of rank %d", r);
+        StepWs pw = step_ws_view(const_cast<void *>(peer_workspaces[r]), args->B, args->d);
+        for (int s = 0; s < 2; ++s) tab[s * kMaxShards + r] = pw.snap[s];
+    }
+    GLOVE_CHECK_CUDA(cudaMemcpyAsync(w.peer_tab, tab, sizeof(tab), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    GLOVE_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return GLOVE_OK;
 }
 
 int glove_train_step(const glove_step_args *args, void *stream) {

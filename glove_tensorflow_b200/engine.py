@@ -442,6 +442,31 @@ class GloveEngine:
         check(lib.glove_shard_stage_step(ctypes.byref(self._args[which]), _stream()), "glove_shard_stage_step")
         return upad
 
+    def set_peer_workspaces(self, ptrs):
+        """Row-sharded peer gather: ``ptrs[r]`` = base of rank r's step workspace as mapped in THIS process.  From now on
+        the update kernel reads the opposite snapshot rows from their owners' memory (NVLink); no exchange launches."""
+        arr = (ctypes.c_void_p * len(ptrs))(*[int(p) for p in ptrs])
+        check(lib.glove_shard_set_peers(ctypes.byref(self._args[0]), arr, len(ptrs), _stream()), "glove_shard_set_peers")
+        for a in self._args:
+            a.peer_gather = 1
+        self.shard_exchange = "peer"
+
+    def enable_peer_gather(self, group=None):
+        """Collective: moves the step workspace into symmetric (peer-mapped) memory and registers every rank's mapping."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        assert self.sharded, "peer gather is the exchange of the row-sharded scheme"
+        self._join_side()
+        torch.cuda.synchronize()
+        ws = symm_mem.empty(self.step_ws.numel(), dtype=torch.uint8, device=self.device)
+        ws.zero_()                                                     # the step workspace must start zeroed
+        self._symm = symm_mem.rendezvous(ws, group if group is not None else dist.group.WORLD)
+        self.step_ws = ws
+        self._args = [self._make_args(i) for i in range(2)]
+        self.set_peer_workspaces(list(self._symm.buffer_ptrs))
+        torch.cuda.synchronize()
+        self._symm.barrier()
+
     def shard_update(self):
         which = self._plan_for(self.host_step)
         check(lib.glove_shard_update_step(ctypes.byref(self._args[which]), _ptr(self._shard_scalars()), _stream()), "glove_shard_update_step")
@@ -485,11 +510,17 @@ class GloveEngine:
         """Owner-computes: stage own rows -> exchange snapshot rows -> fused update of the own segments (in place) ->
         all-reduce of the 3 loss scalars -> finish.  No gradient exchange.  `shard_exchange`:
         'alltoall' (default) sends every owner's rows only to the shards whose work items need them (request lists from the
-        plan, one all_to_all_single with uneven splits); 'allgather' sends every block to everyone (equal-sized native)."""
+        plan, one all_to_all_single with uneven splits); 'allgather' sends every block to everyone (equal-sized native);
+        'peer' (after enable_peer_gather) moves nothing ahead of time: the update kernel reads remote rows over NVLink."""
         import torch.distributed as dist
         upad = self.shard_stage()
         N, r = self.dp_world, self.dp_rank
-        if self.shard_exchange == "alltoall":
+        if self.shard_exchange == "peer":
+            # no exchange at all: once every rank has staged its rows (barrier), the update kernel gathers the opposite
+            # rows from their owners' snapshots over NVLink; the all-reduce below keeps the next stage from overwriting a
+            # snapshot that a peer still reads
+            self._symm.barrier()
+        elif self.shard_exchange == "alltoall":
             send, recv = self.shard_pack()
             dist.all_to_all_single(self._xbuf[1][: sum(recv)], self._xbuf[0][: sum(send)], recv, send)
             self.shard_unpack()

@@ -137,6 +137,10 @@ typedef struct glove_step_args {
     /* row-sharded tables (n_shards > 1): this process holds the rows with id % n_shards == shard (local row id /
      * n_shards, V_local = ceil(V / n_shards)); the plan must come from glove_prepare_batches_sharded.  0 / 1 = not sharded. */
     int32_t n_shards, shard;
+    /* row-sharded tables: 1 = glove_shard_update_step gathers the opposite snapshot rows straight from their owners'
+     * workspaces over NVLink (peer-mapped memory registered with glove_shard_set_peers) instead of from rows that a
+     * collective copied into the local snapshot. */
+    int32_t peer_gather;
 } glove_step_args;
 
 size_t glove_step_workspace_bytes(int32_t B, int32_t d);
@@ -173,6 +177,13 @@ int glove_apply_step(const glove_step_args *args, const float *grad_rows, const 
  * (b) all-to-all of REQUESTED rows only -- glove_shard_pack_step gathers, for every peer, the rows of this shard's block
  * that the peer's work items need (request lists built at plan time, see glove_plan_need_info) into send_buf;
  * all_to_all(v); glove_shard_unpack_step scatters the received rows to their snapshot positions. */
+/* (c) peer gather: no exchange launch at all.  Every rank allocates its step workspace in peer-mapped memory (CUDA IPC /
+ * symmetric memory), registers all of them once with glove_shard_set_peers, sets args->peer_gather = 1, and runs
+ *   stage -> barrier across ranks -> glove_shard_update_step -> all-reduce of loss_scalars (doubles as the barrier that
+ *   keeps the next stage from overwriting a snapshot a peer still reads) -> finish.
+ * The update kernel then loads each opposite row from the snapshot of its owner (position / padded block size) through
+ * NVLink, overlapping the transfer with its arithmetic warp by warp. */
+int glove_shard_set_peers(const glove_step_args *args, const void *const *peer_workspaces, int32_t n_peers, void *stream);
 int glove_shard_stage_step(const glove_step_args *args, void *stream);
 int glove_shard_pack_step(const glove_step_args *args, float *send_buf, void *stream);
 int glove_shard_unpack_step(const glove_step_args *args, const float *recv_buf, void *stream);

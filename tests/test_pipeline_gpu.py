@@ -128,7 +128,8 @@ def test_host_entry_point_matches_device_path():
     assert np.max(np.abs(state["R"] - ref.R)) / np.max(np.abs(ref.R)) < 1e-5
 
 
-def test_host_entry_pipelined_call_is_bit_identical_to_chunked_calls():
+@pytest.mark.parametrize("optimizer,adam_mode", [("Adam", "replay"), ("Adam", "lazy"), ("Adagrad", "replay")])
+def test_host_entry_pipelined_call_is_bit_identical_to_chunked_calls(optimizer, adam_mode):
     """One glove_train_steps_host call over 6 plan chunks (H2D + plan of chunk c+1 and the Adam catch-up overlap the
     steps in flight) == 6 calls of one chunk each == the device-resident path, bit for bit; and == the oracle to 1e-5."""
     import torch
@@ -139,7 +140,7 @@ def test_host_entry_pipelined_call_is_bit_identical_to_chunked_calls():
     pin = {k: torch.from_numpy(coo[k].copy()).pin_memory() for k in ("row", "col", "target", "weight")}
 
     def run(calls):
-        eng = GloveEngine(V, d, learning_rate=0.01, batch_size=B, plan_steps=K, max_steps=64)
+        eng = GloveEngine(V, d, optimizer=optimizer, adam_mode=adam_mode, learning_rate=0.01, batch_size=B, plan_steps=K, max_steps=64)
         eng.load_state(st.R, st.C, st.rb, st.cb, st.g)
         per = chunks // calls * K * B
         losses = []
@@ -154,13 +155,15 @@ def test_host_entry_pipelined_call_is_bit_identical_to_chunked_calls():
     assert np.array_equal(l1, l6) and np.array_equal(l1, l2)
     for k in ("R", "C", "rb", "cb"):
         assert np.array_equal(s1[k], s6[k]) and np.array_equal(s1[k], s2[k]), k
-    dev = GloveEngine(V, d, learning_rate=0.01, batch_size=B, plan_steps=K, max_steps=64)
+    dev = GloveEngine(V, d, optimizer=optimizer, adam_mode=adam_mode, learning_rate=0.01, batch_size=B, plan_steps=K, max_steps=64)
     dev.load_state(st.R, st.C, st.rb, st.cb, st.g)
     dev.set_coo(coo["row"], coo["col"], coo["target"], coo["weight"])
     dev.set_batches(np.arange(chunks * K * B).reshape(chunks * K, B))
     ld = dev.train(chunks * K)
     assert np.array_equal(ld, l1) and np.array_equal(dev.get_state()["R"], s1["R"])
+    if adam_mode == "lazy":
+        return                                        # LazyAdam is not the reference's optimizer: no oracle for it
     ref = st.copy()
-    want = np.array(o.train(ref, coo, np.arange(chunks * K * B).reshape(chunks * K, B), learning_rate=0.01))
+    want = np.array(o.train(ref, coo, np.arange(chunks * K * B).reshape(chunks * K, B), optimizer=optimizer, learning_rate=0.01))
     assert np.max(np.abs(l1 - want) / np.abs(want)) < 1e-5
     assert np.max(np.abs(s1["R"] - ref.R)) / np.max(np.abs(ref.R)) < 1e-5
