@@ -96,6 +96,7 @@ class GloveEngine:
         self.shard_exchange = "alltoall"
         self.prep_ws = torch.empty(lib.glove_prepare_workspace_bytes(self.K, self.B), **u8)
         self.step_ws = torch.zeros(lib.glove_step_workspace_bytes(self.B, self.d), **u8)   # must start zeroed
+        self._plan_override = None
         self.coo = None
         self.nnz = 0
         self.shuffle_key = 0
@@ -327,6 +328,9 @@ class GloveEngine:
         self._ev_plan[which] = ev
 
     def _plan_for(self, step: int) -> int:
+        ov = self._plan_override
+        if ov is not None and ov[1] <= step < ov[1] + self.K:       # a chunk planned from host buffers, any alignment
+            return ov[0]
         first = (step // self.K) * self.K
         which = (step // self.K) & 1
         if self.plan_first[which] != first:
@@ -347,7 +351,8 @@ class GloveEngine:
         if self._ev_catchup is not None and self._ev_catchup[0] == s:
             main.wait_event(self._ev_catchup[1])
         self._ev_catchup = None
-        if (self.optimizer == "Adam" and self.adam_mode == "replay" and (s + 1) % self.K != 0 and s + 1 < self.max_steps
+        k_next = s + 1 - self.plan_first[which] if self.plan_first[which] is not None else 0
+        if (self.optimizer == "Adam" and self.adam_mode == "replay" and 0 < k_next < self.K and s + 1 < self.max_steps
                 and s >= 1):
             self._side.wait_event(self._ev_step_done[(s - 1) & 1])
             check(lib.glove_catchup_step(ctypes.byref(self._args[which]), s + 1, ctypes.c_void_p(self._side.cuda_stream)),
@@ -355,7 +360,7 @@ class GloveEngine:
             ev = torch.cuda.Event()
             ev.record(self._side)
             self._ev_catchup = (s + 1, ev)
-        if s % self.K == 0:
+        if s % self.K == 0 and self._plan_override is None:
             self._prefetch_plan(s)
 
     def _after_step(self):
@@ -610,6 +615,7 @@ class GloveEngine:
         self._plan_need[which] = None
         self.plan_first = [None, None]
         self.plan_first[which] = first
+        self._plan_override = (which, first)
         a = self._args[which]
         for _ in range(self.K):
             if self.sharded:
@@ -624,6 +630,7 @@ class GloveEngine:
             else:
                 check(lib.glove_train_step(ctypes.byref(a), _stream()), "glove_train_step")
             self.host_step += 1
+        self._plan_override = None
         self.plan_first = [None, None]
         idx = torch.arange(first, first + self.K, device=self.device) % self.loss_cap
         return self.loss_out[idx].cpu().numpy()      # D2H of the K losses (synchronises)

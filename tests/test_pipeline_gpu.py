@@ -167,3 +167,30 @@ def test_host_entry_pipelined_call_is_bit_identical_to_chunked_calls(optimizer, 
     want = np.array(o.train(ref, coo, np.arange(chunks * K * B).reshape(chunks * K, B), optimizer=optimizer, learning_rate=0.01))
     assert np.max(np.abs(l1 - want) / np.abs(want)) < 1e-5
     assert np.max(np.abs(s1["R"] - ref.R)) / np.max(np.abs(ref.R)) < 1e-5
+
+
+def test_train_chunk_from_host_at_any_step_alignment():
+    """The data-parallel-aware host entry (bench e2e at N > 1; here N = 1): a chunk planned from HOST buffers must be the
+    one the steps use even when the current step is not a multiple of plan_steps, and the device-resident plan prefetch
+    must not overwrite it."""
+    import torch
+    from glove_tensorflow_b200.engine import GloveEngine
+    V, d, n, B, K = 800, 24, 16384, 256, 4
+    coo = make_coo(V, n, 41)
+    st = o.init_state(V, d, 42)
+    pre = np.random.default_rng(43).integers(0, n, (3, B))              # 3 device-resident steps first: host_step = 3
+    host_idx = np.random.default_rng(44).integers(0, n, (2 * K, B))     # then two host-fed chunks
+    ref = st.copy()
+    want = np.array(o.train(ref, coo, np.concatenate([pre, host_idx]), learning_rate=0.01))
+    eng = GloveEngine(V, d, learning_rate=0.01, batch_size=B, plan_steps=K, max_steps=64)
+    eng.load_state(st.R, st.C, st.rb, st.cb, st.g)
+    eng.set_coo(coo["row"], coo["col"], coo["target"], coo["weight"])
+    eng.set_batches(np.concatenate([pre, np.zeros((2 * K + 8, B), np.int64)]))   # resident batches differ from the host-fed ones
+    got = list(eng.train(3))
+    for c in range(2):
+        sel = host_idx[c * K:(c + 1) * K].reshape(-1)
+        pin = [torch.from_numpy(coo[k][sel].copy()).pin_memory() for k in ("row", "col", "target", "weight")]
+        got += list(eng.train_chunk_from_host(*pin))
+    assert eng.host_step == 3 + 2 * K
+    assert np.max(np.abs(np.array(got) - want) / np.abs(want)) < 1e-5
+    assert np.max(np.abs(eng.get_state()["R"] - ref.R)) / np.max(np.abs(ref.R)) < 1e-5
