@@ -191,7 +191,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cold-state", action="store_true", help="start from step 0 with empty Adam state")
-    ap.add_argument("--shard-exchange", default="alltoall", choices=["alltoall", "allgather", "peer"])
+    ap.add_argument("--shard-exchange", default="peer", choices=["alltoall", "allgather", "peer", "peer-direct"],
+                    help="N>1, row-sharded tables: how the snapshot rows reach the shards that need them (peer = one pull "
+                         "kernel over NVLink peer memory; falls back to alltoall when symmetric memory is unavailable)")
     ap.add_argument("--dp-mode", default="sharded", choices=["sharded", "replicated"],
                     help="N>1: row-sharded tables (owner-computes) or replicated tables with gradient all-reduce")
     args = ap.parse_args()
@@ -244,8 +246,14 @@ def main():
                       adam_mode=args.adam_mode, batch_size=B, plan_steps=K, max_steps=T0 + 2 * total_steps + steps,
                       device=dev, dp_rank=rank, dp_world=N, dp_mode=args.dp_mode)
     eng.shard_exchange = args.shard_exchange
-    if args.shard_exchange == "peer" and world > 1 and args.dp_mode == "sharded":
-        eng.enable_peer_gather()
+    if args.shard_exchange.startswith("peer") and world > 1 and args.dp_mode == "sharded":
+        try:
+            eng.enable_peer_gather(direct=args.shard_exchange == "peer-direct")
+        except Exception as exc:   # no peer-mapped memory on this box: same exchange through NCCL
+            print("bench: peer memory unavailable (%s); using the all-to-all exchange" % exc, file=sys.stderr)
+            args.shard_exchange = eng.shard_exchange = "alltoall"
+    elif world <= 1 or args.dp_mode != "sharded":
+        args.shard_exchange = eng.shard_exchange = "alltoall"
     eng.init_uniform(seed=1)                                   # same seed on every rank: replicas start identical
     row, col, tgt, wgt = gen_coo_device(V, nnz, 1234, dev)     # replicated COO (weak scaling: B grows with N)
     eng.set_coo(row, col, tgt, wgt, shuffle_key=0xC0FFEE)

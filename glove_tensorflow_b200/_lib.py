@@ -66,6 +66,7 @@ SIGNATURES = {
     "glove_grad_step": (ctypes.c_int, [ctypes.POINTER(StepArgs), c_void, c_void, c_void, c_void]),
     "glove_apply_step": (ctypes.c_int, [ctypes.POINTER(StepArgs), c_void, c_void, c_void, c_void]),
     "glove_shard_set_peers": (ctypes.c_int, [ctypes.POINTER(StepArgs), ctypes.POINTER(c_void), c_i32, c_void]),
+    "glove_shard_pull_step": (ctypes.c_int, [ctypes.POINTER(StepArgs), c_void]),
     "glove_shard_stage_step": (ctypes.c_int, [ctypes.POINTER(StepArgs), c_void]),
     "glove_shard_pack_step": (ctypes.c_int, [ctypes.POINTER(StepArgs), c_void, c_void]),
     "glove_shard_unpack_step": (ctypes.c_int, [ctypes.POINTER(StepArgs), c_void, c_void]),

@@ -663,6 +663,63 @@ __global__ void __launch_bounds__(256) exchange_kernel(const StepParams p, float
     }
 }
 
+// PULL (peer-mapped workspaces): every row this shard's work items need from another owner is read ONCE from that owner's
+// snapshot over NVLink and written to the same position of the local snapshot -- pack + all-to-all + unpack in one launch,
+// with no send / receive buffers.  One warp per row, two rows in flight per warp.
+__global__ void __launch_bounds__(256) pull_kernel(const StepParams p, const float *const *peer_tab) {
+    int k, step;
+    if (!batch_index(p, k, step)) return;
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int S4 = p.S >> 2;
+    const int me = p.shard, N = p.n_shards;
+    constexpr int W = kMaxShards + 1;
+    // flattened list of (owner, side) blocks: first[b] = first global row index of block b
+    int first[2 * kMaxShards + 1];
+    first[0] = 0;
+#pragma unroll
+    for (int b = 0; b < 2 * kMaxShards; ++b) {
+        const int q = b >> 1, s = b & 1;
+        int n = 0;
+        if (q < N && q != me) {
+            const int32_t *off = p.side[s].need_off + ((int64_t)k * kMaxShards + me) * W;
+            n = off[q + 1] - off[q];
+        }
+        first[b + 1] = first[b] + n;
+    }
+    const int total = first[2 * kMaxShards];
+    auto locate = [&](int i, const float *&src, float *&dst) {
+        int b = 0;
+#pragma unroll
+        for (int c = 1; c < 2 * kMaxShards; ++c) b += (i >= first[c]);
+        const int q = b >> 1, s = b & 1;
+        const int32_t *off = p.side[s].need_off + ((int64_t)k * kMaxShards + me) * W;
+        const int pos = p.side[s].need_pos[off[q] + (i - first[b])];
+        src = peer_tab[(1 - s) * kMaxShards + q] + (int64_t)pos * p.S;
+        dst = p.snap[1 - s] + (int64_t)pos * p.S;
+    };
+    for (int i = 2 * warp; i < total; i += 2 * nwarps) {
+        const float *sa, *sb = nullptr;
+        float *da, *db = nullptr;
+        locate(i, sa, da);
+        const bool two = i + 1 < total;
+        if (two) locate(i + 1, sb, db);
+        float4 va[4], vb[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int f = lane + 32 * r;
+            if (f < S4) va[r] = __ldcg(reinterpret_cast<const float4 *>(sa + 4 * f));
+            if (two && f < S4) vb[r] = __ldcg(reinterpret_cast<const float4 *>(sb + 4 * f));
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int f = lane + 32 * r;
+            if (f < S4) st4(da + 4 * f, va[r]);
+            if (two && f < S4) st4(db + 4 * f, vb[r]);
+        }
+    }
+}
+
 // ---- DP apply: one warp per segment, gradient comes from the all-reduced dense buffer -------------------------------
 template <int NV>
 __global__ void __launch_bounds__(128) apply_kernel(const StepParams p) {
@@ -736,7 +793,7 @@ static int fill_params(const glove_step_args *a, StepParams &p, int mode) {
     GLOVE_REQUIRE(p.n_shards == 1 || mode != MODE_TRAIN, "step: row-sharded tables need the stage / update / finish split");
     p.v_loc = (int32_t)((a->V + p.n_shards - 1) / p.n_shards);
     p.run_stage = p.run_update = 1;
-    p.peer_snap = (a->peer_gather && p.n_shards > 1) ? w.peer_tab : nullptr;
+    p.peer_snap = (a->peer_gather == 1 && p.n_shards > 1) ? w.peer_tab : nullptr;   // 1: gather inside the update kernel
     return GLOVE_OK;
 }
 
@@ -905,6 +962,17 @@ int glove_shard_pack_step(const glove_step_args *args, float *send_buf, void *st
     if (rc != GLOVE_OK) return rc;
     GLOVE_REQUIRE(send_buf, "glove_shard_pack_step: null buffer");
     exchange_kernel<true><<<kNumSMs * 4, 256, 0, (cudaStream_t)stream>>>(p, send_buf);
+    GLOVE_CHECK_LAUNCH();
+    return GLOVE_OK;
+}
+
+int glove_shard_pull_step(const glove_step_args *args, void *stream) {
+    StepParams p;
+    int rc = fill_params(args, p, MODE_SHARD);
+    if (rc != GLOVE_OK) return rc;
+    GLOVE_REQUIRE(p.n_shards > 1 && args->peer_gather, "glove_shard_pull_step: needs row-sharded tables and registered peers");
+    StepWs w = step_ws_view(args->workspace, args->B, args->d);
+    pull_kernel<<<kNumSMs * 4, 256, 0, (cudaStream_t)stream>>>(p, w.peer_tab);
     GLOVE_CHECK_LAUNCH();
     return GLOVE_OK;
 }

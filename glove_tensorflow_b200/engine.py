@@ -447,16 +447,21 @@ class GloveEngine:
         check(lib.glove_shard_stage_step(ctypes.byref(self._args[which]), _stream()), "glove_shard_stage_step")
         return upad
 
-    def set_peer_workspaces(self, ptrs):
-        """Row-sharded peer gather: ``ptrs[r]`` = base of rank r's step workspace as mapped in THIS process.  From now on
-        the update kernel reads the opposite snapshot rows from their owners' memory (NVLink); no exchange launches."""
+    def set_peer_workspaces(self, ptrs, direct: bool = False):
+        """Row-sharded tables over peer memory: ``ptrs[r]`` = base of rank r's step workspace as mapped in THIS process.
+        From now on the requested snapshot rows are pulled from their owners by one kernel (``shard_exchange='peer'``) or,
+        with ``direct``, read by the update kernel itself while it computes (``'peer-direct'``); no NCCL data movement."""
         arr = (ctypes.c_void_p * len(ptrs))(*[int(p) for p in ptrs])
         check(lib.glove_shard_set_peers(ctypes.byref(self._args[0]), arr, len(ptrs), _stream()), "glove_shard_set_peers")
         for a in self._args:
-            a.peer_gather = 1
-        self.shard_exchange = "peer"
+            a.peer_gather = 1 if direct else 2
+        self.shard_exchange = "peer-direct" if direct else "peer"
 
-    def enable_peer_gather(self, group=None):
+    def shard_pull(self):
+        which = self._plan_for(self.host_step)
+        check(lib.glove_shard_pull_step(ctypes.byref(self._args[which]), _stream()), "glove_shard_pull_step")
+
+    def enable_peer_gather(self, group=None, direct: bool = False):
         """Collective: moves the step workspace into symmetric (peer-mapped) memory and registers every rank's mapping."""
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
@@ -468,7 +473,7 @@ class GloveEngine:
         self._symm = symm_mem.rendezvous(ws, group if group is not None else dist.group.WORLD)
         self.step_ws = ws
         self._args = [self._make_args(i) for i in range(2)]
-        self.set_peer_workspaces(list(self._symm.buffer_ptrs))
+        self.set_peer_workspaces(list(self._symm.buffer_ptrs), direct)
         torch.cuda.synchronize()
         self._symm.barrier()
 
@@ -520,11 +525,13 @@ class GloveEngine:
         import torch.distributed as dist
         upad = self.shard_stage()
         N, r = self.dp_world, self.dp_rank
-        if self.shard_exchange == "peer":
-            # no exchange at all: once every rank has staged its rows (barrier), the update kernel gathers the opposite
-            # rows from their owners' snapshots over NVLink; the all-reduce below keeps the next stage from overwriting a
-            # snapshot that a peer still reads
+        if self.shard_exchange in ("peer", "peer-direct"):
+            # no NCCL data movement: once every rank has staged its rows (barrier), one kernel pulls the requested rows
+            # from their owners' snapshots over NVLink ('peer'), or the update kernel reads them there while it computes
+            # ('peer-direct'); the all-reduce below keeps the next stage from overwriting a block that a peer still reads
             self._symm.barrier()
+            if self.shard_exchange == "peer":
+                self.shard_pull()
         elif self.shard_exchange == "alltoall":
             send, recv = self.shard_pack()
             dist.all_to_all_single(self._xbuf[1][: sum(recv)], self._xbuf[0][: sum(send)], recv, send)

@@ -137,9 +137,9 @@ typedef struct glove_step_args {
     /* row-sharded tables (n_shards > 1): this process holds the rows with id % n_shards == shard (local row id /
      * n_shards, V_local = ceil(V / n_shards)); the plan must come from glove_prepare_batches_sharded.  0 / 1 = not sharded. */
     int32_t n_shards, shard;
-    /* row-sharded tables: 1 = glove_shard_update_step gathers the opposite snapshot rows straight from their owners'
-     * workspaces over NVLink (peer-mapped memory registered with glove_shard_set_peers) instead of from rows that a
-     * collective copied into the local snapshot. */
+    /* row-sharded tables with peer-mapped workspaces (glove_shard_set_peers): 2 = the requested rows are pulled into the
+     * local snapshot by glove_shard_pull_step; 1 = no pull, glove_shard_update_step gathers every opposite row straight
+     * from its owner's workspace over NVLink; 0 = rows arrive through a collective (pack / unpack or all-gather). */
     int32_t peer_gather;
 } glove_step_args;
 
@@ -177,12 +177,15 @@ int glove_apply_step(const glove_step_args *args, const float *grad_rows, const 
  * (b) all-to-all of REQUESTED rows only -- glove_shard_pack_step gathers, for every peer, the rows of this shard's block
  * that the peer's work items need (request lists built at plan time, see glove_plan_need_info) into send_buf;
  * all_to_all(v); glove_shard_unpack_step scatters the received rows to their snapshot positions. */
-/* (c) peer gather: no exchange launch at all.  Every rank allocates its step workspace in peer-mapped memory (CUDA IPC /
- * symmetric memory), registers all of them once with glove_shard_set_peers, sets args->peer_gather = 1, and runs
- *   stage -> barrier across ranks -> glove_shard_update_step -> all-reduce of loss_scalars (doubles as the barrier that
- *   keeps the next stage from overwriting a snapshot a peer still reads) -> finish.
- * The update kernel then loads each opposite row from the snapshot of its owner (position / padded block size) through
- * NVLink, overlapping the transfer with its arithmetic warp by warp. */
+/* (c) peer memory: no NCCL data movement at all.  Every rank allocates its step workspace in peer-mapped memory (CUDA
+ * IPC / symmetric memory) and registers all of them once with glove_shard_set_peers.  A step is
+ *   stage -> barrier across ranks -> [glove_shard_pull_step] -> glove_shard_update_step -> all-reduce of loss_scalars
+ *   (doubles as the barrier that keeps the next stage from overwriting a snapshot block a peer still reads) -> finish.
+ * peer_gather = 2: glove_shard_pull_step reads every REQUESTED row once from its owner's snapshot over NVLink and writes
+ * it to the same position of the local snapshot (pack + all-to-all + unpack in one launch, no staging buffers);
+ * peer_gather = 1: no pull; the update kernel loads each opposite row from the snapshot of its owner (position / padded
+ * block size) while it computes -- one launch fewer, but a row is fetched once per triple instead of once per step. */
+int glove_shard_pull_step(const glove_step_args *args, void *stream);
 int glove_shard_set_peers(const glove_step_args *args, const void *const *peer_workspaces, int32_t n_peers, void *stream);
 int glove_shard_stage_step(const glove_step_args *args, void *stream);
 int glove_shard_pack_step(const glove_step_args *args, float *send_buf, void *stream);

@@ -221,7 +221,7 @@ def test_overlap_streams_do_not_change_results():
         assert np.array_equal(out[0][1][k], out[1][1][k]), k
 
 
-@pytest.mark.parametrize("exchange", ["alltoall", "allgather", "peer"])
+@pytest.mark.parametrize("exchange", ["alltoall", "allgather", "peer", "peer-direct"])
 @pytest.mark.parametrize("world,adam_mode,optimizer,V", [(2, "replay", "Adam", 601), (4, "replay", "Adam", 1000),
                                                          (3, "lazy", "Adam", 333), (2, "replay", "Adagrad", 64),
                                                          (8, "replay", "Adam", 5000)])
@@ -246,16 +246,19 @@ def test_row_sharded_tables_on_one_gpu(world, adam_mode, optimizer, V, exchange)
         e.set_coo(coo["row"], coo["col"], coo["target"], coo["weight"])
         e.set_batches(batches)
         engs.append(e)
-    if exchange == "peer":                                         # on one GPU every "peer" workspace is plain device memory
+    if exchange.startswith("peer"):                                # on one GPU every "peer" workspace is plain device memory
         for e in engs:
-            e.set_peer_workspaces([x.step_ws.data_ptr() for x in engs])
+            e.set_peer_workspaces([x.step_ws.data_ptr() for x in engs], direct=exchange == "peer-direct")
     losses = []
     for s in range(steps):
         upads = [e.shard_stage() for e in engs]
         assert all(u == upads[0] for u in upads)
         torch.cuda.synchronize()
-        if exchange == "peer":
+        if exchange == "peer-direct":
             pass                                                   # the update kernels read each other's snapshots directly
+        elif exchange == "peer":
+            for e in engs:
+                e.shard_pull()                                     # one kernel: requested rows, owner's snapshot -> mine
         elif exchange == "allgather":
             for side in (0, 1):
                 u = upads[0][side]

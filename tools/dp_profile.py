@@ -10,6 +10,7 @@ torch.cuda.set_device(dev); dist.init_process_group("nccl", device_id=dev)
 V, d, Bl = 400000, 300, 65536; B = Bl * world
 eng = GloveEngine(V, d, batch_size=B, plan_steps=16, max_steps=4096 + 2048, device=dev, dp_rank=rank, dp_world=world, dp_mode=mode)
 eng.init_uniform(1); row, col, t, w = bench.gen_coo_device(V, 1 << 24, 1234, dev); eng.set_coo(row, col, t, w, shuffle_key=1)
+if len(sys.argv) > 2 and sys.argv[2].startswith("peer"): eng.enable_peer_gather(direct=sys.argv[2] == "peer-direct")
 bench.steady_state(eng, V, B, 99)
 for _ in range(20): eng.step()
 torch.cuda.synchronize(); dist.barrier()
@@ -20,7 +21,10 @@ for _ in range(n):
     if mode == "sharded":
         ev[0].record(); upad = eng.shard_stage(); ev[1].record()
         N, r = world, rank
-        if len(sys.argv) > 2 and sys.argv[2] == "allgather":
+        if len(sys.argv) > 2 and sys.argv[2].startswith("peer"):
+            eng._symm.barrier()
+            if sys.argv[2] == "peer": eng.shard_pull()
+        elif len(sys.argv) > 2 and sys.argv[2] == "allgather":
             for side in (0, 1):
                 snap, u = eng.snapshot_view(side), upad[side]
                 dist.all_gather_into_tensor(snap[: N * u], snap[r * u:(r + 1) * u])
