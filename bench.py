@@ -323,10 +323,10 @@ def main():
     e2e = None
     if not args.no_e2e:
         # one call = CALL plan chunks (N == 1: pipelined inside glove_train_steps_host); host buffers of `pool` calls rotate
-        CALL = 8 if N == 1 else 1
+        CALL = 8 if N == 1 else 4
         KC = K * CALL
         n_chunks = max(1, args.steps // KC)
-        pool = 2 if N == 1 else 4
+        pool = 2
         hr = [torch.empty(KC * B, dtype=torch.int32).pin_memory() for _ in range(pool)]
         hc = [torch.empty(KC * B, dtype=torch.int32).pin_memory() for _ in range(pool)]
         ha = [torch.empty(KC * B, dtype=torch.float32).pin_memory() for _ in range(pool)]
@@ -341,7 +341,8 @@ def main():
             if N == 1:
                 eng.train_steps_host(hr[i], hc[i], ha[i], hb[i], hl)      # one C-ABI call, HOST buffers in / losses out
             else:
-                eng.train_chunk_from_host(hr[i], hc[i], ha[i], hb[i])
+                KB = K * B
+                eng.train_chunks_from_host([tuple(t[i][j * KB:(j + 1) * KB] for t in (hr, hc, ha, hb)) for j in range(CALL)])
         chunk(0)                                                          # warm
         torch.cuda.synchronize()
         if world > 1:
@@ -361,8 +362,8 @@ def main():
                "d2h_bytes_per_step": 4 + 4.0 / KC, "steps": n_chunks * KC,
                "path": ("glove_train_steps_host, %d steps per call: pinned host COO -> H2D -> plans -> steps -> D2H losses; inside a "
                         "call the copy + plan of chunk c+1 overlap the steps of chunk c" % KC if N == 1 else
-                        "GloveEngine.train_chunk_from_host on every rank: pinned host COO (global batch) -> H2D -> plan -> "
-                        "K x (grad_step, NCCL all-reduce, apply_step) -> D2H losses")}
+                        "GloveEngine.train_chunks_from_host on every rank, %d steps per call: pinned host COO (global batch) -> "
+                        "H2D -> plans -> sharded steps -> D2H losses; copy + plan of chunk c+1 overlap the steps of chunk c" % KC)}
 
     if rank != 0:
         if world > 1:

@@ -597,50 +597,79 @@ class GloveEngine:
         self.plan_first = [None, None]
 
     def train_chunk_from_host(self, host_row, host_col, host_a, host_b):
-        """End-to-end chunk for any world size (data-parallel aware): K*B explicit triples from pinned HOST tensors are
-        copied to a device staging COO, planned in file order and trained for K steps; returns the K losses (numpy).
-        At world size 1 prefer train_steps_host (same thing behind one C-ABI call)."""
+        """One chunk of K*B explicit triples from pinned HOST tensors (see train_chunks_from_host)."""
+        return self.train_chunks_from_host([(host_row, host_col, host_a, host_b)])
+
+    def train_chunks_from_host(self, chunks):
+        """End-to-end path for any world size (data-parallel aware): every chunk is K*B explicit triples in pinned HOST
+        tensors (row, col, colA, colB); it is copied to a device staging COO, planned in file order and trained for K
+        steps.  The copy + plan of chunk c+1 run on the side stream while the steps of chunk c run (two plan buffers, two
+        staging sets).  Returns the losses of all steps (numpy; synchronises).  At world size 1 prefer train_steps_host
+        (the same pipeline behind one C-ABI call)."""
         n = self.K * self.B
-        assert host_row.numel() == n
         self._join_side()
         if getattr(self, "_stage_coo", None) is None:
             i32 = dict(dtype=torch.int32, device=self.device)
             f32 = dict(dtype=torch.float32, device=self.device)
-            self._stage_coo = (torch.empty(n, **i32), torch.empty(n, **i32), torch.empty(n, **f32), torch.empty(n, **f32))
+            self._stage_coo = [(torch.empty(n, **i32), torch.empty(n, **i32), torch.empty(n, **f32), torch.empty(n, **f32))
+                               for _ in range(2)]
             self._stage_idx = torch.arange(n, dtype=torch.int64, device=self.device)
-        for dst, src in zip(self._stage_coo, (host_row, host_col, host_a, host_b)):
-            dst.copy_(src, non_blocking=True)
-        first = self.host_step
-        which = 0
-        row, col, ca, cb = self._stage_coo
-        check(lib.glove_prepare_batches_sharded(_ptr(self.plans[which]), _ptr(self.prep_ws), self.prep_ws.numel(), _ptr(row),
-                                                _ptr(col), _ptr(ca), _ptr(cb), n, _ptr(self._stage_idx), 0, 0, first, self.K,
-                                                self.B, self.V_global, self.dp_world if self.sharded else 1, _stream()),
-              "glove_prepare_batches")
-        self._plan_counts[which] = None
-        self._plan_shards[which] = None
-        self._plan_need[which] = None
-        self.plan_first = [None, None]
-        self.plan_first[which] = first
-        self._plan_override = (which, first)
-        a = self._args[which]
-        for _ in range(self.K):
-            if self.sharded:
-                self._step_sharded()
-                continue
-            if self.dp_world > 1:
-                import torch.distributed as dist
-                gr, gc, gs = self._grad_buffers()
-                check(lib.glove_grad_step(ctypes.byref(a), _ptr(gr), _ptr(gc), _ptr(gs), _stream()), "glove_grad_step")
-                dist.all_reduce(gr); dist.all_reduce(gc); dist.all_reduce(gs)
-                check(lib.glove_apply_step(ctypes.byref(a), _ptr(gr), _ptr(gc), _ptr(gs), _stream()), "glove_apply_step")
-            else:
-                check(lib.glove_train_step(ctypes.byref(a), _stream()), "glove_train_step")
-            self.host_step += 1
+        first0 = self.host_step
+        main = torch.cuda.current_stream()
+        ready, done = [None, None], [None, None]
+        self._prep_stream.wait_stream(main)          # earlier steps may still read the plan buffers
+
+        def stage(c):
+            which = c & 1
+            with torch.cuda.stream(self._prep_stream):
+                if done[which] is not None:           # plan + staging set `which` belonged to chunk c-2
+                    self._prep_stream.wait_event(done[which])
+                for dst, src in zip(self._stage_coo[which], chunks[c]):
+                    assert src.numel() == n and not src.is_cuda
+                    dst.copy_(src, non_blocking=True)
+                row, col, ca, cb = self._stage_coo[which]
+                check(lib.glove_prepare_batches_sharded(_ptr(self.plans[which]), _ptr(self.prep_ws), self.prep_ws.numel(),
+                                                        _ptr(row), _ptr(col), _ptr(ca), _ptr(cb), n, _ptr(self._stage_idx), 0, 0,
+                                                        first0 + c * self.K, self.K, self.B, self.V_global,
+                                                        self.dp_world if self.sharded else 1,
+                                                        ctypes.c_void_p(self._prep_stream.cuda_stream)), "glove_prepare_batches")
+                ready[which] = torch.cuda.Event()
+                ready[which].record(self._prep_stream)
+
+        stage(0)
+        for c in range(len(chunks)):
+            if c + 1 < len(chunks):
+                stage(c + 1)
+            which, first = c & 1, first0 + c * self.K
+            main.wait_event(ready[which])
+            self._plan_counts[which] = self._plan_shards[which] = self._plan_need[which] = None
+            self._ev_plan[which] = None
+            self.plan_first = [None, None]
+            self.plan_first[which] = first
+            self._plan_override = (which, first)
+            a = self._args[which]
+            for _ in range(self.K):
+                if self.sharded:
+                    self._step_sharded()
+                    continue
+                if self.dp_world > 1:
+                    import torch.distributed as dist
+                    gr, gc, gs = self._grad_buffers()
+                    check(lib.glove_grad_step(ctypes.byref(a), _ptr(gr), _ptr(gc), _ptr(gs), _stream()), "glove_grad_step")
+                    dist.all_reduce(gr); dist.all_reduce(gc); dist.all_reduce(gs)
+                    check(lib.glove_apply_step(ctypes.byref(a), _ptr(gr), _ptr(gc), _ptr(gs), _stream()), "glove_apply_step")
+                else:
+                    self._before_step(which)
+                    check(lib.glove_train_step(ctypes.byref(a), _stream()), "glove_train_step")
+                    self._after_step()
+                self.host_step += 1
+            done[which] = torch.cuda.Event()
+            done[which].record(main)
         self._plan_override = None
         self.plan_first = [None, None]
-        idx = torch.arange(first, first + self.K, device=self.device) % self.loss_cap
-        return self.loss_out[idx].cpu().numpy()      # D2H of the K losses (synchronises)
+        main.wait_stream(self._prep_stream)
+        idx = torch.arange(first0, first0 + len(chunks) * self.K, device=self.device) % self.loss_cap
+        return self.loss_out[idx].cpu().numpy()      # D2H of the losses (synchronises)
 
     def batch_counts(self, step: int):
         which = self._plan_for(step)

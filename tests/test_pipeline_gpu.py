@@ -187,10 +187,19 @@ def test_train_chunk_from_host_at_any_step_alignment():
     eng.set_coo(coo["row"], coo["col"], coo["target"], coo["weight"])
     eng.set_batches(np.concatenate([pre, np.zeros((2 * K + 8, B), np.int64)]))   # resident batches differ from the host-fed ones
     got = list(eng.train(3))
+    pins = []
     for c in range(2):
         sel = host_idx[c * K:(c + 1) * K].reshape(-1)
-        pin = [torch.from_numpy(coo[k][sel].copy()).pin_memory() for k in ("row", "col", "target", "weight")]
-        got += list(eng.train_chunk_from_host(*pin))
+        pins.append(tuple(torch.from_numpy(coo[k][sel].copy()).pin_memory() for k in ("row", "col", "target", "weight")))
+    got += list(eng.train_chunks_from_host(pins))                      # both chunks in one pipelined call
     assert eng.host_step == 3 + 2 * K
     assert np.max(np.abs(np.array(got) - want) / np.abs(want)) < 1e-5
     assert np.max(np.abs(eng.get_state()["R"] - ref.R)) / np.max(np.abs(ref.R)) < 1e-5
+    # chunk by chunk gives the same bits, and the engine goes back to its resident COO afterwards
+    eng2 = GloveEngine(V, d, learning_rate=0.01, batch_size=B, plan_steps=K, max_steps=64)
+    eng2.load_state(st.R, st.C, st.rb, st.cb, st.g)
+    eng2.set_coo(coo["row"], coo["col"], coo["target"], coo["weight"])
+    eng2.set_batches(np.concatenate([pre, np.zeros((2 * K + 8, B), np.int64)]))
+    got2 = list(eng2.train(3)) + list(eng2.train_chunk_from_host(*pins[0])) + list(eng2.train_chunk_from_host(*pins[1]))
+    assert np.array_equal(np.array(got2), np.array(got)) and np.array_equal(eng2.get_state()["R"], eng.get_state()["R"])
+    assert np.all(np.isfinite(eng2.train(2)))
