@@ -336,9 +336,11 @@ class GloveEngine:
         if self.plan_first[which] != first:
             torch.cuda.current_stream().wait_stream(self._prep_stream)   # one prepare at a time (shared workspace)
             self.prepare(first, which)
+            ev = torch.cuda.Event()                                     # the catch-up stream reads the plan too
+            ev.record(torch.cuda.current_stream())
+            self._ev_plan[which] = ev
         elif self._ev_plan[which] is not None:      # built on the side stream: order the consumer after it
-            torch.cuda.current_stream().wait_event(self._ev_plan[which])
-            self._ev_plan[which] = None
+            torch.cuda.current_stream().wait_event(self._ev_plan[which])   # (kept: the catch-up stream waits on it too)
         return which
 
     def _before_step(self, which):
@@ -355,6 +357,8 @@ class GloveEngine:
         if (self.optimizer == "Adam" and self.adam_mode == "replay" and 0 < k_next < self.K and s + 1 < self.max_steps
                 and s >= 1):
             self._side.wait_event(self._ev_step_done[(s - 1) & 1])
+            if self._ev_plan[which] is not None:                        # ... and not before its plan is complete
+                self._side.wait_event(self._ev_plan[which])
             check(lib.glove_catchup_step(ctypes.byref(self._args[which]), s + 1, ctypes.c_void_p(self._side.cuda_stream)),
                   "glove_catchup_step")
             ev = torch.cuda.Event()
@@ -643,7 +647,7 @@ class GloveEngine:
             which, first = c & 1, first0 + c * self.K
             main.wait_event(ready[which])
             self._plan_counts[which] = self._plan_shards[which] = self._plan_need[which] = None
-            self._ev_plan[which] = None
+            self._ev_plan[which] = ready[which]
             self.plan_first = [None, None]
             self.plan_first[which] = first
             self._plan_override = (which, first)
