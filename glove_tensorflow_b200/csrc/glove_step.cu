@@ -63,7 +63,6 @@ struct StepWs {
     size_t bytes;
 };
 static inline int64_t snapshot_rows(int32_t B) { return (int64_t)B + B / 4 + 64; }  // room for padded shard blocks
-static inline int64_t max_items_per_batch(int32_t B) { return (int64_t)B + B / kItemMax + 2; }
 static inline int64_t max_parts_per_batch(int32_t B) { return 2 * (int64_t)B / kItemMax + 2; }
 static StepWs step_ws_view(void *base, int32_t B, int32_t d) {
     StepWs w;
