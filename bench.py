@@ -216,7 +216,9 @@ def main():
         ups, dt, cores = cpu_reference(V, d, B_local, steps, warm)
         line = {"metric": "co-occurrence updates/sec", "value": ups, "unit": "updates/s", "n_gpus": 0, "steps": steps,
                 "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference", "config": config,
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+                "config": dict(config, global_batch=B_local, adam_mode="keras-dense (what replay reproduces)",
+                               parallelism="cpu-%d-threads" % cores, state="cold (the dense update costs the same at any step)"),
                 "cpu_baseline": {"value": ups, "unit": "updates/s", "cores": cores, "kind": "port",
                                  "sample": "%d TRAIN steps of B=%d (requested %d), C port of the oracle, OpenMP, "
                                            "legacy-Keras dense Adam; restatement of the reference path, not TensorFlow"
@@ -379,6 +381,16 @@ def main():
                          % (csteps, B_local, dt)}
 
     n_prep = (args.steps + K - 1) // K
+    # own kernels per timed step: stage + update (N=1; the finish is fused into the update), or stage + exchange kernels +
+    # update + finish on row-sharded tables; + the two Adam catch-up kernels in replay mode.  Plan construction: ~20 own
+    # kernels per plan of K steps (CUB sorts / scans inside it not counted).
+    if N == 1:
+        per_step_launches = 2
+    elif args.dp_mode == "sharded":
+        per_step_launches = 3 + {"peer": 1, "peer-direct": 0, "alltoall": 2, "allgather": 0}[args.shard_exchange]
+    else:
+        per_step_launches = 4
+    per_step_launches += 2 if args.adam_mode == "replay" else 0
     line = {"metric": "co-occurrence updates/sec", "value": value, "unit": "updates/s", "n_gpus": N,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -387,7 +399,7 @@ def main():
                            l2_flush="inputs larger than L2 (tables+slots %.1f GB, COO %.1f GB)"
                                     % (2 * V * eng.P * eng.S * 4 / 1e9, nnz * 16 / 1e9),
                            state="cold" if args.cold_state else "steady-state emulation at step %d" % T0),
-            "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * (2 + (2 if args.adam_mode == "replay" else 0)) + n_prep * 20,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * per_step_launches + n_prep * 20,
             "roofline": roofline, "cpu_baseline": cpu, "final_loss": float(losses[-1])}
     print(json.dumps(line))
     if world > 1:
