@@ -2,7 +2,10 @@
 vocabulary rows, context 5 = 85 M pairs) beside the CPU restatement of the reference's pandas algorithm on a bounded
 sample.
 
-    python tools/bench_cooc.py [--tokens 17005207] [--vocab 10001] > gpurun_out/cooc.json
+    python tests/bench_cooc.py [--tokens 17005207] [--vocab 10001] > gpurun_out/cooc.json
+
+Lives under tests/ (not collected by pytest) because it times the oracle as the CPU baseline, and only tests/, smoke() and
+bench.py's cpu_baseline leg may touch oracle/.
 """
 import argparse
 import json
