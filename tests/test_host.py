@@ -152,3 +152,27 @@ def test_dp_partition_rule():
     assert np.array_equal(np.concatenate(parts), idx)
     with pytest.raises(ValueError):
         parallel.dp_shard(idx, 0, 5)
+
+
+def test_decimal_to_float32_round_trips_shortest_representations():
+    """Every finite float32 printed in its shortest round-trip form (and in scientific form with 9 significant digits) must
+    parse back to the same bits: subnormals, powers of two, the largest finite value, both signs."""
+    import ctypes
+    from glove_tensorflow_b200._lib import lib
+    rng = np.random.default_rng(5)
+    bits = np.concatenate([rng.integers(0, 0x7f800000, 60000, dtype=np.uint32),               # all exponents, incl. subnormal
+                           rng.integers(0, 0x00800000, 5000, dtype=np.uint32),                 # subnormals
+                           np.arange(1, 255, dtype=np.uint32) << 23,                           # powers of two
+                           np.array([1, 2, 0x007fffff, 0x00800000, 0x7f7fffff, 0x3f800000, 0x3f7fffff], np.uint32)])
+    vals = bits.view(np.float32)
+    out = ctypes.c_float()
+    for i, v in enumerate(vals):
+        forms = [np.format_float_positional(v, unique=True, trim="-") if 1e-5 < v < 1e9 else np.format_float_scientific(v, unique=True),
+                 "%.8e" % float(v)]
+        if i % 2:
+            forms = ["-" + f for f in forms]
+        for f in forms:
+            s = f.encode()
+            assert lib.glove_parse_float32(s, len(s), ctypes.byref(out)) == 0, f
+            want = (-v if i % 2 else v)
+            assert np.float32(out.value).view(np.uint32) == np.float32(want).view(np.uint32), (f, out.value, want)
