@@ -1,20 +1,25 @@
-// TRAIN step: model_fn(mode=TRAIN) of the reference [ref src/models/estimator.py:13-56] as three sm_100a kernels.
+// TRAIN step: model_fn(mode=TRAIN) of the reference [ref src/models/estimator.py:13-56] as two sm_100a launches.
 //
-//   stage_kernel   one warp per distinct row / col id of the batch: (replay missed idle Adam steps,) publish the
-//                  pre-step row into a compact L2-resident snapshot snap[side][slot][S].  A snapshot row is
+//   stage_kernel   one thread per float4 of every distinct row / col id of the batch: (replay missed idle Adam steps,)
+//                  publish the pre-step row into a compact snapshot snap[side][slot][S].  A snapshot row is
 //                  [x_0..x_{d-1} | bias at column d+side | 1.0 at column d+1-side | 0..], so that
 //                  dot(snap_row[i], snap_col[j]) over all S columns = sum_k R_ik C_jk + rb_i + cb_j with no masking,
 //                  and sum_b e_b * snap_opposite lands the bias gradient sum_b e_b in the own bias column for free.
+//                  stage_kernel<true> + commit_ls_kernel are the same replay run AHEAD of time on a side stream for the
+//                  rows of the next batch that the step in flight cannot touch (glove_catchup_step).
 //   update_kernel  one warp per work item (<= kItemMax triples of one id, both sides in one launch): gather the
 //                  opposite rows from the snapshot with 128-bit loads (software-pipelined one triple ahead),
 //                  warp-shuffle dot product, residual, loss, gradient accumulation in registers, and -- when the item
 //                  is the whole segment -- the fused sparse optimizer update written in place to the packed table.
 //                  All forward reads come from the snapshot, so the row side and the col side never race
-//                  (SURVEY §7 hard part 2) and both sides run in one launch.
-//   fix_kernel     segments longer than kItemMax: partial sums are combined in a fixed order (one CTA per segment) and
-//                  updated; every CTA pre-reduces a slice of the per-item loss terms, and the last CTA to finish sums
-//                  those in CTA order, updates the scalar global bias, publishes the loss and increments the device
-//                  step counter.
+//                  (SURVEY §7 hard part 2) and both sides run in one launch.  Segments longer than kItemMax are split
+//                  into pieces whose partial sums are combined in a fixed order inside the same launch (two-level tree,
+//                  the last warp to finish a chunk / a segment does the adding); the last CTA to finish (ticket) sums
+//                  the per-warp loss terms in warp order, updates the scalar global bias, publishes the loss and
+//                  increments the device step counter.
+//
+// Row-sharded tables split the step into glove_shard_stage / (pack, unpack | pull) / update / finish entry points around
+// the exchange of snapshot rows; replicated data parallelism into glove_grad_step / glove_apply_step (apply_kernel).
 //
 // Everything is deterministic: no floating-point atomics, fixed summation order given (B, kItemMax, grid size).
 #include <stdlib.h>
