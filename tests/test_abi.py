@@ -86,3 +86,18 @@ def test_product_never_imports_the_oracle():
                 src = open(os.path.join(dirpath, f), encoding="utf8").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
                 assert "libglove_oracle" not in src, f
+
+
+def test_csv_schema_layout_matches_the_c_header():
+    from glove_tensorflow_b200 import _lib
+    prog = ('#include <stdio.h>\n#include <stddef.h>\n#include "glove_b200.h"\nint main(){printf("%zu %zu %zu %zu %d %d %d", '
+            'sizeof(glove_csv_schema), offsetof(glove_csv_schema, n_cols), offsetof(glove_csv_schema, column), '
+            'offsetof(glove_csv_schema, kind), GLOVE_CSV_TOKEN, GLOVE_CSV_INT, GLOVE_CSV_FLOAT);return 0;}')
+    with tempfile.TemporaryDirectory() as td:
+        c = os.path.join(td, "t.c")
+        open(c, "w").write(prog)
+        subprocess.check_call(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), c, "-o", os.path.join(td, "t")])
+        out = [int(x) for x in subprocess.check_output([os.path.join(td, "t")]).decode().split()]
+    S = _lib.CsvSchema
+    assert out[:4] == [ctypes.sizeof(S), S.n_cols.offset, S.column.offset, S.kind.offset]
+    assert out[4:] == [_lib.CSV_TOKEN, _lib.CSV_INT, _lib.CSV_FLOAT]
