@@ -243,7 +243,7 @@ def main():
     B = B_local * N                                            # global batch (weak scaling)
     K = args.plan_steps
     steps = (args.steps + K - 1) // K * K if not args.no_e2e else args.steps
-    total_steps = args.warmup + args.steps + 3 * K + 64
+    total_steps = args.warmup + args.steps + 3 * K + 64 + 2 * 8 * K      # + warm and timed e2e calls of up to 8 chunks
     eng = GloveEngine(V, d, optimizer="Adam", learning_rate=0.001, l2_reg=0.01, reg_scale=2.0, head="glove",
                       adam_mode=args.adam_mode, batch_size=B, plan_steps=K, max_steps=T0 + 2 * total_steps + steps,
                       device=dev, dp_rank=rank, dp_world=N, dp_mode=args.dp_mode)
