@@ -211,10 +211,12 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
+        if world > 1 and os.environ.get("OMP_NUM_THREADS") == "1":
+            os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)   # torchrun pins 1 thread per rank; rank 0 runs alone here
         steps = max(1, min(args.steps, 96 if V >= 100_000 else 1024))   # bounded sample (about 10 s) of the same shape
         warm = 1 if args.warmup else 0
         ups, dt, cores = cpu_reference(V, d, B_local, steps, warm)
-        line = {"metric": "co-occurrence updates/sec", "value": ups, "unit": "updates/s", "n_gpus": 0, "steps": steps,
+        line = {"metric": "co-occurrence updates/sec", "value": ups, "unit": "updates/s", "n_gpus": args.gpus, "steps": steps,
                 "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
                 "config": dict(config, global_batch=B_local, adam_mode="keras-dense (what replay reproduces)",
