@@ -2,7 +2,9 @@
 co-occurrence kernels (glove_tensorflow_b200/csrc/glove_cooc.cu).  Nothing in the product path may import this file.
 
 PINNED: tests/test_oracle.py checks this restatement against tests/golden/text8_small, which is the output of the
-reference's own preprocessor (src/data/text8.py imported unmodified, tests/golden/make_golden.py).
+reference's own preprocessor (src/data/text8.py imported unmodified, tests/golden/make_golden.py), and
+tests/golden/pin_cooc_oracle.py ran it against the reference itself on random corpora (30 vocabularies with count ties, 6
+interaction tables with context sizes 1..6: ids, counts and every float64 column equal, max error 0.0).
 
 Follows create_interaction_dataframe [ref src/data/text8.py:84-126] and create_glove_dataframe / glove_weight
 [ref src/data/text8.py:129-139], with the position cross-join replaced by shifted slices of the id array (the same pairs
@@ -40,3 +42,18 @@ def interaction_table(ids, vocab_count, context_size=5, count_minimum=10):
     sym["glove_weight"] = np.clip(np.power(sym["count"] / 100, 0.75), 0, 1)             # [ref :130, :137-139]
     sym["glove_value"] = np.log(sym["value"])                                           # [ref :131]
     return sym.sort_values(["row_token_id", "col_token_id"]).reset_index(drop=True)
+
+
+def vocabulary_frame(tokens, vocab_size, coverage):
+    """create_vocabulary restated [ref src/data/text8.py:61-81]: Counter, coverage cut-off on the count-sorted cumulative
+    share, most_common(vocab_size) filtered by the cut-off, '<UNK>' with the remaining mass, ordered by count."""
+    from collections import Counter
+    freq = Counter(tokens)
+    counts = np.sort(list(freq.values()))[::-1]
+    total = np.sum(counts)
+    cutoff = counts[np.searchsorted(np.cumsum(counts) / total, coverage)]
+    vocab = [t for t, n in freq.most_common(vocab_size) if n >= cutoff]
+    vc = [freq[t] for t in vocab]
+    df = pd.DataFrame({"token": ["<UNK>"] + vocab, "count": [total - np.sum(vc)] + vc})
+    df["proportion"] = df["count"] / total
+    return df.sort_values("count", ascending=False).reset_index(drop=True)

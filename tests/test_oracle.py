@@ -251,3 +251,20 @@ def test_host_vocabulary_matches_the_reference_preprocessor_output():
     np.testing.assert_allclose(got["proportion"], ref["proportion"], rtol=1e-15)
     ids = text8.token_ids(tokens, got["token"].to_numpy())
     assert ids.dtype == np.int32 and ids.max() == len(got) - 1 and np.bincount(ids)[0] > got["count"][0]   # unknown -> row 0
+
+
+def test_host_vocabulary_tie_order_matches_the_oracle_restatement():
+    """Count ties are where a vocabulary can silently diverge (most_common order, then pandas' sort): random corpora with
+    many ties, the product's host function against the oracle's restatement of the reference's lines (which
+    tests/golden/pin_cooc_oracle.py pins on the reference itself)."""
+    from glove_tensorflow_b200 import text8
+    from oracle import cooc_oracle
+    rng = np.random.default_rng(3)
+    for _ in range(25):
+        types, n = int(rng.integers(5, 300)), int(rng.integers(50, 8000))
+        p = 1.0 / np.arange(1, types + 1) ** rng.uniform(0.3, 1.5)
+        toks = ["t%d" % i for i in rng.choice(types, size=n, p=p / p.sum())]
+        vs, cov = int(rng.integers(1, types + 5)), float(rng.uniform(0.3, 0.999))
+        a, b = cooc_oracle.vocabulary_frame(toks, vs, cov), text8.create_vocabulary(toks, vs, cov)
+        assert list(a["token"]) == list(b["token"]) and list(a["count"]) == list(b["count"])
+        np.testing.assert_allclose(a["proportion"], b["proportion"], rtol=1e-15)
