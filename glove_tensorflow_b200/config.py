@@ -22,6 +22,13 @@ def read_config(ini_file="app.ini", environment=None):
 CONFIG = read_config()
 
 JOB_DIR = CONFIG["JOB_DIR"]
+
+# preprocess (ref src/config.py:28-33: no cap on the vocabulary size by default, only the coverage cut-off)
+TEXT8_URL = CONFIG.get("TEXT8_URL", fallback="http://mattmahoney.net/dc/text8.zip")
+DATA_DIR = CONFIG.get("DATA_DIR", fallback="data")
+VOCAB_SIZE = None
+COVERAGE = CONFIG.getfloat("COVERAGE", fallback=0.9)
+CONTEXT_SIZE = CONFIG.getint("CONTEXT_SIZE", fallback=5)
 TRAIN_CSV = CONFIG["TRAIN_CSV"]
 VOCAB_TXT = CONFIG["VOCAB_TXT"]
 EMBEDDINGS_JSON = CONFIG["EMBEDDINGS_JSON"]
@@ -32,6 +39,8 @@ TARGET_NAME = CONFIG["TARGET_NAME"]
 WEIGHT_NAME = CONFIG["WEIGHT_NAME"]
 POS_NAME = CONFIG["POS_NAME"]
 NEG_NAME = CONFIG["NEG_NAME"]
+STRING_IDX = CONFIG.getint("STRING_IDX", fallback=None)   # absent from app.ini in the reference too (src/config.py:42-43)
+NAME_IDX = CONFIG.getint("NAME_IDX", fallback=None)
 
 EMBEDDING_SIZE = CONFIG.getint("EMBEDDING_SIZE")
 L2_REG = CONFIG.getfloat("L2_REG")

@@ -17,8 +17,7 @@ import numpy as np
 
 logger = logging.getLogger(__name__)
 
-TEXT8_URL = "http://mattmahoney.net/dc/text8.zip"      # ref src/config.py
-DATA_DIR, VOCAB_SIZE, COVERAGE, CONTEXT_SIZE = "data", 10000, 0.9, 5
+from .config import CONTEXT_SIZE, COVERAGE, DATA_DIR, TEXT8_URL, VOCAB_SIZE   # ref src/data/text8.py:12 (VOCAB_SIZE = None)
 
 
 def download_data(url=TEXT8_URL, dest_dir=DATA_DIR):
@@ -234,7 +233,7 @@ def process_data(text8, vocab_size=VOCAB_SIZE, coverage=COVERAGE, context_size=C
     tokens, (host: pick the vocabulary among them), map tokens to ids, count pairs, write the columns."""
     corpus = DeviceCorpus(text8, device)
     tokens, counts = corpus.distinct()
-    df_vocab = _frame_from_counts(tokens, counts, int(vocab_size), coverage)
+    df_vocab = _frame_from_counts(tokens, counts, None if vocab_size is None else int(vocab_size), coverage)
     logger.info("vocab created, size: %s.", df_vocab.shape[0])
     vocab_tokens = df_vocab["token"].to_numpy()
     table = cooccurrence_table(corpus.ids(vocab_tokens), df_vocab["count"].to_numpy(), context_size, 10, device)

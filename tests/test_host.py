@@ -176,3 +176,15 @@ def test_decimal_to_float32_round_trips_shortest_representations():
             assert lib.glove_parse_float32(s, len(s), ctypes.byref(out)) == 0, f
             want = (-v if i % 2 else v)
             assert np.float32(out.value).view(np.uint32) == np.float32(want).view(np.uint32), (f, out.value, want)
+
+
+def test_preprocess_defaults_are_the_references():
+    """ref src/config.py:28-33 + configs/app.ini:25-28 (compared once against the imported reference module: all 27
+    upper-case constants of src.config equal ours).  Note VOCAB_SIZE = None: by default only the coverage cut-off limits
+    the vocabulary."""
+    from glove_tensorflow_b200 import config, text8
+    assert config.VOCAB_SIZE is None and config.COVERAGE == 0.9 and config.CONTEXT_SIZE == 5 and config.DATA_DIR == "data"
+    assert config.TEXT8_URL == "http://mattmahoney.net/dc/text8.zip" and config.STRING_IDX is None and config.NAME_IDX is None
+    assert text8.VOCAB_SIZE is None and text8.CONTEXT_SIZE == 5
+    v = text8.create_vocabulary(["a", "b", "a", "c", "b", "a", "d"], None, 0.9)     # no cap: every token above the cut-off
+    assert list(v["token"]) == ["a", "b", "c", "d", "<UNK>"] and list(v["count"]) == [3, 2, 1, 1, 0]
