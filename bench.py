@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """bench.py -- co-occurrence updates/sec of the GloVe TRAIN step on B200 (metric of BASELINE.json).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload wiki6b|text8|cc] [--adam-mode replay|lazy|dense]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload wiki6b|text8|cc|topk]
+                    [--adam-mode replay|replay_exact|lazy|dense]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
     python bench.py --impl reference ...        # the reference path's CPU restatement on the box's host cores
 
@@ -9,7 +10,8 @@ A "step" is one full TRAIN step (gather + loss + gradient + optimizer) over one 
 co-occurrence triples.  Default workload = BASELINE.json configs[2] ("wiki6b": Zipf co-occurrence, V=400k, d=300,
 Adam, B=65,536 per GPU, data-parallel at 1/2/4/8 GPUs) -- the configuration the metric's "at 1/2/4/8 B200" is quoted
 on; it fits one GPU.  ``--workload text8`` is configs[1] (V=10,001, d=64, B=65,536), ``cc`` is configs[3]'s table
-shape (V=2.2M) on replicated tables.
+shape (V=2.2M; row-sharded tables at N>1); ``topk`` is configs[4] alone (cosine top-k over a 2.2M x 300 table, k=10,
+65,536 queries per call, tensor-core roofline) -- the default run also appends it as the ``topk`` record at N=1.
 
 One JSON line is printed by rank 0 (see DESIGN.md "Measurement" for every key).
 """
@@ -33,7 +35,8 @@ WORKLOADS = {
     "cc": (2_200_000, 300, 65_536, 1 << 28),
 }
 ADAM_K = 6  # read + write of (x, m, v)
-T0 = 2048   # global_step the steady-state emulation resumes at
+T0 = 2048   # TRAIN steps run from the cold start before the timed region (or the step the emulated state resumes at)
+TOPK = (2_200_000, 300, 65_536, 10)   # BASELINE configs[4]: V, d, queries per call, k
 
 
 def algorithmic_bytes(B, U_r, U_c, d, k_opt=ADAM_K):
@@ -141,10 +144,14 @@ class ClockSampler(threading.Thread):
         for line in self.proc.stdout:
             self.rows.append((time.time(), [x.strip() for x in line.strip().split(",")]))
 
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            self.proc = None
+
     def summary(self, t_start, t_end):
         if self.proc is not None:
             time.sleep(0.15)
-            self.proc.terminate()
         rows = [(t, r) for t, r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
         if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
@@ -177,20 +184,121 @@ def cpu_reference(V, d, B, steps, warmup, seed=0):
     return steps * B / dt, dt, c_oracle.num_threads()
 
 
+def load_traffic(key):
+    """(bytes per step, source) from profiles/step_traffic.json: {key: {"dram_bytes": n, "source": "profiles/..."}}."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "step_traffic.json")))[key]
+        return float(t["dram_bytes"]), t.get("source")
+    except Exception:
+        return None, None
+
+
+def topk_record(dev, sampler, full_line=False, n_gpus=1, steps=5, warmup=3):
+    """BASELINE configs[4]: cosine top-k of Q = 65,536 query rows over a 2.2M x 300 table, k = 10 (tcgen05 candidate pass +
+    exact fp32 re-score), per GPU (N > 1: replicas, queries sharded -- every rank runs the same call).  Algorithmic flops
+    = 2*Q*V*d (padding d to 320 is overhead, not credit).  `value` is device-timed (CUDA events around the whole topk
+    call incl. normalised-query gather, candidate pass, re-score, guarantee check; query ids resident); `e2e` is the wall
+    time of GloveEngine.topk from HOST query ids to HOST results."""
+    import torch
+    from glove_tensorflow_b200.engine import GloveEngine
+    V, d, Q, k = TOPK
+    iters = max(1, min(steps, 10))
+    eng = GloveEngine(V, d, optimizer="SGD", batch_size=64, plan_steps=1, max_steps=4, device=dev)
+    eng.init_uniform(0)
+    q = torch.randint(0, V, (Q,), generator=torch.Generator().manual_seed(1)).numpy().astype(np.int32)
+    for _ in range(max(1, min(warmup, 3))):
+        eng.topk(q, k)                                                  # warm-up (normalises the table once)
+    torch.cuda.synchronize()
+    t_start = time.time()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    qd = torch.from_numpy(q).to(dev)
+    inv, nb = eng._normalised_table()
+    ev[0].record()
+    for _ in range(iters):
+        eng._topk_call(inv, nb, eng.row_table, eng.P, nb, qd, Q, k, False)
+    ev[1].record()
+    torch.cuda.synchronize()
+    ms = ev[0].elapsed_time(ev[1]) / iters
+    fallbacks = eng.last_topk_fallbacks
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        eng.topk(q, k)
+    wall = (time.perf_counter() - t0) / iters
+    t_end = time.time()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("bf16_tflops", 1590.0))
+    flop = 2.0 * Q * V * d
+    tf = flop / (ms * 1e-3) / 1e12
+    rec = {"metric": "cosine top-k algorithmic TFLOP/s (2*Q*V*d)", "value": tf * n_gpus, "unit": "TFLOP/s", "ms_per_call": ms,
+           "queries_per_s": Q / (ms * 1e-3) * n_gpus, "fallbacks": fallbacks,
+           "config": {"workload": "topk: cosine top-k, V=%d, d=%d, k=%d, Q=%d queries per call per GPU, table U(-0.05,0.05)"
+                                  % (V, d, k, Q), "l2_flush": "bf16 table 1.4 GB + fp32 table 2.7 GB, larger than L2"},
+           "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
+                        "traffic": None, "peak_source": "measured bf16 burst (MEASURED_PEAKS.json)" if peaks else "fallback 1590",
+                        "kernel": "topk_tc_kernel (tcgen05 candidate pass) + exact fp32 re-score; flops are algorithmic"},
+           "e2e": {"value": flop / wall / 1e12 * n_gpus, "unit": "TFLOP/s", "h2d_bytes_per_step": 4 * Q, "d2h_bytes_per_step": 8 * Q * k,
+                   "path": "GloveEngine.topk: host query ids -> device -> candidates -> re-score -> host (sim, idx)"},
+           "clocks": sampler.summary(t_start, t_end) if sampler is not None else None}
+    if full_line:
+        rec.update({"n_gpus": n_gpus, "steps": iters, "warmup": max(1, min(warmup, 3)), "ms_per_step": ms, "higher_is_better": True,
+                    "scaling": "weak", "vs_baseline": None, "dtype": "bf16 candidates, f32 re-score", "data": "synthetic",
+                    "gpu_launches": iters * 6, "cpu_baseline": None})
+    del eng
+    torch.cuda.empty_cache()
+    return rec
+
+
+def topk_reference_line(args):
+    """--impl reference --workload topk: the reference's own PREDICT arithmetic (l2-normalise the whole table, matmul,
+    top_k; src/models/utils.py:12-19, model_utils.py:97-99) restated in NumPy fp32 on the host cores, on a bounded sample
+    of the queries of the same table shape."""
+    from oracle import glove_oracle as o
+    V, d, Q, k = TOPK
+    rng = np.random.default_rng(0)
+    T = rng.uniform(-0.05, 0.05, (V, d)).astype(np.float32)
+    nq = 64
+    q = rng.integers(0, V, nq)
+    o.cosine_topk(T[:1000], q[:4] % 1000, k)
+    t0 = time.perf_counter()
+    o.cosine_topk(T, q, k)
+    dt = time.perf_counter() - t0
+    tf = 2.0 * nq * V * d / dt / 1e12
+    cores = os.cpu_count() or 1
+    return {"metric": "cosine top-k algorithmic TFLOP/s (2*Q*V*d)", "value": tf, "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": 1,
+            "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": "topk: cosine top-k, V=%d, d=%d, k=%d, Q=%d queries per call per GPU, table U(-0.05,0.05)"
+                                   % (V, d, k, Q), "l2_flush": "bf16 table 1.4 GB + fp32 table 2.7 GB, larger than L2"},
+            "cpu_baseline": {"value": tf, "unit": "TFLOP/s", "cores": cores, "kind": "port",
+                             "sample": "%d queries (of %d) against the full table, NumPy fp32 restatement of cosine_similarity + "
+                                       "top_k incl. the per-call normalisation of the table, BLAS threads" % (nq, Q)},
+            "e2e": {"value": tf, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="wiki6b", choices=sorted(WORKLOADS))
-    ap.add_argument("--adam-mode", default="replay", choices=["replay", "lazy", "dense"])
+    ap.add_argument("--workload", default="wiki6b", choices=sorted(WORKLOADS) + ["topk"])
+    ap.add_argument("--adam-mode", default="replay", choices=["replay", "replay_exact", "lazy", "dense"],
+                    help="replay = closed-form replay of idle Adam steps (default; reference semantics), replay_exact = "
+                         "step-by-step replay with the dense sweep's fp32 operations, dense = replay_exact + flush after "
+                         "every step, lazy = LazyAdam (not the reference's arithmetic)")
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: workload's)")
     ap.add_argument("--nnz", type=int, default=None)
     ap.add_argument("--plan-steps", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--cold-state", action="store_true", help="start from step 0 with empty Adam state")
+    ap.add_argument("--cold-state", action="store_true", help="time from step 0 with empty Adam state")
+    ap.add_argument("--emulate-state", action="store_true",
+                    help="instead of really training %d steps first, start from a synthetic steady state (round-1 method)" % T0)
+    ap.add_argument("--no-topk", action="store_true", help="skip the cfg5 top-k record of the default N=1 run")
     ap.add_argument("--shard-exchange", default="peer", choices=["alltoall", "allgather", "peer", "peer-direct"],
                     help="N>1, row-sharded tables: how the snapshot rows reach the shards that need them (peer = one pull "
                          "kernel over NVLink peer memory; falls back to alltoall when symmetric memory is unavailable)")
@@ -198,14 +306,27 @@ def main():
                     help="N>1: row-sharded tables (owner-computes) or replicated tables with gradient all-reduce")
     args = ap.parse_args()
 
-    V, d, B_local, nnz = WORKLOADS[args.workload]
+    V, d, B_local, nnz = WORKLOADS["wiki6b" if args.workload == "topk" else args.workload]
     B_local = args.batch or B_local
     nnz = args.nnz or nnz
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    config = {"workload": "%s: synthetic Zipf(s=1) co-occurrence, V=%d, d=%d, Adam lr 1e-3, l2 0.01, B=%d per GPU"
-                          % (args.workload, V, d, B_local), "nnz": nnz, "batch_per_gpu": B_local}
+    N = max(world, 1)
+    B = B_local * N                                            # global batch (weak scaling)
+    S_pad = (d + 2 + 7) // 8 * 8
+
+    def make_config():
+        """The workload description BOTH arms print (every value is derivable without a GPU)."""
+        return {"workload": "%s: synthetic Zipf(s=1) co-occurrence, V=%d, d=%d, Adam lr 1e-3, l2 0.01, B=%d per GPU"
+                            % (args.workload, V, d, B_local), "nnz": nnz, "batch_per_gpu": B_local, "global_batch": B,
+                "adam_mode": args.adam_mode,
+                "parallelism": ("dp%d" % N) if N == 1 else ("dp%d-%s-tables%s" % (
+                    N, args.dp_mode, "-" + args.shard_exchange if args.dp_mode == "sharded" else "")),
+                "l2_flush": "inputs larger than L2 (tables+slots %.1f GB, COO %.1f GB)"
+                            % (2 * V * 3 * S_pad * 4 / 1e9, nnz * 16 / 1e9),
+                "state": ("cold" if args.cold_state else "steady-state emulation at step %d" % T0 if args.emulate_state
+                          else "trained %d steps from a cold start before the timed region" % T0)}
 
     # ---- reference arm: CPU restatement of the reference TRAIN step on host cores -------------------------------
     if args.impl == "reference":
@@ -213,18 +334,22 @@ def main():
             return
         if world > 1 and os.environ.get("OMP_NUM_THREADS") == "1":
             os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)   # torchrun pins 1 thread per rank; rank 0 runs alone here
-        steps = max(1, min(args.steps, 96 if V >= 100_000 else 1024))   # bounded sample (about 10 s) of the same shape
-        warm = 1 if args.warmup else 0
-        ups, dt, cores = cpu_reference(V, d, B_local, steps, warm)
+        if args.workload == "topk":
+            print(json.dumps(topk_reference_line(args)))
+            return
+        steps = max(1, min(args.steps, 96 if V >= 100_000 else 1024))   # bounded sample of the same shape
+        warm = min(max(args.warmup, 3), 32)
+        ups, dt, cores = cpu_reference(V, d, B, steps, warm)
         line = {"metric": "co-occurrence updates/sec", "value": ups, "unit": "updates/s", "n_gpus": args.gpus, "steps": steps,
                 "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-                "config": dict(config, global_batch=B_local, adam_mode="keras-dense (what replay reproduces)",
-                               parallelism="cpu-%d-threads" % cores, state="cold (the dense update costs the same at any step)"),
+                "config": make_config(),
                 "cpu_baseline": {"value": ups, "unit": "updates/s", "cores": cores, "kind": "port",
-                                 "sample": "%d TRAIN steps of B=%d (requested %d), C port of the oracle, OpenMP, "
-                                           "legacy-Keras dense Adam; restatement of the reference path, not TensorFlow"
-                                           % (steps, B_local, args.steps)},
+                                 "sample": "%d TRAIN steps of B=%d (requested %d) after %d warm-up steps, C port of the oracle, "
+                                           "OpenMP on %d threads, legacy-Keras dense Adam (what adam_mode=replay reproduces; "
+                                           "the dense sweep costs the same at any step, so the state is cold); "
+                                           "restatement of the reference path, not TensorFlow"
+                                           % (steps, B, args.steps, warm, cores)},
                 "e2e": {"value": ups, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -241,13 +366,19 @@ def main():
         sampler.start()
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    N = max(world, 1)
-    B = B_local * N                                            # global batch (weak scaling)
+    if args.workload == "topk":
+        line = topk_record(dev, sampler if rank == 0 else None, full_line=True, n_gpus=N, steps=args.steps, warmup=args.warmup)
+        if rank == 0:
+            sampler.stop()
+            print(json.dumps(line))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     K = args.plan_steps
     steps = (args.steps + K - 1) // K * K if not args.no_e2e else args.steps
     total_steps = args.warmup + args.steps + 3 * K + 64 + 2 * 8 * K      # + warm and timed e2e calls of up to 8 chunks
     eng = GloveEngine(V, d, optimizer="Adam", learning_rate=0.001, l2_reg=0.01, reg_scale=2.0, head="glove",
-                      adam_mode=args.adam_mode, batch_size=B, plan_steps=K, max_steps=T0 + 2 * total_steps + steps,
+                      adam_mode=args.adam_mode, batch_size=B, plan_steps=K, max_steps=2 * T0 + 2 * total_steps + steps,
                       device=dev, dp_rank=rank, dp_world=N, dp_mode=args.dp_mode)
     eng.shard_exchange = args.shard_exchange
     if args.shard_exchange.startswith("peer") and world > 1 and args.dp_mode == "sharded":
@@ -261,8 +392,13 @@ def main():
     eng.init_uniform(seed=1)                                   # same seed on every rank: replicas start identical
     row, col, tgt, wgt = gen_coo_device(V, nnz, 1234, dev)     # replicated COO (weak scaling: B grows with N)
     eng.set_coo(row, col, tgt, wgt, shuffle_key=0xC0FFEE)
-    if not args.cold_state:
+    if args.emulate_state and not args.cold_state:
         steady_state(eng, V, B, seed=99)
+    elif not args.cold_state:
+        # REAL state: T0 TRAIN steps from the cold start (every row the timed region touches then carries the last_step,
+        # m, v a long run gives it; the idle gaps the stage has to replay are the workload's own)
+        for _ in range(T0):
+            eng.step()
     torch.cuda.synchronize()
 
     # ---- warm-up ---------------------------------------------------------------------------------------------------
@@ -295,6 +431,7 @@ def main():
     losses = eng.loss_out[(torch.arange(first_timed, eng.host_step, device=dev) % eng.loss_cap)].cpu().numpy()
     assert np.all(np.isfinite(losses)), "non-finite loss in the timed region"
     value = B * args.steps / (ms * 1e-3)
+    final_loss = losses[-1]
 
     # ---- roofline: per-kernel durations (CUDA events on the launching stream) + algorithmic bytes -------------------
     U = np.array([eng.batch_counts(s)[:2] for s in range(first_timed, first_timed + min(args.steps, 32))], np.float64)
@@ -312,15 +449,20 @@ def main():
         peak = float(peaks.get("hbm_gbs", 6650.0))
         step_ms = ms / args.steps
         achieved = bytes_alg / (step_ms * 1e-3) / 1e9
-        # ncu --set full (profiles/r01_step_kernels_ncu_full.txt): dram read+write per launch of stage_kernel<false> (91 MB) +
-        # update_kernel (355 MB), cold caches, default workload only
-        traffic = 446e6 if (args.workload == "wiki6b" and B_local == 65_536) else None
+        # dram__bytes_read.sum + dram__bytes_write.sum of the step's kernels, per launch, parsed at run time from the committed
+        # ncu export of this workload (profiles/step_traffic.json, written by tools/ncu_summary.py); null when absent
+        traffic, traffic_src = load_traffic("%s/%s/B%d" % (args.workload, args.adam_mode, B_local))
+        upd_alg = bytes_alg - (U_r + U_c) * (4 * d + 4)        # everything but the first read of x (done by the stage)
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6650",
-                    "kernel": "whole step = stage_kernel + update_kernel (algorithmic bytes are per step)",
+                    "traffic": traffic, "traffic_source": traffic_src,
+                    "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6650",
+                    "kernel": "whole step = stage kernel + update_kernel (algorithmic bytes are per step)",
                     "algorithmic_bytes_per_step": bytes_alg, "U_row": U_r, "U_col": U_c,
                     "rho": (U_r + U_c) / (2.0 * B), "frac_of_nominal_8000": achieved / 8000.0,
                     "kernels_ms": kernels_ms,
+                    "update_kernel": {"algorithmic_bytes": upd_alg, "ms": kernels_ms["update"],
+                                      "achieved": upd_alg / (kernels_ms["update"] * 1e-3) / 1e9,
+                                      "frac": upd_alg / (kernels_ms["update"] * 1e-3) / 1e9 / peak},
                     "update_kernel_share": kernels_ms["update"] / max(sum(kernels_ms.values()), 1e-9)}
 
     # ---- e2e: HOST buffers through the C ABI (glove_train_steps_host): H2D of every batch + D2H of every loss --------
@@ -374,10 +516,17 @@ def main():
             dist.destroy_process_group()
         return
 
+    topk = None
+    if N == 1 and not args.no_topk and args.workload == "wiki6b":
+        eng = row = col = tgt = wgt = None                 # free the training state before the 2.2M-row table
+        torch.cuda.empty_cache()
+        topk = topk_record(dev, sampler)
+    sampler.stop()
+
     cpu = None
     if not args.no_cpu_baseline and N == 1:
         csteps = 96 if V >= 100_000 else 1024                      # about 10 s of CPU work on the box's host cores
-        ups, dt, cores = cpu_reference(V, d, B_local, csteps, 1)
+        ups, dt, cores = cpu_reference(V, d, B_local, csteps, 3)
         cpu = {"value": ups, "unit": "updates/s", "cores": cores, "kind": "port",
                "sample": "%d TRAIN steps of B=%d (%.1f s), C port of the oracle with OpenMP, legacy-Keras dense Adam"
                          % (csteps, B_local, dt)}
@@ -392,17 +541,15 @@ def main():
         per_step_launches = 3 + {"peer": 1, "peer-direct": 0, "alltoall": 2, "allgather": 0}[args.shard_exchange]
     else:
         per_step_launches = 4
-    per_step_launches += 2 if args.adam_mode == "replay" else 0
+    per_step_launches += 2 if args.adam_mode in ("replay_exact", "dense") else 0
     line = {"metric": "co-occurrence updates/sec", "value": value, "unit": "updates/s", "n_gpus": N,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(config, global_batch=B, adam_mode=args.adam_mode,
-                           parallelism=("dp%d" % N) if N == 1 else ("dp%d-%s-tables%s" % (N, args.dp_mode, "-" + args.shard_exchange if args.dp_mode == "sharded" else "")),
-                           l2_flush="inputs larger than L2 (tables+slots %.1f GB, COO %.1f GB)"
-                                    % (2 * V * eng.P * eng.S * 4 / 1e9, nnz * 16 / 1e9),
-                           state="cold" if args.cold_state else "steady-state emulation at step %d" % T0),
+            "config": make_config(),
             "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * per_step_launches + n_prep * 20,
-            "roofline": roofline, "cpu_baseline": cpu, "final_loss": float(losses[-1])}
+            "roofline": roofline, "cpu_baseline": cpu, "final_loss": float(final_loss)}
+    if topk is not None:
+        line["topk"] = topk
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -12,7 +12,10 @@ LIB_PATH = os.path.join(_HERE, "libglove_b200.so")
 OK, EINVAL, ECUDA, EWORKSPACE, EUNSUPPORTED = 0, -1, -2, -3, -4
 HEADS = {"glove": 0, "logistic": 1}
 OPTIMIZERS = {"Adam": 0, "Adagrad": 1, "SGD": 2}
-ADAM_MODES = {"replay": 0, "lazy": 1, "dense": 0}  # "dense" = replay + flush after every step (host schedule)
+# "replay" = closed-form replay of idle steps (default, reference semantics); "replay_exact" = step-by-step replay with the
+# dense sweep's fp32 operations; "dense" = replay_exact + flush after every step (the literal legacy-Keras schedule)
+ADAM_MODES = {"replay": 0, "lazy": 1, "replay_exact": 2, "dense": 2}
+ABI_VERSION = 2
 
 c_i32, c_i64, c_u32, c_f32 = ctypes.c_int32, ctypes.c_int64, ctypes.c_uint32, ctypes.c_float
 c_void, c_size = ctypes.c_void_p, ctypes.c_size_t
@@ -24,7 +27,8 @@ class GloveScalars(ctypes.Structure):
 
 
 class StepArgs(ctypes.Structure):
-    _fields_ = [("row_table", c_void), ("col_table", c_void), ("scalars", c_void), ("plan", c_void),
+    _fields_ = [("struct_size", c_u32),
+                ("row_table", c_void), ("col_table", c_void), ("scalars", c_void), ("plan", c_void),
                 ("workspace", c_void), ("workspace_bytes", c_size), ("alpha", c_void), ("alpha_len", c_i32),
                 ("loss_out", c_void), ("loss_cap", c_i32), ("plan_K", c_i32), ("V", c_i64), ("d", c_i32), ("B", c_i32),
                 ("head", c_i32), ("optimizer", c_i32), ("adam_mode", c_i32), ("learning_rate", c_f32),
@@ -59,6 +63,7 @@ SIGNATURES = {
                                                      c_i64, c_u32, c_i32, c_i32, c_i32, c_i32, c_i32, c_void]),
     "glove_plan_shard_info": (ctypes.c_int, [c_void, c_i32, c_i32, c_i32, ctypes.POINTER(c_i32), c_void]),
     "glove_plan_batch_counts": (ctypes.c_int, [c_void, c_i32, c_i32, c_i32, ctypes.POINTER(c_i32), c_void]),
+    "glove_step_args_size": (c_size, []),
     "glove_step_workspace_bytes": (c_size, [c_i32, c_i32]),
     "glove_train_step": (ctypes.c_int, [ctypes.POINTER(StepArgs), c_void]),
     "glove_catchup_step": (ctypes.c_int, [ctypes.POINTER(StepArgs), c_i32, c_void]),
@@ -77,6 +82,8 @@ SIGNATURES = {
     "glove_step_snapshot_offset": (c_size, [c_i32, c_i32, c_i32]),
     "glove_flush_lazy_state": (ctypes.c_int, [c_void, c_i64, c_i32, c_i32, c_i32, c_void, c_i32, c_i32, c_f32, c_f32, c_f32,
                                               c_void]),
+    "glove_flush_lazy_state_exact": (ctypes.c_int, [c_void, c_i64, c_i32, c_i32, c_i32, c_void, c_i32, c_i32, c_f32, c_f32,
+                                                    c_f32, c_void]),
     "glove_eval_workspace_bytes": (c_size, [c_i64, c_i32]),
     "glove_eval_loss": (ctypes.c_int, [c_void, c_void, c_void, c_i32, c_i32, c_void, c_void, c_void, c_void, c_i64,
                                        c_i64, c_i32, c_i32, c_void, c_void, c_size, c_void]),
@@ -115,8 +122,10 @@ SIGNATURES = {
                                          ctypes.POINTER(c_i64), c_void]),
     "glove_host_staging_bytes": (c_size, [c_i32, c_i32]),
     "glove_host_plan_bytes": (c_size, [c_i32, c_i32]),
-    "glove_train_steps_host": (ctypes.c_int, [ctypes.POINTER(StepArgs), c_void, c_void, c_size, c_void, c_size, c_void,
-                                              c_void, c_void, c_void, c_i32, c_void, c_void]),
+    "glove_host_pipe_create": (ctypes.c_int, [ctypes.POINTER(c_void)]),
+    "glove_host_pipe_destroy": (ctypes.c_int, [c_void]),
+    "glove_train_steps_host": (ctypes.c_int, [c_void, ctypes.POINTER(StepArgs), c_void, c_void, c_size, c_void, c_size,
+                                              c_void, c_void, c_void, c_void, c_i32, c_void, c_void]),
 }
 
 if not os.path.exists(LIB_PATH):
@@ -130,8 +139,12 @@ for _name, (_res, _args) in SIGNATURES.items():
     _fn.restype = _res
     _fn.argtypes = _args
 
-if lib.glove_abi_version() != 1:
-    raise ImportError("glove_tensorflow_b200: ABI version mismatch in %s" % LIB_PATH)
+if lib.glove_abi_version() != ABI_VERSION:
+    raise ImportError("glove_tensorflow_b200: ABI version mismatch in %s (library %d, binding %d)"
+                      % (LIB_PATH, lib.glove_abi_version(), ABI_VERSION))
+if lib.glove_step_args_size() != ctypes.sizeof(StepArgs):
+    raise ImportError("glove_tensorflow_b200: glove_step_args is %d bytes in %s, %d in the ctypes binding"
+                      % (lib.glove_step_args_size(), LIB_PATH, ctypes.sizeof(StepArgs)))
 
 
 class GloveError(RuntimeError):

@@ -82,8 +82,9 @@ def build_parser():
                    help="number of steps per checkpoint (default: %(default)s)")
     p.add_argument("--top-k", type=int, default=TOP_K, help="number of similar items (default: %(default)s)")
     # --- B200-only knobs (defaults = reference semantics) ---
-    p.add_argument("--adam-mode", default="replay", choices=["replay", "dense", "lazy"],
-                   help="replay/dense = legacy Keras Adam (reference); lazy = LazyAdam (default: %(default)s)")
+    p.add_argument("--adam-mode", default="replay", choices=["replay", "replay_exact", "dense", "lazy"],
+                   help="replay / replay_exact / dense = legacy Keras Adam (reference): idle steps applied in closed form / "
+                        "replayed step by step / swept after every step; lazy = LazyAdam (default: %(default)s)")
     p.add_argument("--reg-scale", type=float, default=None,
                    help="activity-L2 multiplicity; default 2 for the estimator trainers under TF 2.11 (SURVEY A4)")
     p.add_argument("--plan-steps", type=int, default=16, help="batches planned per prepare call (default: %(default)s)")

@@ -2,6 +2,8 @@
 // One call = K TRAIN steps on K*B explicit triples that live in HOST memory: H2D copies, plan construction, K steps,
 // D2H copy of the K losses -- what K iterations of `session.run(train_op)` fed by input_fn do in the reference
 // [ref src/models/estimator.py:79-95, src/models/data_utils.py:4-26].
+#include <new>
+
 #include "glove_common.cuh"
 
 namespace glove {
@@ -35,34 +37,51 @@ static HostStaging staging_view(void *base, int32_t K, int32_t B) {
     return v;
 }
 
-// helper streams / events of the host entry, one set per device, created on first use and kept for the process lifetime
-struct HostPipe {
-    bool ready = false;
-    cudaStream_t copy = nullptr, side = nullptr;
-    cudaEvent_t plan_ready[2] = {nullptr, nullptr}, chunk_done[2] = {nullptr, nullptr}, step_done[2] = {nullptr, nullptr};
-    cudaEvent_t caught_up = nullptr, entered = nullptr;
-};
-static HostPipe g_pipe[64];
-static int host_pipe(HostPipe **out) {
-    int dev = 0;
-    GLOVE_CHECK_CUDA(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64) return set_error(GLOVE_EINVAL, "glove_train_steps_host: device index %d", dev);
-    HostPipe &hp = g_pipe[dev];
-    if (!hp.ready) {
-        GLOVE_CHECK_CUDA(cudaStreamCreateWithFlags(&hp.copy, cudaStreamNonBlocking));
-        GLOVE_CHECK_CUDA(cudaStreamCreateWithFlags(&hp.side, cudaStreamNonBlocking));
-        cudaEvent_t *evs[] = {&hp.plan_ready[0], &hp.plan_ready[1], &hp.chunk_done[0], &hp.chunk_done[1],
-                              &hp.step_done[0], &hp.step_done[1], &hp.caught_up, &hp.entered};
-        for (cudaEvent_t *e : evs) GLOVE_CHECK_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
-        hp.ready = true;
-    }
-    *out = &hp;
-    return GLOVE_OK;
-}
 }  // namespace glove
 using namespace glove;
 
+// helper streams / events of the host entry: CALLER-OWNED (glove_host_pipe_create / _destroy), one per concurrent caller
+// and device -- the library keeps no process-global state, so two pipes can drive two streams or devices at once
+struct glove_host_pipe {
+    int device = -1;
+    cudaStream_t copy = nullptr, side = nullptr;
+    cudaEvent_t plan_ready[2] = {nullptr, nullptr}, chunk_done[2] = {nullptr, nullptr}, step_done[2] = {nullptr, nullptr};
+    cudaEvent_t caught_up = nullptr;
+};
+
 extern "C" {
+
+int glove_host_pipe_create(glove_host_pipe **out) {
+    GLOVE_REQUIRE(out, "glove_host_pipe_create: null output");
+    *out = nullptr;
+    glove_host_pipe *hp = new (std::nothrow) glove_host_pipe();
+    GLOVE_REQUIRE(hp, "glove_host_pipe_create: out of memory");
+    cudaError_t e = cudaGetDevice(&hp->device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&hp->copy, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&hp->side, cudaStreamNonBlocking);
+    cudaEvent_t *evs[] = {&hp->plan_ready[0], &hp->plan_ready[1], &hp->chunk_done[0], &hp->chunk_done[1],
+                          &hp->step_done[0], &hp->step_done[1], &hp->caught_up};
+    for (cudaEvent_t *ev : evs)
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        glove_host_pipe_destroy(hp);
+        return set_error(GLOVE_ECUDA, "glove_host_pipe_create: %s", cudaGetErrorString(e));
+    }
+    *out = hp;
+    return GLOVE_OK;
+}
+
+int glove_host_pipe_destroy(glove_host_pipe *hp) {
+    if (!hp) return GLOVE_OK;
+    cudaEvent_t evs[] = {hp->plan_ready[0], hp->plan_ready[1], hp->chunk_done[0], hp->chunk_done[1],
+                         hp->step_done[0], hp->step_done[1], hp->caught_up};
+    for (cudaEvent_t ev : evs)
+        if (ev) cudaEventDestroy(ev);
+    if (hp->copy) cudaStreamDestroy(hp->copy);
+    if (hp->side) cudaStreamDestroy(hp->side);
+    delete hp;
+    return GLOVE_OK;
+}
 
 size_t glove_host_staging_bytes(int32_t K, int32_t B) {
     if (K <= 0 || B <= 0) return 0;
@@ -77,21 +96,25 @@ size_t glove_host_plan_bytes(int32_t K, int32_t B) {
 //   copy stream : H2D(c) -> glove_prepare_batches(c)            (waits until the steps of chunk c-2 released the buffers)
 //   main stream : plan_K x glove_train_step(c)                   (waits for plan_ready[c])
 //   side stream : glove_catchup_step(s+1) while step s runs      (exact-replay Adam only; needs step s-1 finished)
-int glove_train_steps_host(const glove_step_args *args, void *plan, void *prepare_ws, size_t prepare_ws_bytes,
+int glove_train_steps_host(glove_host_pipe *hp, const glove_step_args *args, void *plan, void *prepare_ws, size_t prepare_ws_bytes,
                            void *staging, size_t staging_bytes, const int32_t *host_row, const int32_t *host_col,
                            const float *host_colA, const float *host_colB, int32_t K, float *host_losses,
                            void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    GLOVE_REQUIRE(args && plan && prepare_ws && staging && host_row && host_col && host_colA && host_colB && host_losses,
+    GLOVE_REQUIRE(hp && args && plan && prepare_ws && staging && host_row && host_col && host_colA && host_colB && host_losses,
                   "glove_train_steps_host: null pointer");
+    GLOVE_REQUIRE(args->struct_size == sizeof(glove_step_args), "glove_train_steps_host: glove_step_args.struct_size mismatch");
+    {
+        int dev = -1;
+        GLOVE_CHECK_CUDA(cudaGetDevice(&dev));
+        GLOVE_REQUIRE(dev == hp->device, "glove_train_steps_host: pipe was created on device %d, current device is %d", hp->device, dev);
+    }
     const int32_t PK = args->plan_K;
     GLOVE_REQUIRE(PK > 0 && K > 0 && K % PK == 0 && K <= kHostLossCap,
                   "glove_train_steps_host: K must be a multiple of args->plan_K, at most %d", kHostLossCap);
     HostStaging st = staging_view(staging, PK, args->B);
     if (staging_bytes < st.bytes)
         return set_error(GLOVE_EWORKSPACE, "glove_train_steps_host: staging %zu < required %zu", staging_bytes, st.bytes);
-    HostPipe *hp = nullptr;
-    if (int rc = host_pipe(&hp)) return rc;
     const int64_t N = (int64_t)PK * args->B;
     const int n_chunks = K / PK;
     void *plans[2] = {plan, (char *)plan + align_up(glove_plan_bytes(PK, args->B))};
@@ -101,7 +124,7 @@ int glove_train_steps_host(const glove_step_args *args, void *plan, void *prepar
     read_step_kernel<<<1, 1, 0, stream>>>(args->scalars, st.step);
     GLOVE_CHECK_CUDA(cudaMemcpyAsync(&first_step, st.step, 4, cudaMemcpyDeviceToHost, stream));
     GLOVE_CHECK_CUDA(cudaStreamSynchronize(stream));   // everything enqueued before this call has finished
-    const bool catchup = args->optimizer == GLOVE_OPT_ADAM && args->adam_mode == GLOVE_ADAM_REPLAY && args->n_shards <= 1 &&
+    const bool catchup = args->optimizer == GLOVE_OPT_ADAM && args->adam_mode == GLOVE_ADAM_REPLAY_EXACT && args->n_shards <= 1 &&
                          args->dp_world <= 1;
     glove_step_args a = *args;
     a.loss_out = st.losses;

@@ -41,6 +41,8 @@ struct StepParams {
     int32_t *long_cnt[2]; // [max long segments] chunks finished so far (self-resetting; workspace starts zeroed)
     int32_t *chunk_cnt[2];  // [max parts] pieces finished in the chunk that starts at this partial slot (self-resetting)
     double *warp_out;     // [kMaxWarps][3] per-warp sums of {data loss, sum e, reg term}
+    int32_t *gap[2];      // [snapshot rows] closed-form replay: idle steps the staged row owed (0 = moments are current)
+    float l2b1, l2b2;     // log2(beta1), log2(beta2) (host double, rounded once)
     float *grad[2];       // MODE_GRAD / MODE_APPLY: dense per-slot gradient buffers
     float *grad_scalars;  // [4]
     const float *alpha;
@@ -65,6 +67,7 @@ struct StepWs {
     int32_t *chunk_cnt[2];
     double *warp_out;
     const float **peer_tab;   // [2][kMaxShards] snapshot bases of the peers (glove_shard_set_peers)
+    int32_t *gap[2];
     size_t bytes;
 };
 static inline int64_t snapshot_rows(int32_t B) { return (int64_t)B + B / 4 + 64; }  // room for padded shard blocks
@@ -81,6 +84,7 @@ static StepWs step_ws_view(void *base, int32_t B, int32_t d) {
     for (int s = 0; s < 2; ++s) w.chunk_cnt[s] = (int32_t *)take(sizeof(int32_t) * (size_t)max_parts_per_batch(B));
     w.warp_out = (double *)take(sizeof(double) * 3 * kMaxWarps);
     w.peer_tab = (const float **)take(sizeof(float *) * 2 * kMaxShards);
+    for (int s = 0; s < 2; ++s) w.gap[s] = (int32_t *)take(sizeof(int32_t) * (size_t)snapshot_rows(B));
     w.bytes = off;
     return w;
 }
@@ -179,7 +183,7 @@ __global__ void __launch_bounds__(256) stage_kernel(const StepParams p, int step
     const int pos0[2] = {p.shard * p.side[0].b_upad[k], p.shard * p.side[1].b_upad[k]};  // first snapshot row of the block
     const int64_t id0 = (int64_t)p.shard * p.v_loc;                                       // first (remapped) id owned
     const int S4 = p.S >> 2;
-    const bool replay = (p.opt == GLOVE_OPT_ADAM && p.adam_mode == GLOVE_ADAM_REPLAY);
+    const bool replay = (p.opt == GLOVE_OPT_ADAM && p.adam_mode == GLOVE_ADAM_REPLAY_EXACT);
     const int total = (U0 + U1) * S4;
 
     // ---- pass 1 (stage only): rows that are current are a pure 128-bit copy; 4 chunks per warp in flight
@@ -282,6 +286,71 @@ __global__ void __launch_bounds__(256) stage_kernel(const StepParams p, int step
     }
 }
 
+// ---- K1 (GLOVE_ADAM_REPLAY, the default): stage with the closed-form replay -------------------------------------------
+// One warp per distinct id of the batch.  The pre-step row (plane 0) is loaded one row ahead; a row that owes idle Adam
+// steps (0 < last_step < step) also loads its moments, gets the run of idle steps applied in closed form (replay_x4:
+// one sqrt, one reciprocal and a cubic per element, independent of the gap) and is published to the snapshot.  NOTHING
+// is written back to the table: the update kernel of the same step re-reads the moments anyway, scales them by
+// b1^gap / b2^gap (gap is left in p.gap[side][position]) and writes x, m, v once.  HBM traffic per row: 3 plane reads
+// (1 for rows touched by the previous step) + the snapshot write; arithmetic is O(1) per element, so the kernel is
+// bound by HBM, not by the MUFU pipe like the sequential replay (stage_kernel pass 2).
+template <int NV>
+__global__ void __launch_bounds__(256) stage_closed_kernel(const StepParams p) {
+    __shared__ ReplayTables tabs;
+    int k, step;
+    const bool ok = batch_index(p, k, step);
+    replay_tables_init(tabs, p.b1, p.b2);
+    if (!ok) return;
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int seg0[2] = {p.side[0].b_seg[k], p.side[1].b_seg[k]};
+    const int own0[2] = {p.side[0].b_own[k * (kMaxShards + 1) + p.shard], p.side[1].b_own[k * (kMaxShards + 1) + p.shard]};
+    const int U0 = p.side[0].b_own[k * (kMaxShards + 1) + p.shard + 1] - own0[0];
+    const int U1 = p.side[1].b_own[k * (kMaxShards + 1) + p.shard + 1] - own0[1];
+    const int pos0[2] = {p.shard * p.side[0].b_upad[k], p.shard * p.side[1].b_upad[k]};
+    const int64_t id0 = (int64_t)p.shard * p.v_loc;
+    const int S4 = p.S >> 2;
+    const int total = U0 + U1;
+    auto row_of = [&](int w) -> const float * {
+        const int s = w >= U0 ? 1 : 0;
+        const int j = s ? w - U0 : w;
+        return p.table[s] + ((int64_t)__ldg(p.side[s].seg_id + seg0[s] + own0[s] + j) - id0) * p.P * p.S;
+    };
+    float4 xn[NV];
+    const float *row_n = nullptr;
+    if (warp < total) { row_n = row_of(warp); load_row<NV>(xn, row_n, lane, S4); }
+#pragma unroll 1
+    for (int w = warp; w < total; w += nwarps) {
+        const int s = w >= U0 ? 1 : 0;
+        const int j = s ? w - U0 : w;
+        const float *row = row_n;
+        float4 x[NV];
+#pragma unroll
+        for (int r = 0; r < NV; ++r) x[r] = xn[r];
+        const int lcol = ls_col(p.d, s);
+        const int ls = __float_as_int(row_col<NV>(x, lcol, lane));
+        const int gap = (ls > 0 && ls < step) ? step - ls : 0;
+        float4 m[NV], v[NV];
+        if (gap) { load_row<NV>(m, row + p.S, lane, S4); load_row<NV>(v, row + 2 * p.S, lane, S4); }
+        if (w + nwarps < total) { row_n = row_of(w + nwarps); load_row<NV>(xn, row_n, lane, S4); }   // next row's plane 0
+        if (gap) {
+            const ReplayCoef c = replay_coef(tabs, p.alpha, ls, gap, p.l2b1, p.l2b2, lane);
+#pragma unroll
+            for (int r = 0; r < NV; ++r) x[r] = replay_x4(x[r], m[r], v[r], c, p.eps);
+        }
+#pragma unroll
+        for (int r = 0; r < NV; ++r) {
+            const int f = lane + 32 * r;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (4 * f + c == lcol) f4c(x[r], c) = 1.0f;     // 1.0 in the other side's bias column
+        }
+        const int pos = pos0[s] + j;
+        store_row<NV>(p.snap[s] + (int64_t)pos * p.S, x, lane, S4);
+        if (lane == 0) p.gap[s][pos] = gap;
+    }
+}
+
 // second half of the catch-up: mark the pre-replayed rows current (same predicate as stage_kernel<true>)
 __global__ void __launch_bounds__(256) commit_ls_kernel(const StepParams p, int step) {
     const int k = step - p.hdr->first_step;
@@ -307,11 +376,18 @@ __global__ void __launch_bounds__(256) commit_ls_kernel(const StepParams p, int 
 // stage kernel has already decayed m, v through step-1, so the moments are read as-is.
 template <int NV>
 __device__ __forceinline__ void apply_row(const StepParams &p, float *row, float4 (&x)[NV], const float4 (&G)[NV],
-                                          float4 (&s1)[NV], float4 (&s2)[NV], int s, int step, int lane) {
+                                          float4 (&s1)[NV], float4 (&s2)[NV], int s, int step, int lane, int gap) {
     // s1 / s2 = optimizer slot planes 1 / 2 of the row, already loaded by the caller (prefetched at item start)
+    // gap = idle steps the row owed when it was staged (closed-form replay: the moments in the table are `gap` steps old)
     const int S4 = p.S >> 2;
     if (p.opt == GLOVE_OPT_ADAM) {
         const float na = -__ldg(p.alpha + step);
+        if (gap > 0) {
+            float dm, dv;
+            replay_decay(gap, p.l2b1, p.l2b2, dm, dv);
+#pragma unroll
+            for (int r = 0; r < NV; ++r) { s1[r] = scale4(s1[r], dm); s2[r] = scale4(s2[r], dv); }
+        }
 #pragma unroll
         for (int r = 0; r < NV; ++r) {
             float2 xa = make_float2(x[r].x, x[r].y), xb = make_float2(x[r].z, x[r].w);
@@ -456,6 +532,7 @@ __global__ void __launch_bounds__(128, (NV <= 3 ? 4 : 3)) update_kernel(const St
     const float ce = (2.0f * p.rs * p.l2) / ((float)p.d * (float)p.B), cbias = (2.0f * p.rs * p.l2) / (float)p.B;
     const float reg_unscale = (float)p.B / (2.0f * p.rs);  // coef * reg_unscale = l2/d (embedding) | l2 (bias)
     const bool train = p.mode == MODE_TRAIN || p.mode == MODE_SHARD;
+    const bool closed = p.opt == GLOVE_OPT_ADAM && p.adam_mode == GLOVE_ADAM_REPLAY;   // moments in the table are gap steps old
     const int64_t id0 = (int64_t)p.shard * p.v_loc;   // first (remapped) id held by this shard
     double w_ld = 0.0, w_se = 0.0, w_rg = 0.0;   // this warp's share of the step's loss terms (fixed item order)
 
@@ -498,6 +575,7 @@ __global__ void __launch_bounds__(128, (NV <= 3 ? 4 : 3)) update_kernel(const St
             float4 x[NV], acc[NV], bufA[NV], bufB[NV], s1[NV], s2[NV];
             load_row<NV>(x, p.snap[s] + (int64_t)slot * p.S, lane, S4);
             const bool applies = train && part == 0;
+            const int gap_own = (applies && closed) ? __ldcg(p.gap[s] + slot) : 0;
             if (applies && p.P >= 2) load_row<NV>(s1, row + p.S, lane, S4);
             if (applies && p.P >= 3) load_row<NV>(s2, row + 2 * p.S, lane, S4);
             const int itn = itl + nwarps;
@@ -597,14 +675,14 @@ __global__ void __launch_bounds__(128, (NV <= 3 ? 4 : 3)) update_kernel(const St
                             load_row<NV>(x, p.snap[s] + (int64_t)lr.y * p.S, lane, S4);
                             if (p.P >= 2) load_row<NV>(s1, lrow + p.S, lane, S4);
                             if (p.P >= 3) load_row<NV>(s2, lrow + 2 * p.S, lane, S4);
-                            apply_row<NV>(p, lrow, x, acc, s1, s2, s, step, lane);
+                            apply_row<NV>(p, lrow, x, acc, s1, s2, s, step, lane, closed ? __ldcg(p.gap[s] + lr.y) : 0);
                         }
                     }
                 }
             } else if (!train) {
                 store_row<NV>(p.grad[s] + (int64_t)slot * p.S, acc, lane, S4);
             } else {
-                apply_row<NV>(p, row, x, acc, s1, s2, s, step, lane);
+                apply_row<NV>(p, row, x, acc, s1, s2, s, step, lane, gap_own);
             }
             ir = ir_next;
             itl = itn;
@@ -747,7 +825,8 @@ __global__ void __launch_bounds__(128) apply_kernel(const StepParams p) {
         load_row<NV>(G, p.grad[s] + (int64_t)j * p.S, lane, S4);
         if (p.P >= 2) load_row<NV>(s1, row + p.S, lane, S4);
         if (p.P >= 3) load_row<NV>(s2, row + 2 * p.S, lane, S4);
-        apply_row<NV>(p, row, x, G, s1, s2, s, step, lane);
+        const int gap = (p.opt == GLOVE_OPT_ADAM && p.adam_mode == GLOVE_ADAM_REPLAY) ? __ldcg(p.gap[s] + pos0[s] + j) : 0;
+        apply_row<NV>(p, row, x, G, s1, s2, s, step, lane, gap);
     }
 }
 
@@ -764,6 +843,9 @@ static int fill_params(const glove_step_args *a, StepParams &p, int mode) {
     GLOVE_REQUIRE(a->V > 0 && a->d > 0 && a->B > 0 && a->plan_K > 0, "step: bad sizes");
     GLOVE_REQUIRE(a->head == GLOVE_HEAD_GLOVE || a->head == GLOVE_HEAD_LOGISTIC, "step: unsupported head %d", a->head);
     GLOVE_REQUIRE(a->optimizer >= 0 && a->optimizer <= 2, "step: unsupported optimizer %d", a->optimizer);
+    GLOVE_REQUIRE(a->adam_mode >= 0 && a->adam_mode <= 2, "step: unsupported adam_mode %d", a->adam_mode);
+    GLOVE_REQUIRE(a->struct_size == sizeof(glove_step_args), "step: glove_step_args.struct_size %u != %zu (ABI mismatch)",
+                  (unsigned)a->struct_size, sizeof(glove_step_args));
     if (a->optimizer == GLOVE_OPT_ADAM) GLOVE_REQUIRE(a->alpha && a->alpha_len > 0, "step: Adam needs the alpha table");
     const int32_t S = table_stride(a->d);
     if (S / 4 > 32 * 4) return set_error(GLOVE_EUNSUPPORTED, "step: embedding size %d > 510 not supported", a->d);
@@ -780,6 +862,8 @@ static int fill_params(const glove_step_args *a, StepParams &p, int mode) {
         p.grad[s] = nullptr;
     }
     p.warp_out = w.warp_out;
+    p.gap[0] = w.gap[0]; p.gap[1] = w.gap[1];
+    p.l2b1 = replay_log2(a->beta1); p.l2b2 = replay_log2(a->beta2);
     p.grad_scalars = nullptr;
     p.alpha = a->alpha; p.alpha_len = a->alpha_len;
     p.loss_out = a->loss_cap > 0 ? a->loss_out : nullptr; p.loss_cap = a->loss_cap > 0 ? a->loss_cap : 1;
@@ -812,13 +896,17 @@ static int occupancy_grid(Kern kern, int threads) {
 
 template <int NV>
 static int launch_step(const StepParams &p, cudaStream_t stream, cudaEvent_t *ev = nullptr) {
-    static int g_stage = 0, g_update = 0, g_apply = 0;
+    static int g_stage = 0, g_stage_closed = 0, g_update = 0, g_apply = 0;
     if (!g_stage) g_stage = occupancy_grid(stage_kernel<false>, 256);
+    if (!g_stage_closed) g_stage_closed = occupancy_grid(stage_closed_kernel<NV>, 256);
     if (!g_update) g_update = occupancy_grid(update_kernel<NV, GLOVE_HEAD_GLOVE, false>, 128);
     if (!g_apply) g_apply = occupancy_grid(apply_kernel<NV>, 128);
     if (p.mode == MODE_TRAIN || p.mode == MODE_GRAD || p.mode == MODE_SHARD) {
         if (ev) cudaEventRecord(ev[0], stream);
-        if (p.run_stage) stage_kernel<false><<<g_stage, 256, 0, stream>>>(p, 0);
+        if (p.run_stage) {
+            if (p.opt == GLOVE_OPT_ADAM && p.adam_mode == GLOVE_ADAM_REPLAY) stage_closed_kernel<NV><<<g_stage_closed, 256, 0, stream>>>(p);
+            else stage_kernel<false><<<g_stage, 256, 0, stream>>>(p, 0);
+        }
         if (ev) cudaEventRecord(ev[1], stream);
         const bool dp = p.dp_world > 1;
         if (!p.run_update) {
@@ -896,7 +984,7 @@ int glove_catchup_step(const glove_step_args *args, int32_t step_index, void *st
     StepParams p;
     int rc = fill_params(args, p, args && args->n_shards > 1 ? MODE_GRAD : MODE_TRAIN);
     if (rc != GLOVE_OK) return rc;
-    if (p.opt != GLOVE_OPT_ADAM || p.adam_mode != GLOVE_ADAM_REPLAY) return GLOVE_OK;
+    if (p.opt != GLOVE_OPT_ADAM || p.adam_mode != GLOVE_ADAM_REPLAY_EXACT) return GLOVE_OK;
     static int grid = 0;
     if (!grid) {
         grid = occupancy_grid(stage_kernel<true>, 256);

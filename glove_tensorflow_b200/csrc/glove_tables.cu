@@ -82,6 +82,35 @@ __global__ void __launch_bounds__(256) flush_kernel(float *table, int64_t V, int
     }
 }
 
+// Closed-form flush (GLOVE_ADAM_REPLAY): same per-element arithmetic as stage_closed_kernel (replay_x4), written back
+// to the table together with the decayed moments.  One warp per row, lanes stride the float4 columns.
+__global__ void __launch_bounds__(256) flush_closed_kernel(float *table, int64_t V, int32_t d, int32_t S, int32_t side,
+                                                           const float *__restrict__ alpha, int32_t to_step, float b1,
+                                                           float b2, float l2b1, float l2b2, float eps) {
+    __shared__ ReplayTables tabs;
+    replay_tables_init(tabs, b1, b2);
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int32_t lcol = ls_col(d, side), S4 = S >> 2;
+    for (int64_t r = warp; r < V; r += nwarps) {
+        float *x = table + r * 3 * S, *m = x + S, *v = m + S;
+        const int32_t ls = __float_as_int(x[lcol]);
+        if (ls <= 0 || ls >= to_step) continue;
+        const int gap = to_step - ls;
+        const ReplayCoef c = replay_coef(tabs, alpha, ls, gap, l2b1, l2b2, lane);
+        for (int32_t f = lane; f < S4; f += 32) {
+            float4 xv = ld4(x + 4 * f);
+            const float4 mv = ld4(m + 4 * f), vv = ld4(v + 4 * f);
+            xv = replay_x4(xv, mv, vv, c, eps);
+            if ((lcol >> 2) == f) f4c(xv, lcol & 3) = __int_as_float(to_step);
+            st4(x + 4 * f, xv);
+            st4(m + 4 * f, scale4(mv, c.dm));
+            st4(v + 4 * f, scale4(vv, c.dv));
+        }
+    }
+}
+
 }  // namespace glove
 
 using namespace glove;
@@ -90,6 +119,7 @@ extern "C" {
 
 const char *glove_last_error(void) { return err_buf(); }
 int32_t glove_abi_version(void) { return GLOVE_B200_ABI_VERSION; }
+size_t glove_step_args_size(void) { return sizeof(glove_step_args); }
 int32_t glove_table_stride(int32_t d) { return table_stride(d); }
 int32_t glove_table_planes(int32_t optimizer) { return table_planes(optimizer); }
 
@@ -145,6 +175,19 @@ int glove_set_last_step(float *table, int64_t V, int32_t d, int32_t planes, int3
 
 int glove_flush_lazy_state(float *table, int64_t V, int32_t d, int32_t optimizer, int32_t side, const float *alpha,
                            int32_t alpha_len, int32_t to_step, float beta1, float beta2, float epsilon, void *stream) {
+    GLOVE_REQUIRE(table && V > 0 && d > 0 && (side == 0 || side == 1), "glove_flush_lazy_state: bad arguments");
+    if (optimizer != GLOVE_OPT_ADAM) return GLOVE_OK;  // Adagrad / SGD are truly sparse: nothing to replay
+    GLOVE_REQUIRE(alpha && to_step <= alpha_len, "glove_flush_lazy_state: alpha table too short (%d < %d)", alpha_len,
+                  to_step);
+    if (to_step <= 0) return GLOVE_OK;
+    flush_closed_kernel<<<grid_for(V * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+        table, V, d, table_stride(d), side, alpha, to_step, beta1, beta2, replay_log2(beta1), replay_log2(beta2), epsilon);
+    GLOVE_CHECK_LAUNCH();
+    return GLOVE_OK;
+}
+
+int glove_flush_lazy_state_exact(float *table, int64_t V, int32_t d, int32_t optimizer, int32_t side, const float *alpha,
+                                 int32_t alpha_len, int32_t to_step, float beta1, float beta2, float epsilon, void *stream) {
     GLOVE_REQUIRE(table && V > 0 && d > 0 && (side == 0 || side == 1), "glove_flush_lazy_state: bad arguments");
     if (optimizer != GLOVE_OPT_ADAM) return GLOVE_OK;  // Adagrad / SGD are truly sparse: nothing to replay
     GLOVE_REQUIRE(alpha && to_step <= alpha_len, "glove_flush_lazy_state: alpha table too short (%d < %d)", alpha_len,

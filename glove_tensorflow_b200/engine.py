@@ -115,6 +115,15 @@ class GloveEngine:
         self._norm_cache = None
         self.last_topk_fallbacks = None
 
+    def __del__(self):
+        pipe = getattr(self, "_host_pipe", None)
+        if pipe is not None:
+            try:
+                lib.glove_host_pipe_destroy(pipe)
+            except Exception:
+                pass
+            self._host_pipe = None
+
     # ---- state ---------------------------------------------------------------------------------------------------
     def _write_scalars(self, **kw):
         host = self.scalars.cpu().numpy().copy()
@@ -241,10 +250,10 @@ class GloveEngine:
         self._join_side()
         if self.optimizer != "Adam" or self.adam_mode == "lazy":
             return
+        fn = lib.glove_flush_lazy_state if self.adam_mode == "replay" else lib.glove_flush_lazy_state_exact
         for side, t in enumerate((self.row_table, self.col_table)):
-            check(lib.glove_flush_lazy_state(_ptr(t), self.V, self.d, self.opt_id, side, _ptr(self.alpha), self.max_steps,
-                                             self.host_step, ADAM_BETA1, ADAM_BETA2, KERAS_EPSILON, _stream()),
-                  "glove_flush_lazy_state")
+            check(fn(_ptr(t), self.V, self.d, self.opt_id, side, _ptr(self.alpha), self.max_steps,
+                     self.host_step, ADAM_BETA1, ADAM_BETA2, KERAS_EPSILON, _stream()), "glove_flush_lazy_state")
 
     # ---- input ---------------------------------------------------------------------------------------------------
     def set_coo(self, row, col, col_a, col_b, shuffle_key: int = 0):
@@ -268,6 +277,7 @@ class GloveEngine:
 
     def _make_args(self, which):
         a = _lib.StepArgs()
+        a.struct_size = ctypes.sizeof(_lib.StepArgs)
         a.row_table, a.col_table = self.row_table.data_ptr(), self.col_table.data_ptr()
         a.scalars = self.scalars.data_ptr()
         a.plan = self.plans[which].data_ptr()
@@ -354,8 +364,8 @@ class GloveEngine:
             main.wait_event(self._ev_catchup[1])
         self._ev_catchup = None
         k_next = s + 1 - self.plan_first[which] if self.plan_first[which] is not None else 0
-        if (self.optimizer == "Adam" and self.adam_mode == "replay" and 0 < k_next < self.K and s + 1 < self.max_steps
-                and s >= 1):
+        if (self.optimizer == "Adam" and self.adam_mode in ("replay_exact", "dense") and 0 < k_next < self.K
+                and s + 1 < self.max_steps and s >= 1):
             self._side.wait_event(self._ev_step_done[(s - 1) & 1])
             if self._ev_plan[which] is not None:                        # ... and not before its plan is complete
                 self._side.wait_event(self._ev_plan[which])
@@ -587,13 +597,16 @@ class GloveEngine:
         (numel = steps * B); H2D copies, plan builds, steps and the D2H loss read all happen inside ONE C-ABI call
         (glove_train_steps_host), pipelined chunk against chunk."""
         if getattr(self, "_host_staging", None) is None:
+            pipe = ctypes.c_void_p(0)
+            check(lib.glove_host_pipe_create(ctypes.byref(pipe)), "glove_host_pipe_create")
+            self._host_pipe = pipe
             self._host_staging = torch.empty(lib.glove_host_staging_bytes(self.K, self.B), dtype=torch.uint8, device=self.device)
             self._host_plans = torch.empty(lib.glove_host_plan_bytes(self.K, self.B), dtype=torch.uint8, device=self.device)
         steps = host_row.numel() // self.B
         assert steps * self.B == host_row.numel() and steps % self.K == 0 and not host_row.is_cuda
         assert host_losses.numel() >= steps
         self._join_side()
-        check(lib.glove_train_steps_host(ctypes.byref(self._args[0]), _ptr(self._host_plans), _ptr(self.prep_ws),
+        check(lib.glove_train_steps_host(self._host_pipe, ctypes.byref(self._args[0]), _ptr(self._host_plans), _ptr(self.prep_ws),
                                          self.prep_ws.numel(), _ptr(self._host_staging), self._host_staging.numel(),
                                          _ptr(host_row), _ptr(host_col), _ptr(host_a), _ptr(host_b), steps,
                                          _ptr(host_losses), _stream()), "glove_train_steps_host")

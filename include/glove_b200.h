@@ -36,7 +36,10 @@
 extern "C" {
 #endif
 
-#define GLOVE_B200_ABI_VERSION 1
+/* 2: glove_step_args starts with struct_size and ends with peer_gather (n_shards, shard, peer_gather were appended in
+ *    round 1 without a bump); adam_mode gained GLOVE_ADAM_REPLAY_EXACT and GLOVE_ADAM_REPLAY became the closed-form
+ *    replay; glove_train_steps_host takes a caller-owned glove_host_pipe; glove_train_steps_graph added. */
+#define GLOVE_B200_ABI_VERSION 2
 
 enum { GLOVE_OK = 0, GLOVE_EINVAL = -1, GLOVE_ECUDA = -2, GLOVE_EWORKSPACE = -3, GLOVE_EUNSUPPORTED = -4 };
 
@@ -50,10 +53,16 @@ enum { GLOVE_OPT_ADAM = 0, GLOVE_OPT_ADAGRAD = 1, GLOVE_OPT_SGD = 2 };
 
 /* adam_mode:
  *   GLOVE_ADAM_REPLAY  reference semantics (legacy Keras Adam decays m, v and moves x on ALL rows every step) obtained
- *                      without dense sweeps: a row's missed zero-gradient steps are replayed in registers when it is
- *                      next touched (and by glove_flush_lazy_state before eval / export / checkpoint).
+ *                      without dense sweeps: the zero-gradient steps a row missed are applied when it is next touched
+ *                      (and by glove_flush_lazy_state before eval / export / checkpoint), in CLOSED FORM: the run
+ *                      sum_j alpha_j b1^j m0 / (b2^(j/2) sqrt(v0) + eps) is a cubic in q = sqrt(v0)/(sqrt(v0)+eps) with
+ *                      per-row coefficients, so a run of any length costs one sqrt + one reciprocal per element.  Equal to
+ *                      the sequential recurrence to fp32 resolution (closer to its fp64 value than the fp32 recurrence is).
+ *   GLOVE_ADAM_REPLAY_EXACT  the same schedule with the run replayed step by step with exactly the fp32 operations of the
+ *                      dense sweep: bit-identical to flushing after every step (the literal legacy-Keras schedule), at the
+ *                      price of O(gap) arithmetic per element.  Kept as the arithmetic ground truth of the tests.
  *   GLOVE_ADAM_LAZY    LazyAdam: untouched rows frozen.  NOT the reference's arithmetic; kept for measurement. */
-enum { GLOVE_ADAM_REPLAY = 0, GLOVE_ADAM_LAZY = 1 };
+enum { GLOVE_ADAM_REPLAY = 0, GLOVE_ADAM_LAZY = 1, GLOVE_ADAM_REPLAY_EXACT = 2 };
 
 /* Device-resident scalars (32 bytes).  step = global_step = number of optimizer steps applied so far
  * [ref src/models/estimator.py:44-45].  g = MatrixFactorisation.global_bias [ref src/models/model_utils.py:39]. */
@@ -116,6 +125,8 @@ int glove_plan_batch_counts(const void *plan, int32_t K, int32_t B, int32_t k, i
 
 /* ---- TRAIN: model_fn(mode=TRAIN) + optimizer.get_updates [ref src/models/estimator.py:13-56] ------------------- */
 typedef struct glove_step_args {
+    uint32_t struct_size;         /* = sizeof(glove_step_args) as compiled by the CALLER (glove_step_args_size() is the
+                                   * library's): every entry point refuses a mismatch instead of reading past the struct */
     float *row_table, *col_table; /* packed tables */
     glove_scalars *scalars;       /* device */
     const void *plan;             /* from glove_prepare_batches; the batch used is (scalars->step - plan.first_step) */
@@ -143,10 +154,11 @@ typedef struct glove_step_args {
     int32_t peer_gather;
 } glove_step_args;
 
+size_t glove_step_args_size(void);
 size_t glove_step_workspace_bytes(int32_t B, int32_t d);
 /* one full TRAIN step; increments scalars->step */
 int glove_train_step(const glove_step_args *args, void *stream);
-/* Optional overlap aid for GLOVE_ADAM_REPLAY: replays, ahead of time and on ANOTHER stream, the idle Adam steps of the
+/* Optional overlap aid for GLOVE_ADAM_REPLAY_EXACT: replays, ahead of time and on ANOTHER stream, the idle Adam steps of the
  * rows of step `step_index`'s batch that are not in the batch of step_index-1 (so the step in flight cannot touch
  * them).  Must be ordered after the completion of step_index-2 and before the start of step_index (events); a no-op
  * for the first batch of a plan and for other optimizers / modes.  Results are bit-identical with or without it. */
@@ -198,11 +210,14 @@ int glove_shard_finish_step(const glove_step_args *args, const float *loss_scala
 int64_t glove_step_snapshot_rows(int32_t B);
 size_t glove_step_snapshot_offset(int32_t B, int32_t d, int32_t side);
 
-/* Replays the missed zero-gradient Adam steps of every row up to (not including) step to_step.  Required before the
- * tables are read from outside the step (eval, export, checkpoint) in GLOVE_ADAM_REPLAY mode; calling it after every
- * step gives the literal dense-sweep schedule of legacy Keras Adam. */
+/* Applies the missed zero-gradient Adam steps of every row up to (not including) step to_step (closed form, as the
+ * stage of GLOVE_ADAM_REPLAY does).  Required before the tables are read from outside the step (eval, export,
+ * checkpoint).  glove_flush_lazy_state_exact replays them step by step (GLOVE_ADAM_REPLAY_EXACT); calling it after
+ * every step is the literal dense-sweep schedule of legacy Keras Adam. */
 int glove_flush_lazy_state(float *table, int64_t V, int32_t d, int32_t optimizer, int32_t side, const float *alpha,
                            int32_t alpha_len, int32_t to_step, float beta1, float beta2, float epsilon, void *stream);
+int glove_flush_lazy_state_exact(float *table, int64_t V, int32_t d, int32_t optimizer, int32_t side, const float *alpha,
+                                 int32_t alpha_len, int32_t to_step, float beta1, float beta2, float epsilon, void *stream);
 
 /* ---- EVAL: model_fn(mode=EVAL), RegressionHead metrics [ref src/models/estimator.py:87-92] -------------------- */
 /* Forward-only pass over COO positions [first, first+count) in file order in batches of batch_size.  out: double
@@ -335,12 +350,17 @@ int glove_cooc_finish(const uint64_t *keys, const int64_t *agg, int64_t n, int32
 /* Runs K TRAIN steps (K a multiple of args->plan_K, at most 4096) on K*B explicit triples held in HOST memory (pinned
  * recommended) and copies the K losses back to host_losses.  Internally a pipeline over the chunks of plan_K steps:
  * H2D + plan construction of chunk c+1 on a helper stream while the steps of chunk c run on `stream`, and (exact-replay
- * Adam) the catch-up of step s+1 on a second helper stream while step s runs.  Device state (tables, scalars, plans,
+ * Adam) the catch-up of step s+1 on a second helper stream while step s runs (GLOVE_ADAM_REPLAY_EXACT only).  Device state (tables, scalars, plans,
  * workspaces) stays caller-owned: `plan` holds glove_host_plan_bytes(plan_K, B) bytes (two plans), `staging`
  * glove_host_staging_bytes(plan_K, B).  Synchronises the stream on entry and before returning. */
 size_t glove_host_staging_bytes(int32_t plan_K, int32_t B);
 size_t glove_host_plan_bytes(int32_t plan_K, int32_t B);
-int glove_train_steps_host(const glove_step_args *args, void *plan, void *prepare_ws, size_t prepare_ws_bytes,
+/* The helper streams and events of the pipeline live in a CALLER-OWNED handle (created on the current device): the
+ * library keeps no process-global state, and two handles can drive two streams / devices concurrently. */
+typedef struct glove_host_pipe glove_host_pipe;
+int glove_host_pipe_create(glove_host_pipe **out);
+int glove_host_pipe_destroy(glove_host_pipe *pipe);
+int glove_train_steps_host(glove_host_pipe *pipe, const glove_step_args *args, void *plan, void *prepare_ws, size_t prepare_ws_bytes,
                            void *staging, size_t staging_bytes, const int32_t *host_row, const int32_t *host_col,
                            const float *host_colA, const float *host_colB, int32_t K, float *host_losses,
                            void *stream);

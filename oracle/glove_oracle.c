@@ -10,7 +10,10 @@
  * Used only by tests/ (checker), and by bench.py's cpu_baseline / --impl reference legs (timed on host cores with
  * OpenMP over the dense Adam sweeps, which is where the reference's CPU time goes).  The product never links it.
  *
- * Build: see oracle/Makefile (gcc -O2 -ffp-contract=off -fopenmp -shared -fPIC).
+ * Build: see oracle/Makefile (gcc -O2 -ffp-contract=off -fopenmp -shared -fPIC).  The same source compiled with
+ * -DORACLE_F64 (libglove_oracle64.so) carries every variable and every operation in double: the fp64 SHADOW of the
+ * oracle, used by the parity tests to tell rounding noise of the fp32 oracle from errors of the CUDA path
+ * (hyper-parameters b1, b2, eps and the alpha table keep their fp32 VALUES, so both precisions solve the same problem).
  */
 #include <math.h>
 #include <stdint.h>
@@ -28,14 +31,32 @@
 #define ADAM_DENSE 0 /* legacy Keras: decay + apply on ALL rows every step */
 #define ADAM_LAZY 1  /* LazyAdam: touched rows only (not the reference; divergence measurement) */
 
-static const float B1 = 0.9f, B2 = 0.999f, EPS = 1e-7f;
+#ifdef ORACLE_F64
+typedef double real;
+#define RC(x) ((double)(x##f)) /* the fp32 VALUE of the constant, carried in double */
+#define R_SQRT sqrt
+#define R_FMAX fmax
+#define R_LOG1P log1p
+#define R_EXP exp
+#define R_FABS fabs
+#else
+typedef float real;
+#define RC(x) x##f
+#define R_SQRT sqrtf
+#define R_FMAX fmaxf
+#define R_LOG1P log1pf
+#define R_EXP expf
+#define R_FABS fabsf
+#endif
+
+static const real B1 = RC(0.9), B2 = RC(0.999), EPS = RC(1e-7);
 
 typedef struct {
     int32_t V, d;
-    float *R, *C, *rb, *cb; /* [V,d] [V,d] [V] [V] */
+    real *R, *C, *rb, *cb; /* [V,d] [V,d] [V] [V] */
     /* optimizer slots: Adam uses s0 = m, s1 = v; Adagrad uses s0 = accumulator; SGD none */
-    float *R_s0, *R_s1, *C_s0, *C_s1, *rb_s0, *rb_s1, *cb_s0, *cb_s1;
-    float g, g_s0, g_s1;
+    real *R_s0, *R_s1, *C_s0, *C_s1, *rb_s0, *rb_s1, *cb_s0, *cb_s1;
+    real g, g_s0, g_s1;
     int32_t step;
 } oracle_state;
 
@@ -47,71 +68,71 @@ int glove_oracle_num_threads(void) {
 #endif
 }
 
-static float softplusf_(float x) { return fmaxf(x, 0.0f) + log1pf(expf(-fabsf(x))); }
-static float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+static real softplusf_(real x) { return R_FMAX(x, RC(0.0)) + R_LOG1P(R_EXP(-R_FABS(x))); }
+static real sigmoidf_(real x) { return RC(1.0) / (RC(1.0) + R_EXP(-x)); }
 
 /* dense (all-rows) legacy Adam on one table of n elements, touched rows already scatter-added into m, v */
-static void adam_dense_table(float *x, float *m, float *v, int64_t rows, int64_t width, const int32_t *slot_of,
-                             const float *G, float alpha) {
-    const float omb1 = 1.0f - B1, omb2 = 1.0f - B2;
+static void adam_dense_table(real *x, real *m, real *v, int64_t rows, int64_t width, const int32_t *slot_of,
+                             const real *G, real alpha) {
+    const real omb1 = RC(1.0) - B1, omb2 = RC(1.0) - B2;
 #pragma omp parallel for schedule(static)
     for (int64_t r = 0; r < rows; ++r) {
-        float *xr = x + r * width, *mr = m + r * width, *vr = v + r * width;
+        real *xr = x + r * width, *mr = m + r * width, *vr = v + r * width;
         int32_t s = slot_of[r];
         if (s >= 0) {
-            const float *g = G + (int64_t)s * width;
+            const real *g = G + (int64_t)s * width;
             for (int64_t k = 0; k < width; ++k) {
-                float gk = g[k];
-                float mk = mr[k] * B1;
+                real gk = g[k];
+                real mk = mr[k] * B1;
                 mk = mk + gk * omb1;
-                float vk = vr[k] * B2;
+                real vk = vr[k] * B2;
                 vk = vk + (gk * gk) * omb2;
                 mr[k] = mk; vr[k] = vk;
-                xr[k] = xr[k] - (alpha * mk) / (sqrtf(vk) + EPS);
+                xr[k] = xr[k] - (alpha * mk) / (R_SQRT(vk) + EPS);
             }
         } else {
             for (int64_t k = 0; k < width; ++k) {
-                float mk = mr[k] * B1, vk = vr[k] * B2;
+                real mk = mr[k] * B1, vk = vr[k] * B2;
                 mr[k] = mk; vr[k] = vk;
-                xr[k] = xr[k] - (alpha * mk) / (sqrtf(vk) + EPS);
+                xr[k] = xr[k] - (alpha * mk) / (R_SQRT(vk) + EPS);
             }
         }
     }
 }
 
-static void adam_lazy_table(float *x, float *m, float *v, int64_t width, const int32_t *uniq, int32_t n_uniq,
-                            const float *G, float alpha) {
-    const float omb1 = 1.0f - B1, omb2 = 1.0f - B2;
+static void adam_lazy_table(real *x, real *m, real *v, int64_t width, const int32_t *uniq, int32_t n_uniq,
+                            const real *G, real alpha) {
+    const real omb1 = RC(1.0) - B1, omb2 = RC(1.0) - B2;
 #pragma omp parallel for schedule(static)
     for (int32_t s = 0; s < n_uniq; ++s) {
         int64_t r = uniq[s];
-        float *xr = x + r * width, *mr = m + r * width, *vr = v + r * width;
-        const float *g = G + (int64_t)s * width;
+        real *xr = x + r * width, *mr = m + r * width, *vr = v + r * width;
+        const real *g = G + (int64_t)s * width;
         for (int64_t k = 0; k < width; ++k) {
-            float gk = g[k];
-            float mk = mr[k] * B1 + gk * omb1;
-            float vk = vr[k] * B2 + (gk * gk) * omb2;
+            real gk = g[k];
+            real mk = mr[k] * B1 + gk * omb1;
+            real vk = vr[k] * B2 + (gk * gk) * omb2;
             mr[k] = mk; vr[k] = vk;
-            xr[k] = xr[k] - (alpha * mk) / (sqrtf(vk) + EPS);
+            xr[k] = xr[k] - (alpha * mk) / (R_SQRT(vk) + EPS);
         }
     }
 }
 
-static void adagrad_table(float *x, float *acc, int64_t width, const int32_t *uniq, int32_t n_uniq, const float *G,
-                          float lr) {
+static void adagrad_table(real *x, real *acc, int64_t width, const int32_t *uniq, int32_t n_uniq, const real *G,
+                          real lr) {
 #pragma omp parallel for schedule(static)
     for (int32_t s = 0; s < n_uniq; ++s) {
         int64_t r = uniq[s];
-        const float *g = G + (int64_t)s * width;
+        const real *g = G + (int64_t)s * width;
         for (int64_t k = 0; k < width; ++k) {
-            float a = acc[r * width + k] + g[k] * g[k];
+            real a = acc[r * width + k] + g[k] * g[k];
             acc[r * width + k] = a;
-            x[r * width + k] -= (lr * g[k]) / (sqrtf(a) + EPS);
+            x[r * width + k] -= (lr * g[k]) / (R_SQRT(a) + EPS);
         }
     }
 }
 
-static void sgd_table(float *x, int64_t width, const int32_t *uniq, int32_t n_uniq, const float *G, float lr) {
+static void sgd_table(real *x, int64_t width, const int32_t *uniq, int32_t n_uniq, const real *G, real lr) {
 #pragma omp parallel for schedule(static)
     for (int32_t s = 0; s < n_uniq; ++s) {
         int64_t r = uniq[s];
@@ -123,21 +144,21 @@ static void sgd_table(float *x, int64_t width, const int32_t *uniq, int32_t n_un
  * colA/colB = (glove_value, glove_weight) for the glove head, (value, neg_weight) for the logistic head.
  * alpha[step] is the fp32 Adam step-size table shared with the CUDA path.  losses[n_steps] receives the pre-update
  * loss of every step.  Returns 0, or -1 on allocation failure / bad arguments. */
-int glove_oracle_train(oracle_state *st, const int32_t *row, const int32_t *col, const float *colA,
-                       const float *colB, const int64_t *batch_idx, int32_t n_steps, int32_t B, int32_t head,
-                       int32_t optimizer, float lr, float l2, float reg_scale, float neg_factor, int32_t adam_mode,
-                       const float *alpha, float *losses) {
+int glove_oracle_train(oracle_state *st, const int32_t *row, const int32_t *col, const real *colA,
+                       const real *colB, const int64_t *batch_idx, int32_t n_steps, int32_t B, int32_t head,
+                       int32_t optimizer, real lr, real l2, real reg_scale, real neg_factor, int32_t adam_mode,
+                       const real *alpha, real *losses) {
     const int32_t V = st->V, d = st->d;
     if (B <= 0 || V <= 0 || d <= 0) return -1;
     int32_t *slot_r = (int32_t *)malloc(sizeof(int32_t) * V), *slot_c = (int32_t *)malloc(sizeof(int32_t) * V);
     int32_t *uniq_r = (int32_t *)malloc(sizeof(int32_t) * B), *uniq_c = (int32_t *)malloc(sizeof(int32_t) * B);
-    float *GR = (float *)malloc(sizeof(float) * (size_t)B * d), *GC = (float *)malloc(sizeof(float) * (size_t)B * d);
-    float *Grb = (float *)malloc(sizeof(float) * B), *Gcb = (float *)malloc(sizeof(float) * B);
-    float *e = (float *)malloc(sizeof(float) * B), *z = (float *)malloc(sizeof(float) * B);
+    real *GR = (real *)malloc(sizeof(real) * (size_t)B * d), *GC = (real *)malloc(sizeof(real) * (size_t)B * d);
+    real *Grb = (real *)malloc(sizeof(real) * B), *Gcb = (real *)malloc(sizeof(real) * B);
+    real *e = (real *)malloc(sizeof(real) * B), *z = (real *)malloc(sizeof(real) * B);
     if (!slot_r || !slot_c || !uniq_r || !uniq_c || !GR || !GC || !Grb || !Gcb || !e || !z) return -1;
     for (int32_t r = 0; r < V; ++r) slot_r[r] = slot_c[r] = -1;
-    const float fB = (float)B, fd = (float)d;
-    const float ce = (2.0f * reg_scale * l2) / (fd * fB), cb_ = (2.0f * reg_scale * l2) / fB;
+    const real fB = (real)B, fd = (real)d;
+    const real ce = (RC(2.0) * reg_scale * l2) / (fd * fB), cb_ = (RC(2.0) * reg_scale * l2) / fB;
 
     for (int32_t s = 0; s < n_steps; ++s) {
         const int64_t *idx = batch_idx + (int64_t)s * B;
@@ -146,40 +167,40 @@ int glove_oracle_train(oracle_state *st, const int32_t *row, const int32_t *col,
 #pragma omp parallel for schedule(static) reduction(+ : data, sq_r, sq_c, sq_rb, sq_cb)
         for (int32_t b = 0; b < B; ++b) {
             int64_t t = idx[b];
-            const float *Ri = st->R + (int64_t)row[t] * d, *Cj = st->C + (int64_t)col[t] * d;
-            float ep = 0.0f, nr = 0.0f, nc = 0.0f;
+            const real *Ri = st->R + (int64_t)row[t] * d, *Cj = st->C + (int64_t)col[t] * d;
+            real ep = RC(0.0), nr = RC(0.0), nc = RC(0.0);
             for (int32_t k = 0; k < d; ++k) { ep += Ri[k] * Cj[k]; nr += Ri[k] * Ri[k]; nc += Cj[k] * Cj[k]; }
-            float rbv = st->rb[row[t]], cbv = st->cb[col[t]];
-            float zb = ((ep + rbv) + cbv) + st->g;
+            real rbv = st->rb[row[t]], cbv = st->cb[col[t]];
+            real zb = ((ep + rbv) + cbv) + st->g;
             z[b] = zb;
             if (head == HEAD_GLOVE) {
-                float r_ = zb - colA[t];
+                real r_ = zb - colA[t];
                 data += (double)(colB[t] * r_ * r_);
-                e[b] = (2.0f / fB) * colB[t] * r_;
+                e[b] = (RC(2.0) / fB) * colB[t] * r_;
             } else {
-                float sg = sigmoidf_(zb);
+                real sg = sigmoidf_(zb);
                 data += (double)(colA[t] * softplusf_(-zb)) + (double)neg_factor * (double)(colB[t] * softplusf_(zb));
-                e[b] = (colA[t] * (sg - 1.0f) + neg_factor * colB[t] * sg) / fB;
+                e[b] = (colA[t] * (sg - RC(1.0)) + neg_factor * colB[t] * sg) / fB;
             }
             sq_r += nr; sq_c += nc; sq_rb += (double)(rbv * rbv); sq_cb += (double)(cbv * cbv);
         }
         double reg = (double)reg_scale * ((double)(l2 / fd) * sq_r / B + (double)(l2 / fd) * sq_c / B +
                                           (double)l2 * sq_rb / B + (double)l2 * sq_cb / B +
                                           (double)l2 * (double)st->g * (double)st->g);
-        losses[s] = (float)(data / B + reg);
+        losses[s] = (real)(data / B + reg);
 
         /* de-duplicated gradients, duplicates summed in batch order */
         int32_t n_r = 0, n_c = 0;
-        float se = 0.0f;
+        real se = RC(0.0);
         for (int32_t b = 0; b < B; ++b) {
             int64_t t = idx[b];
             int32_t i = row[t], j = col[t];
-            const float *Ri = st->R + (int64_t)i * d, *Cj = st->C + (int64_t)j * d;
+            const real *Ri = st->R + (int64_t)i * d, *Cj = st->C + (int64_t)j * d;
             int32_t sr = slot_r[i], sc = slot_c[j];
-            if (sr < 0) { sr = slot_r[i] = n_r; uniq_r[n_r++] = i; memset(GR + (int64_t)sr * d, 0, sizeof(float) * d); Grb[sr] = 0.0f; }
-            if (sc < 0) { sc = slot_c[j] = n_c; uniq_c[n_c++] = j; memset(GC + (int64_t)sc * d, 0, sizeof(float) * d); Gcb[sc] = 0.0f; }
-            float eb = e[b];
-            float *gr = GR + (int64_t)sr * d, *gc = GC + (int64_t)sc * d;
+            if (sr < 0) { sr = slot_r[i] = n_r; uniq_r[n_r++] = i; memset(GR + (int64_t)sr * d, 0, sizeof(real) * d); Grb[sr] = RC(0.0); }
+            if (sc < 0) { sc = slot_c[j] = n_c; uniq_c[n_c++] = j; memset(GC + (int64_t)sc * d, 0, sizeof(real) * d); Gcb[sc] = RC(0.0); }
+            real eb = e[b];
+            real *gr = GR + (int64_t)sr * d, *gc = GC + (int64_t)sc * d;
             for (int32_t k = 0; k < d; ++k) {
                 gr[k] += eb * Cj[k] + ce * Ri[k];
                 gc[k] += eb * Ri[k] + ce * Cj[k];
@@ -188,10 +209,10 @@ int glove_oracle_train(oracle_state *st, const int32_t *row, const int32_t *col,
             Gcb[sc] += eb + cb_ * st->cb[j];
             se += eb;
         }
-        float dg = se + (2.0f * reg_scale * l2) * st->g;
+        real dg = se + (RC(2.0) * reg_scale * l2) * st->g;
 
         if (optimizer == OPT_ADAM) {
-            float a = alpha[st->step];
+            real a = alpha[st->step];
             if (adam_mode == ADAM_DENSE) {
                 adam_dense_table(st->R, st->R_s0, st->R_s1, V, d, slot_r, GR, a);
                 adam_dense_table(st->C, st->C_s0, st->C_s1, V, d, slot_c, GC, a);
@@ -203,17 +224,17 @@ int glove_oracle_train(oracle_state *st, const int32_t *row, const int32_t *col,
                 adam_lazy_table(st->rb, st->rb_s0, st->rb_s1, 1, uniq_r, n_r, Grb, a);
                 adam_lazy_table(st->cb, st->cb_s0, st->cb_s1, 1, uniq_c, n_c, Gcb, a);
             }
-            float gm = st->g_s0 + (dg - st->g_s0) * (1.0f - B1);
-            float gv = st->g_s1 + (dg * dg - st->g_s1) * (1.0f - B2);
-            st->g = st->g - (a * gm) / (sqrtf(gv) + EPS);
+            real gm = st->g_s0 + (dg - st->g_s0) * (RC(1.0) - B1);
+            real gv = st->g_s1 + (dg * dg - st->g_s1) * (RC(1.0) - B2);
+            st->g = st->g - (a * gm) / (R_SQRT(gv) + EPS);
             st->g_s0 = gm; st->g_s1 = gv;
         } else if (optimizer == OPT_ADAGRAD) {
             adagrad_table(st->R, st->R_s0, d, uniq_r, n_r, GR, lr);
             adagrad_table(st->C, st->C_s0, d, uniq_c, n_c, GC, lr);
             adagrad_table(st->rb, st->rb_s0, 1, uniq_r, n_r, Grb, lr);
             adagrad_table(st->cb, st->cb_s0, 1, uniq_c, n_c, Gcb, lr);
-            float ga = st->g_s0 + dg * dg;
-            st->g = st->g - (lr * dg) / (sqrtf(ga) + EPS);
+            real ga = st->g_s0 + dg * dg;
+            st->g = st->g - (lr * dg) / (R_SQRT(ga) + EPS);
             st->g_s0 = ga;
         } else {
             sgd_table(st->R, d, uniq_r, n_r, GR, lr);

@@ -210,6 +210,58 @@ def _adam_untouched_step(x, m, v, alpha, b1, b2, eps):
     x -= ((alpha * m).astype(f32) / (np.sqrt(v).astype(f32) + eps)).astype(f32)
 
 
+def idle_run_sequential(x, m, v, alpha, ls: int, T: int, dtype=f32):
+    """The zero-gradient steps s = ls .. T-1 of legacy-Keras Adam on untouched elements, one after the other in
+    ``dtype`` (what the dense sweep of the reference does to a row between two touches).  Returns (x, m, v)."""
+    x, m, v = (np.array(a, dtype) for a in (x, m, v))
+    b1, b2, eps = dtype(f32(ADAM_BETA1)), dtype(f32(ADAM_BETA2)), dtype(f32(KERAS_EPSILON))
+    for s in range(ls, T):
+        _adam_untouched_step_t(x, m, v, dtype(alpha[s]), b1, b2, eps, dtype)
+    return x, m, v
+
+
+def _adam_untouched_step_t(x, m, v, alpha, b1, b2, eps, dtype):
+    m *= b1
+    v *= b2
+    x -= ((alpha * m).astype(dtype) / (np.sqrt(v).astype(dtype) + eps)).astype(dtype)
+
+
+REPLAY_WINDOW, REPLAY_TERMS = 192, 4
+
+
+def idle_run_closed_form(x, m, v, alpha, ls: int, T: int):
+    """fp32 restatement of the CUDA path's closed-form replay (csrc/glove_common.cuh: replay_coef / replay_x2), the
+    default ``adam_mode='replay'``:  with r = sqrt(v0), D = r + eps, q = r / D, u_j = 1 - b2^(j/2),
+        x_T = x_ls - (m0 / D) * sum_{k<4} q^k T_k,   T_k = sum_{j=1..min(gap,192)} alpha[ls+j-1] b1^j u_j^k,
+        m_T = b1^gap m0,  v_T = b2^gap v0.
+    Not part of the reference: it is the thing under test (against idle_run_sequential in fp64)."""
+    x, m, v = (np.array(a, f32) for a in (x, m, v))
+    gap = T - ls
+    if gap <= 0:
+        return x, m, v
+    b1, b2, eps = float(f32(ADAM_BETA1)), float(f32(ADAM_BETA2)), f32(KERAS_EPSILON)
+    n = min(gap, REPLAY_WINDOW)
+    j = np.arange(1, n + 1, dtype=np.float64)
+    pb1 = np.exp2(j * np.log2(b1)).astype(f32)
+    u = (-np.expm1(0.5 * j * np.log(b2))).astype(f32)
+    a = (np.asarray(alpha[ls:ls + n], f32) * pb1).astype(f32)
+    Tk = []
+    for _ in range(REPLAY_TERMS):
+        Tk.append(f32(np.sum(a, dtype=f32)))
+        a = (a * u).astype(f32)
+    r = np.sqrt(np.maximum(v, f32(1e-30))).astype(f32)
+    D = (r + eps).astype(f32)
+    inv = (f32(1) / D).astype(f32)
+    q = (r * inv).astype(f32)
+    poly = np.full_like(x, Tk[3])
+    for k in (2, 1, 0):
+        poly = (poly * q + Tk[k]).astype(f32)
+    x = (x - ((m * inv).astype(f32) * poly).astype(f32)).astype(f32)
+    dm = f32(np.exp2(np.float64(f32(gap * f32(np.log2(b1))))))
+    dv = f32(np.exp2(np.float64(f32(gap * f32(np.log2(b2))))))
+    return x, (m * dm).astype(f32), (v * dv).astype(f32)
+
+
 def apply_adam(st: State, grads, dg, alpha: np.float32, adam_mode: str = "keras_dense"):
     """Legacy tf.keras.optimizers.Adam._resource_apply_sparse (non-lazy): every step
         M <- b1 M (all rows); M[U] += (1-b1) G;  V <- b2 V (all rows); V[U] += (1-b2) G^2;

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(_lib.lib, n), "libglove_b200.so does not export %s" % n
         assert n in _lib.SIGNATURES, "_lib.SIGNATURES has no prototype for %s" % n
     assert sorted(_lib.SIGNATURES) == names
-    assert _lib.lib.glove_abi_version() == 1
+    assert _lib.lib.glove_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_struct_layouts_match_the_c_header():
@@ -43,6 +43,43 @@ def test_struct_layouts_match_the_c_header():
     assert int(out[1]) == ctypes.sizeof(_lib.GloveScalars) == 32
     for f, off in zip(fields, out[2:]):
         assert getattr(_lib.StepArgs, f).offset == int(off), f
+
+
+def test_integration_md_binding_stub_matches_the_header():
+    """The ctypes stub a maintainer would paste from INTEGRATION.md must describe the struct the library reads: same
+    fields in the same order, same size and offsets as the compiled header (round 1 shipped a stub 16 bytes short)."""
+    from glove_tensorflow_b200 import _lib
+    md = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    m = re.search(r"class StepArgs\(ctypes\.Structure\):.*?\n(    _fields_ = \[.*?\])\n", md, flags=re.S)
+    assert m, "INTEGRATION.md lost its StepArgs stub"
+    ns = dict(ctypes=ctypes, vp=ctypes.c_void_p, i32=ctypes.c_int32, i64=ctypes.c_int64, f32=ctypes.c_float,
+              u32=ctypes.c_uint32, sz=ctypes.c_size_t)
+    exec("class StepArgs(ctypes.Structure):\n" + m.group(1), ns)
+    Stub = ns["StepArgs"]
+    src = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    body = re.search(r"typedef struct glove_step_args \{(.*?)\} glove_step_args;", src, flags=re.S).group(1)
+    c_fields = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if decl:
+            c_fields += [n.strip().lstrip("*") for n in re.sub(r"^(const\s+)?\w+\s+", "", decl).split(",")]
+    assert [n for n, _ in Stub._fields_] == c_fields == [n for n, _ in _lib.StepArgs._fields_]
+    assert ctypes.sizeof(Stub) == ctypes.sizeof(_lib.StepArgs) == _lib.lib.glove_step_args_size()
+    for n, _ in Stub._fields_:
+        assert getattr(Stub, n).offset == getattr(_lib.StepArgs, n).offset, n   # _lib.StepArgs is checked against gcc above
+
+
+def test_stale_step_args_are_refused():
+    """struct_size guards every glove_step_args entry point: a binding compiled against another layout gets GLOVE_EINVAL
+    with a message, not a read past its struct."""
+    from glove_tensorflow_b200 import _lib
+    args = _lib.StepArgs()
+    args.struct_size = ctypes.sizeof(_lib.StepArgs) - 16          # round 1's stub
+    args.row_table = args.col_table = args.scalars = args.plan = args.workspace = 8   # non-null, never dereferenced
+    args.V, args.d, args.B, args.plan_K = 10, 4, 8, 1
+    args.optimizer = 2
+    assert _lib.lib.glove_train_step(ctypes.byref(args), None) == _lib.EINVAL
+    assert b"struct_size" in _lib.lib.glove_last_error()
 
 
 def test_size_queries_and_layout_helpers():

@@ -268,3 +268,63 @@ def test_host_vocabulary_tie_order_matches_the_oracle_restatement():
         a, b = cooc_oracle.vocabulary_frame(toks, vs, cov), text8.create_vocabulary(toks, vs, cov)
         assert list(a["token"]) == list(b["token"]) and list(a["count"]) == list(b["count"])
         np.testing.assert_allclose(a["proportion"], b["proportion"], rtol=1e-15)
+
+
+# ---- closed-form replay of idle Adam steps (the CUDA path's default adam_mode) vs the sequential recurrence -----------
+@pytest.mark.parametrize("scale_v", [1e-12, 1e-8, 1e-4, 1.0])
+@pytest.mark.parametrize("ls,gap", [(1, 1), (1, 5), (3, 40), (10, 200), (2000, 1), (2000, 17), (2000, 130), (2000, 1000),
+                                    (5, 3000)])
+def test_closed_form_replay_is_closer_to_fp64_than_the_fp32_recurrence(scale_v, ls, gap):
+    """x after a run of idle steps: |closed form (fp32) - sequential fp64| must not exceed the error of the sequential
+    fp32 recurrence (+ 2 ulp of x), for moments from the eps-dominated to the v-dominated regime."""
+    rng = np.random.default_rng(ls * 7919 + gap)
+    n = 2048
+    alpha = o.alpha_table(1e-3, ls + gap + 1)
+    x = rng.uniform(-.05, .05, n).astype(np.float32)
+    v = (rng.uniform(0.01, 1, n) * scale_v).astype(np.float32)
+    m = (rng.normal(0, 1, n) * np.sqrt(scale_v) * rng.uniform(0.05, 1, n)).astype(np.float32)
+    x64, m64, v64 = o.idle_run_sequential(x, m, v, alpha, ls, ls + gap, np.float64)
+    x32, m32, v32 = o.idle_run_sequential(x, m, v, alpha, ls, ls + gap, np.float32)
+    xc, mc, vc = o.idle_run_closed_form(x, m, v, alpha, ls, ls + gap)
+    err_c, err_s = np.max(np.abs(xc - x64)), np.max(np.abs(x32 - x64))
+    ulp = float(np.spacing(np.float32(np.max(np.abs(x64)))))
+    assert err_c <= err_s + 2 * ulp, (err_c, err_s, ulp)
+    assert err_c <= 1e-5 * np.max(np.abs(x64))            # far inside the north-star tolerance on its own
+    big = np.abs(m64) > 1e-30
+    if big.any():
+        assert np.max(np.abs(mc[big] - m64[big]) / np.abs(m64[big])) < 2e-6
+    assert np.max(np.abs(vc - v64) / np.abs(v64)) < 2e-6
+
+
+def test_closed_form_replay_zero_state_and_padding():
+    """never-updated elements (m = v = 0) and a zero gap are exact no-ops"""
+    alpha = o.alpha_table(1e-3, 64)
+    x = np.linspace(-0.05, 0.05, 16).astype(np.float32)
+    z = np.zeros_like(x)
+    xc, mc, vc = o.idle_run_closed_form(x, z, z, alpha, 3, 50)
+    assert np.array_equal(xc, x) and not mc.any() and not vc.any()
+    xc, mc, vc = o.idle_run_closed_form(x, x, np.abs(x), alpha, 7, 7)
+    assert np.array_equal(xc, x) and np.array_equal(mc, x)
+
+
+def test_fp64_shadow_of_the_c_oracle():
+    """libglove_oracle64.so is the same source in double: it must agree with the fp32 build to fp32 noise and with a
+    float64 NumPy evaluation of the first step's loss."""
+    from oracle import c_oracle
+    V, d, B, steps = 300, 16, 64, 25
+    coo = make_coo(V, 4 * B, 3)
+    batches = np.random.default_rng(4).integers(0, 4 * B, (steps, B))
+    st = o.init_state(V, d, 5)
+    c32 = c_oracle.COracle(st.R, st.C, st.rb, st.cb)
+    c64 = c_oracle.COracle(st.R, st.C, st.rb, st.cb, dtype=np.float64)
+    l32 = c32.train(coo, batches, learning_rate=0.01)
+    l64 = c64.train(coo, batches, learning_rate=0.01)
+    assert c64.R.dtype == np.float64 and l64.dtype == np.float64
+    assert np.max(np.abs(l32 - l64) / np.abs(l64)) < 2e-6
+    assert np.max(np.abs(c32.R - c64.R)) / np.max(np.abs(c64.R)) < 5e-5
+    b = {k: v[batches[0]] for k, v in coo.items()}
+    z = (np.sum(st.R[b["row"]].astype(np.float64) * st.C[b["col"]], -1) + st.rb[b["row"]] + st.cb[b["col"]])
+    data = np.sum(b["weight"].astype(np.float64) * (z - b["target"]) ** 2) / B
+    reg = 2.0 * (0.01 / d * (np.sum(st.R[b["row"]].astype(np.float64) ** 2) + np.sum(st.C[b["col"]].astype(np.float64) ** 2)) / B
+                 + 0.01 * (np.sum(st.rb[b["row"]].astype(np.float64) ** 2) + np.sum(st.cb[b["col"]].astype(np.float64) ** 2)) / B)
+    assert abs(l64[0] - (data + reg)) < 1e-6 * abs(l64[0])      # l2 = 0.01f, not 0.01: fp32-valued hyper-parameters

@@ -1,5 +1,6 @@
 """Parity of the CUDA TRAIN step (through the C ABI) against the CPU oracle on identical injected tables, batches and
-hyper-parameters.  Tolerance (north_star): per-step loss and updated embeddings within 1e-5 relative, fp32."""
+hyper-parameters.  Tolerance (north_star): per-step loss and updated embeddings within 1e-5 relative, fp32 -- judged
+against the fp64 shadow of the oracle (see _assert_close)."""
 import numpy as np
 import pytest
 
@@ -9,27 +10,62 @@ from oracle import glove_oracle as o
 pytestmark = pytest.mark.gpu
 
 RTOL = 1e-5
+SHADOW_C = 3.0          # the CUDA path may be at most this many times further from the fp64 shadow than the fp32 oracle is
+MAXIMA = {}             # test id -> observed maxima (written to gpurun_out/parity_maxima.json at session end)
 
 
 def _rel(a, b):
-    """max |a-b| / max |b|: error relative to the scale of the tensor.  (An element-wise relative error is not
-    meaningful here: Adam's m / (sqrt(v) + eps) turns the fp32 summation-order noise of a near-cancelling gradient sum
-    into an absolute step error ~ lr * 1e-7 * |terms| / eps-scale, which the oracle itself shows when the triples of a
-    batch are merely re-ordered -- see test_error_is_at_the_oracles_own_reordering_noise.)"""
+    """max |a-b| / max |b|: error relative to the scale of the tensor (an element-wise relative error is meaningless
+    next to zero-crossing embeddings)."""
     return float(np.max(np.abs(np.asarray(a, np.float64) - b)) / max(float(np.max(np.abs(b))), 1e-30))
 
 
+def _record(name, **kw):
+    MAXIMA.setdefault(name, {}).update({k: float(v) for k, v in kw.items()})
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _dump_maxima():
+    yield
+    import json, os
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, "parity_maxima.json"), "w") as f:
+        json.dump(MAXIMA, f, indent=1, sort_keys=True)
+
+
+def _c_mode(adam_mode):
+    return "lazy" if adam_mode == "lazy" else "keras_dense"
+
+
+def _shadow(st, coo, batches, *, optimizer, head, lr, reg_scale, adam_mode, neg_factor=0.7, l2_reg=0.01, both=True):
+    """fp32 C oracle and its fp64 shadow (same source, -DORACLE_F64) on the same injected problem."""
+    from oracle import c_oracle
+    out = []
+    for dt in ((np.float32, np.float64) if both else (np.float64,)):
+        c = c_oracle.COracle(st.R, st.C, st.rb, st.cb, g=float(st.g), optimizer=optimizer, dtype=dt)
+        l = c.train(coo, batches, head=head, learning_rate=lr, l2_reg=l2_reg, reg_scale=reg_scale, neg_factor=neg_factor,
+                    adam_mode=_c_mode(adam_mode))
+        out.append((c, l))
+    return out
+
+
 def _run_pair(V, d, B, steps, *, optimizer="Adam", head="glove", adam_mode="replay", K=4, seed=0, hot=None, lr=0.01,
-              reg_scale=2.0, n=None, zipf=True):
+              reg_scale=2.0, n=None, zipf=True, numpy_oracle=True):
     from glove_tensorflow_b200.engine import GloveEngine
     n = n or max(4 * B, 1000)
     coo = make_coo(V, n, seed, zipf=zipf, hot=hot)
     rng = np.random.default_rng(seed + 1)
     batches = rng.integers(0, n, (steps, B))
     st = o.init_state(V, d, seed + 2)
-    ref = st.copy()
-    ref_losses = o.train(ref, coo, batches, optimizer=optimizer, head=head, learning_rate=lr, reg_scale=reg_scale,
-                         adam_mode="lazy" if adam_mode == "lazy" else "keras_dense", neg_factor=0.7)
+    (c32, l32), (c64, l64) = _shadow(st, coo, batches, optimizer=optimizer, head=head, lr=lr, reg_scale=reg_scale,
+                                     adam_mode=adam_mode)
+    if numpy_oracle:        # the cited NumPy restatement (slow: small cases only); the C port is checked against it on the CPU
+        ref = st.copy()
+        ref_losses = np.array(o.train(ref, coo, batches, optimizer=optimizer, head=head, learning_rate=lr,
+                                      reg_scale=reg_scale, adam_mode=_c_mode(adam_mode), neg_factor=0.7))
+    else:
+        ref, ref_losses = c32, l32
     eng = GloveEngine(V, d, optimizer=optimizer, head=head, adam_mode=adam_mode, learning_rate=lr, reg_scale=reg_scale,
                       neg_factor=0.7, batch_size=B, plan_steps=K, max_steps=steps + 8)
     eng.load_state(st.R, st.C, st.rb, st.cb, st.g)
@@ -38,23 +74,29 @@ def _run_pair(V, d, B, steps, *, optimizer="Adam", head="glove", adam_mode="repl
     eng.set_batches(batches)
     losses = eng.train(steps)
     got = eng.get_state()
-    # the oracle's own fp32 summation-order noise on this exact problem: same batches, triples of each batch reversed
-    rev = st.copy()
-    o.train(rev, coo, batches[:, ::-1], optimizer=optimizer, head=head, learning_rate=lr, reg_scale=reg_scale,
-            adam_mode="lazy" if adam_mode == "lazy" else "keras_dense", neg_factor=0.7)
-    got["_noise"] = {k: _rel(getattr(rev, k), getattr(ref, k)) for k in ("R", "C", "rb", "cb")}
+    got["_o32"], got["_o64"], got["_l64"] = c32, c64, l64
     return ref, np.array(ref_losses), got, losses, eng
 
 
-def _assert_close(ref, ref_losses, got, losses):
+def _assert_close(ref, ref_losses, got, losses, name=None):
+    """north_star: per-step loss and updated tables within 1e-5 relative (fp32).  The tables are compared with the fp64
+    SHADOW of the oracle: the CUDA path must be within 1e-5 of it, or -- where fp32 rounding of the recurrence itself
+    exceeds that (Adam's m / (sqrt(v) + eps) amplifies the rounding of near-cancelling gradient sums) -- no more than
+    SHADOW_C times further from it than the fp32 oracle is.  Observed maxima go to gpurun_out/parity_maxima.json."""
+    import os
+    name = name or os.environ.get("PYTEST_CURRENT_TEST", "?").split("::")[-1].split(" ")[0]
     assert np.all(np.isfinite(losses))
-    assert float(np.max(np.abs(losses - ref_losses) / np.abs(ref_losses))) < RTOL, (losses[:4], ref_losses[:4])
+    e_loss = float(np.max(np.abs(losses - ref_losses) / np.abs(ref_losses)))
+    e_loss64 = float(np.max(np.abs(losses - got["_l64"]) / np.abs(got["_l64"])))
+    _record(name, loss_vs_oracle32=e_loss, loss_vs_shadow64=e_loss64)
+    assert e_loss < RTOL, (losses[:4], ref_losses[:4])
+    c32, c64 = got["_o32"], got["_o64"]
     for k in ("R", "C", "rb", "cb"):
-        # 1e-5 of the tensor scale, or -- where Adam makes the problem itself chaotic at that level -- a small multiple
-        # of the deviation the oracle shows against itself when only the summation order changes
-        tol = max(RTOL, 8 * got.get("_noise", {}).get(k, 0.0))
-        assert _rel(got[k], getattr(ref, k)) < tol, (k, _rel(got[k], getattr(ref, k)), tol)
-    assert abs(float(got["g"]) - float(ref.g)) <= RTOL * max(abs(float(ref.g)), 1e-3)
+        e_gpu, e_o32 = _rel(got[k], getattr(c64, k)), _rel(getattr(c32, k), getattr(c64, k))
+        _record(name, **{k + "_gpu_vs_shadow64": e_gpu, k + "_oracle32_vs_shadow64": e_o32,
+                         k + "_gpu_vs_oracle32": _rel(got[k], getattr(ref, k))})
+        assert e_gpu <= max(RTOL, SHADOW_C * e_o32), (k, e_gpu, e_o32)
+    assert abs(float(got["g"]) - float(c64.g)) <= RTOL * max(abs(float(c64.g)), 1e-3)
     assert got["step"] == ref.step
 
 
@@ -95,29 +137,35 @@ def test_lazy_mode_matches_lazy_oracle():
     _assert_close(ref, rl, got, l)
 
 
-def test_dense_mode_matches_oracle_and_replay_bit_exact():
-    """The replay schedule and the literal dense sweep must give bit-identical tables on the GPU."""
-    ref, rl, got_r, l_r, _ = _run_pair(3000, 24, 128, 60, adam_mode="replay", zipf=False, K=7)
+def test_dense_mode_matches_oracle_and_exact_replay_bit_exact():
+    """The step-by-step replay schedule and the literal dense sweep must give bit-identical tables on the GPU; the
+    closed-form replay (the default) must match the oracle like they do."""
+    ref, rl, got_r, l_r, _ = _run_pair(3000, 24, 128, 60, adam_mode="replay_exact", zipf=False, K=7)
     _, _, got_d, l_d, _ = _run_pair(3000, 24, 128, 60, adam_mode="dense", zipf=False, K=7)
-    _assert_close(ref, rl, got_d, l_d)
-    _assert_close(ref, rl, got_r, l_r)
+    _, _, got_c, l_c, _ = _run_pair(3000, 24, 128, 60, adam_mode="replay", zipf=False, K=7)
+    _assert_close(ref, rl, got_d, l_d, "dense_vs_exact/dense")
+    _assert_close(ref, rl, got_r, l_r, "dense_vs_exact/replay_exact")
+    _assert_close(ref, rl, got_c, l_c, "dense_vs_exact/replay_closed_form")
     for k in ("R", "C", "rb", "cb"):
         assert np.array_equal(got_r[k], got_d[k]), k
     assert np.array_equal(l_r, l_d)
 
 
-def test_error_is_at_the_oracles_own_reordering_noise():
-    """GPU-vs-oracle deviation must be of the order of the oracle's own deviation when each batch is merely reversed
-    (same sets, different fp32 summation order)."""
+def test_closed_form_replay_long_idle_gaps():
+    """Rows idle for hundreds of steps between two touches (uniform ids over a vocabulary much larger than the batch):
+    the closed-form replay must track the dense-sweep oracle through the whole drift of every row."""
+    ref, rl, got, l, _ = _run_pair(20000, 16, 64, 400, zipf=False, K=16, lr=0.001, numpy_oracle=False, seed=11)
+    _assert_close(ref, rl, got, l)
+
+
+def test_error_is_at_the_oracles_own_rounding_noise():
+    """The CUDA path must be no further from the fp64 shadow than the fp32 oracle is (x SHADOW_C), on a problem where
+    Adam amplifies fp32 rounding visibly (lr 0.01, heavy duplicates)."""
     V, d, B, steps, lr = 400, 32, 256, 40, 0.01
     ref, rl, got, l, _ = _run_pair(V, d, B, steps, lr=lr, seed=5)
-    coo = make_coo(V, max(4 * B, 1000), 5)
-    batches = np.random.default_rng(6).integers(0, max(4 * B, 1000), (steps, B))
-    rev = o.init_state(V, d, 7)
-    o.train(rev, coo, batches[:, ::-1], learning_rate=lr, neg_factor=0.7)
-    noise = float(np.max(np.abs(rev.R - ref.R)))
-    err = float(np.max(np.abs(got["R"] - ref.R)))
-    assert err <= 20 * noise + 1e-8, (err, noise)
+    e_gpu = _rel(got["R"], got["_o64"].R)
+    e_o32 = _rel(got["_o32"].R, got["_o64"].R)
+    assert e_gpu <= SHADOW_C * e_o32 + 1e-7, (e_gpu, e_o32)
     _assert_close(ref, rl, got, l)
 
 
@@ -201,15 +249,17 @@ def test_data_parallel_replicas_on_one_gpu(world, adam_mode, optimizer):
     assert np.max(np.abs(np.array(losses) - ref_losses) / np.abs(ref_losses)) < RTOL
 
 
-def test_overlap_streams_do_not_change_results():
-    """Catch-up on the side stream + plan prefetch vs everything on one stream: bit-identical tables and losses."""
+@pytest.mark.parametrize("adam_mode", ["replay", "replay_exact"])
+def test_overlap_streams_do_not_change_results(adam_mode):
+    """Plan prefetch (and, for the step-by-step replay, the catch-up on the side stream) vs everything on one stream:
+    bit-identical tables and losses."""
     from glove_tensorflow_b200.engine import GloveEngine
     V, d, B, steps, n = 5000, 64, 1024, 70, 60000
     coo = make_coo(V, n, 41)
     st = o.init_state(V, d, 42)
     out = []
     for overlap in (True, False):
-        eng = GloveEngine(V, d, learning_rate=0.01, batch_size=B, plan_steps=6, max_steps=steps + 8)
+        eng = GloveEngine(V, d, learning_rate=0.01, batch_size=B, plan_steps=6, max_steps=steps + 8, adam_mode=adam_mode)
         eng.overlap = overlap
         eng.load_state(st.R, st.C, st.rb, st.cb, st.g)
         eng.set_coo(coo["row"], coo["col"], coo["target"], coo["weight"], shuffle_key=3)
