@@ -298,6 +298,8 @@ def main():
     ap.add_argument("--cold-state", action="store_true", help="time from step 0 with empty Adam state")
     ap.add_argument("--emulate-state", action="store_true",
                     help="instead of really training %d steps first, start from a synthetic steady state (round-1 method)" % T0)
+    ap.add_argument("--pretrain-steps", type=int, default=T0,
+                    help="TRAIN steps run from the cold start before the timed region (default %d; profiling runs use fewer)" % T0)
     ap.add_argument("--no-topk", action="store_true", help="skip the cfg5 top-k record of the default N=1 run")
     ap.add_argument("--shard-exchange", default="peer", choices=["alltoall", "allgather", "peer", "peer-direct"],
                     help="N>1, row-sharded tables: how the snapshot rows reach the shards that need them (peer = one pull "
@@ -326,7 +328,7 @@ def main():
                 "l2_flush": "inputs larger than L2 (tables+slots %.1f GB, COO %.1f GB)"
                             % (2 * V * 3 * S_pad * 4 / 1e9, nnz * 16 / 1e9),
                 "state": ("cold" if args.cold_state else "steady-state emulation at step %d" % T0 if args.emulate_state
-                          else "trained %d steps from a cold start before the timed region" % T0)}
+                          else "trained %d steps from a cold start before the timed region" % args.pretrain_steps)}
 
     # ---- reference arm: CPU restatement of the reference TRAIN step on host cores -------------------------------
     if args.impl == "reference":
@@ -397,7 +399,7 @@ def main():
     elif not args.cold_state:
         # REAL state: T0 TRAIN steps from the cold start (every row the timed region touches then carries the last_step,
         # m, v a long run gives it; the idle gaps the stage has to replay are the workload's own)
-        for _ in range(T0):
+        for _ in range(args.pretrain_steps):
             eng.step()
     torch.cuda.synchronize()
 

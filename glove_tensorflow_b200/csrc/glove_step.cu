@@ -43,6 +43,9 @@ struct StepParams {
     double *warp_out;     // [kMaxWarps][3] per-warp sums of {data loss, sum e, reg term}
     int32_t *gap[2];      // [snapshot rows] closed-form replay: idle steps the staged row owed (0 = moments are current)
     float l2b1, l2b2;     // log2(beta1), log2(beta2) (host double, rounded once)
+    float invB, ce, cbias, reg_unscale;   // 1/B; 2 s l2/(d B); 2 s l2/B; B/(2 s): host-computed with the same fp32 operations
+    int32_t ablate;       // measurement only (GLOVE_ABLATE): 1 no table stores, 2 no L2 gathers, 4 no moment loads
+    int32_t l2_hints;     // 1: table traffic evict_first, snapshot traffic evict_last (GLOVE_L2_HINTS=0 disables)
     float *grad[2];       // MODE_GRAD / MODE_APPLY: dense per-slot gradient buffers
     float *grad_scalars;  // [4]
     const float *alpha;
@@ -110,6 +113,14 @@ __device__ __forceinline__ void load_row(float4 (&x)[NV], const float *row, int 
     }
 }
 template <int NV>
+__device__ __forceinline__ void load_row_hint(float4 (&x)[NV], const float *row, int lane, int S4, uint64_t pol) {
+#pragma unroll
+    for (int r = 0; r < NV; ++r) {
+        const int f = lane + 32 * r;
+        x[r] = (r < NV - 1 || f < S4) ? ld4_hint(row + 4 * f, pol) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+template <int NV>
 __device__ __forceinline__ void load_row_nc(float4 (&x)[NV], const float *row, int lane, int S4) {
 #pragma unroll
     for (int r = 0; r < NV; ++r) {
@@ -118,11 +129,13 @@ __device__ __forceinline__ void load_row_nc(float4 (&x)[NV], const float *row, i
     }
 }
 template <int NV>
-__device__ __forceinline__ void store_row(float *row, const float4 (&x)[NV], int lane, int S4) {
+__device__ __forceinline__ void store_row(float *row, const float4 (&x)[NV], int lane, int S4, uint64_t pol = 0) {
 #pragma unroll
     for (int r = 0; r < NV; ++r) {
         const int f = lane + 32 * r;
-        if (r < NV - 1 || f < S4) st4(row + 4 * f, x[r]);
+        if (r < NV - 1 || f < S4) {
+            if (pol) st4_hint(row + 4 * f, x[r], pol); else st4(row + 4 * f, x[r]);
+        }
     }
 }
 
@@ -311,6 +324,8 @@ __global__ void __launch_bounds__(256) stage_closed_kernel(const StepParams p) {
     const int64_t id0 = (int64_t)p.shard * p.v_loc;
     const int S4 = p.S >> 2;
     const int total = U0 + U1;
+    const uint64_t pol_stream = p.l2_hints ? l2_policy_evict_first() : l2_policy_evict_normal();
+    const uint64_t pol_keep = p.l2_hints ? l2_policy_evict_last() : l2_policy_evict_normal();
     auto row_of = [&](int w) -> const float * {
         const int s = w >= U0 ? 1 : 0;
         const int j = s ? w - U0 : w;
@@ -318,7 +333,7 @@ __global__ void __launch_bounds__(256) stage_closed_kernel(const StepParams p) {
     };
     float4 xn[NV];
     const float *row_n = nullptr;
-    if (warp < total) { row_n = row_of(warp); load_row<NV>(xn, row_n, lane, S4); }
+    if (warp < total) { row_n = row_of(warp); load_row_hint<NV>(xn, row_n, lane, S4, pol_stream); }
 #pragma unroll 1
     for (int w = warp; w < total; w += nwarps) {
         const int s = w >= U0 ? 1 : 0;
@@ -331,8 +346,8 @@ __global__ void __launch_bounds__(256) stage_closed_kernel(const StepParams p) {
         const int ls = __float_as_int(row_col<NV>(x, lcol, lane));
         const int gap = (ls > 0 && ls < step) ? step - ls : 0;
         float4 m[NV], v[NV];
-        if (gap) { load_row<NV>(m, row + p.S, lane, S4); load_row<NV>(v, row + 2 * p.S, lane, S4); }
-        if (w + nwarps < total) { row_n = row_of(w + nwarps); load_row<NV>(xn, row_n, lane, S4); }   // next row's plane 0
+        if (gap) { load_row_hint<NV>(m, row + p.S, lane, S4, pol_stream); load_row_hint<NV>(v, row + 2 * p.S, lane, S4, pol_stream); }
+        if (w + nwarps < total) { row_n = row_of(w + nwarps); load_row_hint<NV>(xn, row_n, lane, S4, pol_stream); }   // next row's plane 0
         if (gap) {
             const ReplayCoef c = replay_coef(tabs, p.alpha, ls, gap, p.l2b1, p.l2b2, lane);
 #pragma unroll
@@ -346,7 +361,7 @@ __global__ void __launch_bounds__(256) stage_closed_kernel(const StepParams p) {
                 if (4 * f + c == lcol) f4c(x[r], c) = 1.0f;     // 1.0 in the other side's bias column
         }
         const int pos = pos0[s] + j;
-        store_row<NV>(p.snap[s] + (int64_t)pos * p.S, x, lane, S4);
+        store_row<NV>(p.snap[s] + (int64_t)pos * p.S, x, lane, S4, pol_keep);
         if (lane == 0) p.gap[s][pos] = gap;
     }
 }
@@ -376,7 +391,8 @@ __global__ void __launch_bounds__(256) commit_ls_kernel(const StepParams p, int 
 // stage kernel has already decayed m, v through step-1, so the moments are read as-is.
 template <int NV>
 __device__ __forceinline__ void apply_row(const StepParams &p, float *row, float4 (&x)[NV], const float4 (&G)[NV],
-                                          float4 (&s1)[NV], float4 (&s2)[NV], int s, int step, int lane, int gap) {
+                                          float4 (&s1)[NV], float4 (&s2)[NV], int s, int step, int lane, int gap,
+                                          uint64_t store_pol = 0) {
     // s1 / s2 = optimizer slot planes 1 / 2 of the row, already loaded by the caller (prefetched at item start)
     // gap = idle steps the row owed when it was staged (closed-form replay: the moments in the table are `gap` steps old)
     const int S4 = p.S >> 2;
@@ -399,8 +415,8 @@ __device__ __forceinline__ void apply_row(const StepParams &p, float *row, float
             s1[r] = make_float4(ma.x, ma.y, mb.x, mb.y);
             s2[r] = make_float4(va.x, va.y, vb.x, vb.y);
         }
-        store_row<NV>(row + p.S, s1, lane, S4);
-        store_row<NV>(row + 2 * p.S, s2, lane, S4);
+        store_row<NV>(row + p.S, s1, lane, S4, store_pol);
+        store_row<NV>(row + 2 * p.S, s2, lane, S4, store_pol);
     } else if (p.opt == GLOVE_OPT_ADAGRAD) {
 #pragma unroll
         for (int r = 0; r < NV; ++r) {
@@ -411,7 +427,7 @@ __device__ __forceinline__ void apply_row(const StepParams &p, float *row, float
             x[r] = make_float4(xa.x, xa.y, xb.x, xb.y);
             s1[r] = make_float4(aa.x, aa.y, ab.x, ab.y);
         }
-        store_row<NV>(row + p.S, s1, lane, S4);
+        store_row<NV>(row + p.S, s1, lane, S4, store_pol);
     } else {
 #pragma unroll
         for (int r = 0; r < NV; ++r)
@@ -419,14 +435,15 @@ __device__ __forceinline__ void apply_row(const StepParams &p, float *row, float
             for (int c = 0; c < 4; ++c) sgd_update(f4c(x[r], c), f4v(G[r], c), p.lr);
     }
     const int lcol = ls_col(p.d, s);
+    const int lc = lcol & 3;
+    const float lsv = __int_as_float(step + 1);
 #pragma unroll
-    for (int r = 0; r < NV; ++r) {
-        const int f = lane + 32 * r;
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-            if (4 * f + c == lcol) f4c(x[r], c) = __int_as_float(step + 1);
-    }
-    store_row<NV>(row, x, lane, S4);
+    for (int r = 0; r < NV; ++r)
+        if (lane + 32 * r == (lcol >> 2)) {
+            x[r].x = lc == 0 ? lsv : x[r].x; x[r].y = lc == 1 ? lsv : x[r].y;
+            x[r].z = lc == 2 ? lsv : x[r].z; x[r].w = lc == 3 ? lsv : x[r].w;
+        }
+    store_row<NV>(row, x, lane, S4, store_pol);
 }
 
 // ---- end of step: loss, global bias, step counter --------------------------------------------------------------------------------------
@@ -487,18 +504,53 @@ __device__ __forceinline__ void axpy_row(float4 (&acc)[NV], float e, const float
     }
 }
 
+// activity-L2 of one row: acc_c <- [coef_c != 0] acc_c + n coef_c x_c and the lane's share of sum_c coef_c x_c^2,
+// coef = ce on the embedding columns, cbias on the bias column, 0 elsewhere (there acc holds the opposite bias that was
+// multiplied in, and is cleared).  A float4 chunk that lies wholly inside the embedding columns -- all but one chunk of
+// the row -- takes the packed path; only the chunk that straddles column d does the per-column select.
+template <int NV>
+__device__ __forceinline__ float activity_l2(float4 (&acc)[NV], const float4 (&x)[NV], float fn, float ce, float cbias, int d,
+                                             int bcol, int lane) {
+    float2 sq2 = make_float2(0.f, 0.f);
+    float sq = 0.0f;
+    const float2 ce2 = make_float2(ce, ce), fn2 = make_float2(fn, fn);
+#pragma unroll
+    for (int r = 0; r < NV; ++r) {
+        const int col0 = 4 * (lane + 32 * r);
+        if (col0 + 3 < d) {
+            const float2 xl = make_float2(x[r].x, x[r].y), xh = make_float2(x[r].z, x[r].w);
+            const float2 cl = __fmul2_rn(ce2, xl), ch = __fmul2_rn(ce2, xh);
+            const float2 al = __ffma2_rn(fn2, cl, make_float2(acc[r].x, acc[r].y));
+            const float2 ah = __ffma2_rn(fn2, ch, make_float2(acc[r].z, acc[r].w));
+            acc[r] = make_float4(al.x, al.y, ah.x, ah.y);
+            sq2 = __ffma2_rn(cl, xl, sq2);
+            sq2 = __ffma2_rn(ch, xh, sq2);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int col = col0 + c;
+                const float cf = col < d ? ce : (col == bcol ? cbias : 0.0f);
+                const float xv = f4v(x[r], c);
+                const float cx = cf * xv;
+                f4c(acc[r], c) = (cf != 0.0f ? f4c(acc[r], c) : 0.0f) + fn * cx;
+                sq += cx * xv;
+            }
+        }
+    }
+    return sq + (sq2.x + sq2.y);
+}
+
 constexpr int kChunk = 16;  // pieces per first-level combine of a split segment
 
-// acc = sum_{i < n} rows[i * stride_rows] in index order; 4 rows in flight (the caller lends 4 dead row buffers).
+// acc = sum_{i < n} rows[i * stride_rows] in index order; 3 rows in flight (the caller lends 3 dead row buffers).
 // L2-coherent loads (the rows were written by other SMs in this launch).
 template <int NV>
 __device__ __forceinline__ void sum_partials(float4 (&acc)[NV], const float *base, int n, int stride_rows, int S,
-                                             float4 (&b0)[NV], float4 (&b1)[NV], float4 (&b2)[NV], float4 (&b3)[NV],
-                                             int lane, int S4) {
+                                             float4 (&b0)[NV], float4 (&b1)[NV], float4 (&b2)[NV], int lane, int S4) {
 #pragma unroll
     for (int r = 0; r < NV; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
-    for (int q = 0; q < n; q += 4) {
+    for (int q = 0; q < n; q += 3) {
 #pragma unroll
         for (int r = 0; r < NV; ++r) {
             const int f = lane + 32 * r;
@@ -508,14 +560,12 @@ __device__ __forceinline__ void sum_partials(float4 (&acc)[NV], const float *bas
             b0[r] = in ? __ldcg(reinterpret_cast<const float4 *>(p0)) : z;
             b1[r] = (in && q + 1 < n) ? __ldcg(reinterpret_cast<const float4 *>(p0 + (int64_t)stride_rows * S)) : z;
             b2[r] = (in && q + 2 < n) ? __ldcg(reinterpret_cast<const float4 *>(p0 + 2 * (int64_t)stride_rows * S)) : z;
-            b3[r] = (in && q + 3 < n) ? __ldcg(reinterpret_cast<const float4 *>(p0 + 3 * (int64_t)stride_rows * S)) : z;
         }
 #pragma unroll
         for (int r = 0; r < NV; ++r) {
             acc[r].x += b0[r].x; acc[r].y += b0[r].y; acc[r].z += b0[r].z; acc[r].w += b0[r].w;
             acc[r].x += b1[r].x; acc[r].y += b1[r].y; acc[r].z += b1[r].z; acc[r].w += b1[r].w;
             acc[r].x += b2[r].x; acc[r].y += b2[r].y; acc[r].z += b2[r].z; acc[r].w += b2[r].w;
-            acc[r].x += b3[r].x; acc[r].y += b3[r].y; acc[r].z += b3[r].z; acc[r].w += b3[r].w;
         }
     }
 }
@@ -557,7 +607,7 @@ __global__ void __launch_bounds__(128, (NV <= 3 ? 4 : 3)) update_kernel(const St
                     buf[r] = (r < NV - 1 || f < S4) ? __ldcg(reinterpret_cast<const float4 *>(base + 4 * f)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             } else {
-                load_row_nc<NV>(buf, opp_base + (int64_t)pos * p.S, lane, S4);
+                load_row_nc<NV>(buf, opp_base + (int64_t)((p.ablate & 2) ? (pos & 63) : pos) * p.S, lane, S4);
             }
         };
         const int4 *rec = ps.rec;
@@ -576,8 +626,8 @@ __global__ void __launch_bounds__(128, (NV <= 3 ? 4 : 3)) update_kernel(const St
             load_row<NV>(x, p.snap[s] + (int64_t)slot * p.S, lane, S4);
             const bool applies = train && part == 0;
             const int gap_own = (applies && closed) ? __ldcg(p.gap[s] + slot) : 0;
-            if (applies && p.P >= 2) load_row<NV>(s1, row + p.S, lane, S4);
-            if (applies && p.P >= 3) load_row<NV>(s2, row + 2 * p.S, lane, S4);
+            if (applies && p.P >= 2 && !(p.ablate & 4)) load_row<NV>(s1, row + p.S, lane, S4);
+            if (applies && p.P >= 3 && !(p.ablate & 4)) load_row<NV>(s2, row + 2 * p.S, lane, S4);
             const int itn = itl + nwarps;
             const int4 ir_next = itn < nI ? __ldg(ps.item_rec + it0 + itn) : ir;
 #pragma unroll
@@ -657,7 +707,7 @@ __global__ void __launch_bounds__(128, (NV <= 3 ? 4 : 3)) update_kernel(const St
                 if (__shfl_sync(0xffffffffu, last, 0)) {
                     __threadfence();
                     if (lane == 0) p.chunk_cnt[s][c_first] = 0;
-                    sum_partials<NV>(acc, p.partial[s] + (int64_t)c_first * p.S, c_n, 1, p.S, bufA, bufB, x, s1, lane, S4);
+                    sum_partials<NV>(acc, p.partial[s] + (int64_t)c_first * p.S, c_n, 1, p.S, bufA, bufB, x, lane, S4);
                     const int n_chunks = (lr.w + kChunk - 1) / kChunk;
                     if (n_chunks > 1) store_row<NV>(p.partial[s] + (int64_t)c_first * p.S, acc, lane, S4);
                     __threadfence();
@@ -667,7 +717,7 @@ __global__ void __launch_bounds__(128, (NV <= 3 ? 4 : 3)) update_kernel(const St
                         __threadfence();
                         if (lane == 0) p.long_cnt[s][ir.x] = 0;     // ready for the next step
                         if (n_chunks > 1)
-                            sum_partials<NV>(acc, p.partial[s] + (int64_t)lr.z * p.S, n_chunks, kChunk, p.S, bufA, bufB, x, s1, lane, S4);
+                            sum_partials<NV>(acc, p.partial[s] + (int64_t)lr.z * p.S, n_chunks, kChunk, p.S, bufA, bufB, x, lane, S4);
                         if (!train) {
                             store_row<NV>(p.grad[s] + (int64_t)lr.y * p.S, acc, lane, S4);
                         } else {
@@ -682,7 +732,7 @@ __global__ void __launch_bounds__(128, (NV <= 3 ? 4 : 3)) update_kernel(const St
             } else if (!train) {
                 store_row<NV>(p.grad[s] + (int64_t)slot * p.S, acc, lane, S4);
             } else {
-                apply_row<NV>(p, row, x, acc, s1, s2, s, step, lane, gap_own);
+                apply_row<NV>(p, (p.ablate & 1) ? p.partial[s] + (int64_t)(warp & 63) * 3 * p.S : row, x, acc, s1, s2, s, step, lane, gap_own);
             }
             ir = ir_next;
             itl = itn;
@@ -692,6 +742,221 @@ __global__ void __launch_bounds__(128, (NV <= 3 ? 4 : 3)) update_kernel(const St
     __shared__ double sh_red[3][128];
     __shared__ int is_last;
     if (lane == 0) { p.warp_out[3 * warp] = w_ld; p.warp_out[3 * warp + 1] = w_se; p.warp_out[3 * warp + 2] = w_rg; }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(&p.sc->ticket, 1) == (int)gridDim.x - 1);
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        const int tid = threadIdx.x;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+        for (int w = tid; w < nwarps; w += 128) {
+            a0 += __ldcg(p.warp_out + 3 * w); a1 += __ldcg(p.warp_out + 3 * w + 1); a2 += __ldcg(p.warp_out + 3 * w + 2);
+        }
+        sh_red[0][tid] = a0; sh_red[1][tid] = a1; sh_red[2][tid] = a2;
+        __syncthreads();
+        for (int o = 64; o > 0; o >>= 1) {
+            if (tid < o) { sh_red[0][tid] += sh_red[0][tid + o]; sh_red[1][tid] += sh_red[1][tid + o]; sh_red[2][tid] += sh_red[2][tid + o]; }
+            __syncthreads();
+        }
+        if (tid == 0) finish_step(p, step, nullptr, sh_red[0][0], sh_red[1][0], sh_red[2][0]);
+    }
+}
+
+// ---- K2 with L1 prefetch across items (the default) -------------------------------------------------------------------
+// Same work split, arithmetic and summation order as update_kernel: bit-identical results.  ncu on update_kernel shows
+// the warps (16 / SM at 128 registers) stalled on three chains of dependent loads per item: item record -> triple records
+// -> gathered rows, and the optimizer planes, whose DRAM latency is longer than the ~1 us a typical item (2.7 triples)
+// lives.  Register double-buffering cannot go deeper at this register count, so the depth comes from the L1 instead
+// (prefetch.global.L1 holds no register and no shared memory): the triple records of item i+1 are fetched while item i
+// is gathered; before item i's epilogue every lane q prefetches the opposite row of triple q of item i+1 (all its
+// gathers at once), and the lanes together prefetch the snapshot row and the optimizer planes of item i+2.  The loads
+// proper then hit L1.  (The L1 is invalidated between launches, so the snapshot written by the stage is never stale.)
+template <int NV, int HEAD, bool DP>
+__global__ void __launch_bounds__(128, (NV <= 3 ? 4 : 3)) update_kernel3(const StepParams p) {
+    int k, step;
+    if (!batch_index(p, k, step)) return;
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int S4 = p.S >> 2;
+    const int row_bytes = p.S * 4;
+    const float gbias = p.sc->g;
+    const bool train = p.mode == MODE_TRAIN || p.mode == MODE_SHARD;
+    const bool closed = p.opt == GLOVE_OPT_ADAM && p.adam_mode == GLOVE_ADAM_REPLAY;
+    const int64_t id0 = (int64_t)p.shard * p.v_loc;
+    const uint64_t pol_keep = p.l2_hints ? l2_policy_evict_last() : l2_policy_evict_normal();
+    const uint64_t pol_stream = p.l2_hints ? l2_policy_evict_first() : l2_policy_evict_normal();
+    // this warp's share of the step's loss terms (fixed item order), kept in shared memory to save six registers
+    __shared__ double w_acc[4][3];
+    double *const wa = w_acc[threadIdx.x >> 5];
+    if (lane < 3) wa[lane] = 0.0;
+    __syncwarp();
+
+#pragma unroll 1
+    for (int s = 0; s < 2; ++s) {
+        const PlanSide &ps = p.side[s];
+        const int oi0 = p.mode == MODE_SHARD ? ps.b_own_item[k * (kMaxShards + 1) + p.shard] : 0;
+        const int4 *const irec = ps.item_rec + ps.b_item[k] + oi0;
+        const int nI = (p.mode == MODE_SHARD ? ps.b_own_item[k * (kMaxShards + 1) + p.shard + 1] : ps.b_item[k + 1] - ps.b_item[k]) - oi0;
+        const float *opp_base = p.snap[1 - s];
+        const float *own_base = p.snap[s];
+        const float *const *peer = p.peer_snap ? p.peer_snap + (1 - s) * kMaxShards : nullptr;
+        const int upad_opp = peer ? max(p.side[1 - s].b_upad[k], 1) : 1;
+        auto load_opp = [&](float4 (&buf)[NV], int pos) {
+            if (peer) {
+                const float *base = reinterpret_cast<const float *>(__ldg(reinterpret_cast<const unsigned long long *>(peer + pos / upad_opp))) + (int64_t)pos * p.S;
+#pragma unroll
+                for (int r = 0; r < NV; ++r) {
+                    const int f = lane + 32 * r;
+                    buf[r] = (r < NV - 1 || f < S4) ? __ldcg(reinterpret_cast<const float4 *>(base + 4 * f)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            } else {
+                const float *base = opp_base + (int64_t)pos * p.S;
+#pragma unroll
+                for (int r = 0; r < NV; ++r) {
+                    const int f = lane + 32 * r;
+                    buf[r] = (r < NV - 1 || f < S4) ? ld4(base + 4 * f) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        };
+        auto load_own = [&](float4 (&buf)[NV], int slot) {
+            const float *base = own_base + (int64_t)slot * p.S;
+#pragma unroll
+            for (int r = 0; r < NV; ++r) {
+                const int f = lane + 32 * r;
+                buf[r] = (r < NV - 1 || f < S4) ? ld4(base + 4 * f) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        const int4 *rec = ps.rec;
+        const int bcol = bias_col(p.d, s);
+        int itl = warp;
+        if (itl >= nI) continue;
+        // pipeline state: ir / myrec / x / bufA (first gather) of the CURRENT item are in registers when an iteration starts
+        int4 ir = __ldg(irec + itl);
+        int4 ir_next = itl + nwarps < nI ? __ldg(irec + itl + nwarps) : ir;
+        int4 myrec = lane < (ir.w & 0xff) ? __ldg(rec + ir.z + lane) : make_int4(0, 0, 0, 0);
+        float4 x[NV], acc[NV], bufA[NV], bufB[NV], s1[NV], s2[NV];
+        load_own(x, ir.y);
+        load_opp(bufA, __shfl_sync(0xffffffffu, myrec.x, 0));
+#pragma unroll 1
+        while (itl < nI) {
+            const int slot = ir.y, n = ir.w & 0xff, part = ir.w >> 8;
+            float *row = p.table[s] + (part ? 0 : (int64_t)ir.x - id0) * p.P * p.S;
+            const bool applies = train && part == 0;
+            const int gap_own = (applies && closed) ? __ldcg(p.gap[s] + slot) : 0;
+            if (applies && p.P >= 2) load_row<NV>(s1, row + p.S, lane, S4);
+            if (applies && p.P >= 3) load_row<NV>(s2, row + 2 * p.S, lane, S4);
+            const int itn = itl + nwarps, itnn = itn + nwarps;
+            const bool has_next = itn < nI;
+            const int4 ir_nn = itnn < nI ? __ldg(irec + itnn) : ir_next;
+            const int4 myrec_next = (has_next && lane < (ir_next.w & 0xff)) ? __ldg(rec + ir_next.z + lane) : make_int4(0, 0, 0, 0);
+#pragma unroll
+            for (int r = 0; r < NV; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+            float loss_d = 0.0f, sum_e = 0.0f;
+            int n_eff = 0;
+#pragma unroll 1
+            for (int q = 0; q < n; q += 2) {
+                const bool hasB = q + 1 < n;
+                if (hasB) load_opp(bufB, __shfl_sync(0xffffffffu, myrec.x, q + 1));
+                {
+                    const float a = __int_as_float(__shfl_sync(0xffffffffu, myrec.y, q));
+                    const float b = __int_as_float(__shfl_sync(0xffffffffu, myrec.z, q));
+                    float e, l;
+                    head_eval(HEAD, dot_row<NV>(x, bufA) + gbias, a, b, p.invB, p.nf, e, l);
+                    if (DP) {
+                        const bool mine = __shfl_sync(0xffffffffu, myrec.w, q) / p.dp_block == p.dp_rank;
+                        e = mine ? e : 0.f; l = mine ? l : 0.f; n_eff += mine;
+                    }
+                    loss_d += l; sum_e += e;
+                    axpy_row<NV>(acc, e, bufA);
+                }
+                if (hasB) {
+                    if (q + 2 < n) load_opp(bufA, __shfl_sync(0xffffffffu, myrec.x, q + 2));
+                    const float a = __int_as_float(__shfl_sync(0xffffffffu, myrec.y, q + 1));
+                    const float b = __int_as_float(__shfl_sync(0xffffffffu, myrec.z, q + 1));
+                    float e, l;
+                    head_eval(HEAD, dot_row<NV>(x, bufB) + gbias, a, b, p.invB, p.nf, e, l);
+                    if (DP) {
+                        const bool mine = __shfl_sync(0xffffffffu, myrec.w, q + 1) / p.dp_block == p.dp_rank;
+                        e = mine ? e : 0.f; l = mine ? l : 0.f; n_eff += mine;
+                    }
+                    loss_d += l; sum_e += e;
+                    axpy_row<NV>(acc, e, bufB);
+                }
+            }
+            if (!DP) n_eff = n;
+            const float fn = (float)n_eff;
+            const float sq = warp_sum(activity_l2<NV>(acc, x, fn, p.ce, p.cbias, p.d, bcol, lane));
+            if (lane == 0) {
+                if (s == 0) { wa[0] += (double)loss_d; wa[1] += (double)sum_e; }
+                wa[2] += (double)(fn * p.reg_unscale * sq);
+            }
+
+            // ---- prefetch into L1: every opposite row of item i+1 (lane q: the row of its triple q), and the snapshot row +
+            // optimizer planes of item i+2
+            if (has_next && !peer && lane < (ir_next.w & 0xff)) {
+                const char *r0 = reinterpret_cast<const char *>(opp_base + (int64_t)myrec_next.x * p.S);
+                for (int o = 0; o < row_bytes; o += 128) prefetch_l1(r0 + o);
+            }
+            if (itnn < nI) {
+                const char *xr = reinterpret_cast<const char *>(own_base + (int64_t)ir_nn.y * p.S);
+                if (128 * lane < row_bytes) prefetch_l1(xr + 128 * lane);
+                if (train && (ir_nn.w >> 8) == 0 && p.P >= 2) {
+                    const char *mv = reinterpret_cast<const char *>(p.table[s] + ((int64_t)ir_nn.x - id0) * p.P * p.S + p.S);
+                    if (128 * lane < (p.P - 1) * row_bytes) prefetch_l1(mv + 128 * lane);
+                }
+            }
+            if (part) {
+                store_row<NV>(p.partial[s] + (int64_t)(part - 1) * p.S, acc, lane, S4);
+                const int4 lr = __ldg(ps.long_rec + ps.b_long[k] + ir.x);   // {token id, slot, first partial, pieces}
+                const int piece = (part - 1) - lr.z, chunk = piece / kChunk;
+                const int c_first = lr.z + chunk * kChunk;
+                const int c_n = min(kChunk, lr.w - chunk * kChunk);
+                __threadfence();
+                int last = 0;
+                if (lane == 0) last = atomicAdd(p.chunk_cnt[s] + c_first, 1) == c_n - 1;
+                if (__shfl_sync(0xffffffffu, last, 0)) {
+                    __threadfence();
+                    if (lane == 0) p.chunk_cnt[s][c_first] = 0;
+                    sum_partials<NV>(acc, p.partial[s] + (int64_t)c_first * p.S, c_n, 1, p.S, bufA, bufB, x, lane, S4);
+                    const int n_chunks = (lr.w + kChunk - 1) / kChunk;
+                    if (n_chunks > 1) store_row<NV>(p.partial[s] + (int64_t)c_first * p.S, acc, lane, S4);
+                    __threadfence();
+                    last = 0;
+                    if (lane == 0) last = atomicAdd(p.long_cnt[s] + ir.x, 1) == n_chunks - 1;
+                    if (__shfl_sync(0xffffffffu, last, 0)) {
+                        __threadfence();
+                        if (lane == 0) p.long_cnt[s][ir.x] = 0;     // ready for the next step
+                        if (n_chunks > 1)
+                            sum_partials<NV>(acc, p.partial[s] + (int64_t)lr.z * p.S, n_chunks, kChunk, p.S, bufA, bufB, x, lane, S4);
+                        if (!train) {
+                            store_row<NV>(p.grad[s] + (int64_t)lr.y * p.S, acc, lane, S4);
+                        } else {
+                            float *lrow = p.table[s] + ((int64_t)lr.x - id0) * p.P * p.S;
+                            load_row<NV>(x, p.snap[s] + (int64_t)lr.y * p.S, lane, S4);
+                            if (p.P >= 2) load_row<NV>(s1, lrow + p.S, lane, S4);
+                            if (p.P >= 3) load_row<NV>(s2, lrow + 2 * p.S, lane, S4);
+                            apply_row<NV>(p, lrow, x, acc, s1, s2, s, step, lane, closed ? __ldcg(p.gap[s] + lr.y) : 0, pol_stream);
+                        }
+                    }
+                }
+            } else if (!train) {
+                store_row<NV>(p.grad[s] + (int64_t)slot * p.S, acc, lane, S4);
+            } else {
+                apply_row<NV>(p, row, x, acc, s1, s2, s, step, lane, gap_own, pol_stream);
+            }
+            ir = ir_next; ir_next = ir_nn; myrec = myrec_next;
+            itl = itn;
+            if (itl < nI) {
+                load_own(x, ir.y);
+                load_opp(bufA, __shfl_sync(0xffffffffu, myrec.x, 0));
+            }
+        }
+    }
+    // ---- end of step: per-warp loss terms -> last CTA (ticket) adds them in warp order and finishes the step
+    __shared__ double sh_red[3][128];
+    __shared__ int is_last;
+    if (lane == 0) { p.warp_out[3 * warp] = wa[0]; p.warp_out[3 * warp + 1] = wa[1]; p.warp_out[3 * warp + 2] = wa[2]; }
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) is_last = (atomicAdd(&p.sc->ticket, 1) == (int)gridDim.x - 1);
@@ -837,6 +1102,24 @@ __global__ void apply_finish_kernel(const StepParams p, const float *reduced) {
 }
 
 // ---- host side -------------------------------------------------------------------------------------------------------
+// measurement switches, read once from the environment (defaults = the shipped configuration)
+struct Tuning {
+    int l2_hints;        // GLOVE_L2_HINTS (default 1): L2 eviction-priority hints on table / snapshot traffic
+    int ablate;
+    int update_kernel;   // GLOVE_UPDATE_KERNEL (default 3): 3 = update_kernel3 (next item's records, first gather and own row
+                         // prefetched under the epilogue), 1 = update_kernel (round-1 structure)
+};
+static const Tuning &tuning() {
+    static const Tuning t = [] {
+        Tuning v{1, 0, 3};
+        if (const char *e = getenv("GLOVE_ABLATE")) v.ablate = atoi(e);
+        if (const char *e = getenv("GLOVE_L2_HINTS")) v.l2_hints = atoi(e) != 0;
+        if (const char *e = getenv("GLOVE_UPDATE_KERNEL")) v.update_kernel = atoi(e) == 1 ? 1 : 3;
+        return v;
+    }();
+    return t;
+}
+
 static int fill_params(const glove_step_args *a, StepParams &p, int mode) {
     GLOVE_REQUIRE(a, "step: null args");
     GLOVE_REQUIRE(a->row_table && a->col_table && a->scalars && a->plan && a->workspace, "step: null pointer in args");
@@ -864,6 +1147,8 @@ static int fill_params(const glove_step_args *a, StepParams &p, int mode) {
     p.warp_out = w.warp_out;
     p.gap[0] = w.gap[0]; p.gap[1] = w.gap[1];
     p.l2b1 = replay_log2(a->beta1); p.l2b2 = replay_log2(a->beta2);
+    p.l2_hints = tuning().l2_hints;
+    p.ablate = tuning().ablate;
     p.grad_scalars = nullptr;
     p.alpha = a->alpha; p.alpha_len = a->alpha_len;
     p.loss_out = a->loss_cap > 0 ? a->loss_out : nullptr; p.loss_cap = a->loss_cap > 0 ? a->loss_cap : 1;
@@ -871,6 +1156,10 @@ static int fill_params(const glove_step_args *a, StepParams &p, int mode) {
     p.head = a->head; p.opt = a->optimizer; p.adam_mode = a->adam_mode; p.mode = mode;
     p.lr = a->learning_rate; p.l2 = a->l2_reg; p.rs = a->reg_scale; p.nf = a->neg_factor;
     p.b1 = a->beta1; p.b2 = a->beta2; p.eps = a->epsilon;
+    p.invB = 1.0f / (float)p.B;
+    p.ce = (2.0f * p.rs * p.l2) / ((float)p.d * (float)p.B);
+    p.cbias = (2.0f * p.rs * p.l2) / (float)p.B;
+    p.reg_unscale = (float)p.B / (2.0f * p.rs);
     p.dp_world = mode == MODE_TRAIN ? 1 : (a->dp_world > 1 ? a->dp_world : 1);
     p.dp_rank = a->dp_rank;
     if (p.dp_world > 1) GLOVE_REQUIRE(a->B % p.dp_world == 0 && a->dp_rank >= 0 && a->dp_rank < p.dp_world, "step: bad dp split");
@@ -910,6 +1199,16 @@ static int launch_step(const StepParams &p, cudaStream_t stream, cudaEvent_t *ev
         if (ev) cudaEventRecord(ev[1], stream);
         const bool dp = p.dp_world > 1;
         if (!p.run_update) {
+        } else if (tuning().update_kernel == 3) {
+            static int g_update3 = 0;
+            if (!g_update3) g_update3 = occupancy_grid(update_kernel3<NV, GLOVE_HEAD_GLOVE, false>, 128);
+            if (p.head == GLOVE_HEAD_GLOVE) {
+                if (dp) update_kernel3<NV, GLOVE_HEAD_GLOVE, true><<<g_update3, 128, 0, stream>>>(p);
+                else update_kernel3<NV, GLOVE_HEAD_GLOVE, false><<<g_update3, 128, 0, stream>>>(p);
+            } else {
+                if (dp) update_kernel3<NV, GLOVE_HEAD_LOGISTIC, true><<<g_update3, 128, 0, stream>>>(p);
+                else update_kernel3<NV, GLOVE_HEAD_LOGISTIC, false><<<g_update3, 128, 0, stream>>>(p);
+            }
         } else if (p.head == GLOVE_HEAD_GLOVE) {
             if (dp) update_kernel<NV, GLOVE_HEAD_GLOVE, true><<<g_update, 128, 0, stream>>>(p);
             else update_kernel<NV, GLOVE_HEAD_GLOVE, false><<<g_update, 128, 0, stream>>>(p);

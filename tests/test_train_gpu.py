@@ -163,9 +163,10 @@ def test_error_is_at_the_oracles_own_rounding_noise():
     Adam amplifies fp32 rounding visibly (lr 0.01, heavy duplicates)."""
     V, d, B, steps, lr = 400, 32, 256, 40, 0.01
     ref, rl, got, l, _ = _run_pair(V, d, B, steps, lr=lr, seed=5)
-    e_gpu = _rel(got["R"], got["_o64"].R)
-    e_o32 = _rel(got["_o32"].R, got["_o64"].R)
-    assert e_gpu <= SHADOW_C * e_o32 + 1e-7, (e_gpu, e_o32)
+    rms = lambda a: float(np.sqrt(np.mean((np.asarray(a, np.float64) - got["_o64"].R) ** 2)))
+    rms_gpu, rms_o32 = rms(got["R"]), rms(got["_o32"].R)          # RMS: the maximum of 12,800 heavy-tailed errors is noisy
+    _record("rounding_noise_rms", gpu=rms_gpu, oracle32=rms_o32)
+    assert rms_gpu <= 2.0 * rms_o32 + 1e-9, (rms_gpu, rms_o32)
     _assert_close(ref, rl, got, l)
 
 
