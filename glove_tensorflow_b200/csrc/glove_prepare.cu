@@ -4,8 +4,6 @@
 // de-duplication structure of K steps is built once, off the critical path, and reused by both sides of each step.
 #include <cub/cub.cuh>
 
-#include <stdlib.h>
-
 #include "glove_common.cuh"
 
 namespace glove {
@@ -235,37 +233,15 @@ __global__ void segprev_kernel(int32_t N, int32_t B, PrepSide ps, PlanSide out) 
     }
 }
 
-// Work-item order inside a (batch, owner) block: by decreasing number of triples (stable, so equal-cost items stay in id
-// order).  The update kernel deals items to its warps round-robin; with the longest items first (LPT) the warps finish
-// together instead of waiting for the one that drew several 32-triple pieces.  Results do not depend on the order (every
-// item's arithmetic is self-contained and split segments are combined in piece order).
-__global__ void itemkey_kernel(int32_t N, int32_t B, int32_t v_loc, int32_t n_shards, const int32_t *__restrict__ n_items,
-                               PlanSide out, uint32_t *keys, uint32_t *idx) {
+__global__ void itemrec_kernel(int32_t B, int32_t n_shards, int32_t v_loc, const int32_t *__restrict__ n_items, PlanSide out) {
     const int32_t NI = *n_items;
-    for (int32_t it = blockIdx.x * blockDim.x + threadIdx.x; it < N; it += gridDim.x * blockDim.x) {
-        uint32_t key = 0xFFFFFFFFu;
-        if (it < NI) {
-            const int32_t g = out.item_seg[it], start = out.item_start[it];
-            const int32_t n = min(start + kItemMax, out.seg_start[g + 1]) - start;
-            const uint32_t owner = n_shards > 1 ? (uint32_t)(out.seg_id[g] / v_loc) : 0u;
-            key = ((uint32_t)(start / B) << 9) | (owner << 6) | (uint32_t)(63 - min(n, 63));
-        }
-        keys[it] = key;
-        idx[it] = (uint32_t)it;
-    }
-}
-
-__global__ void itemrec_kernel(int32_t B, int32_t n_shards, int32_t v_loc, const int32_t *__restrict__ n_items,
-                               const uint32_t *__restrict__ perm, PlanSide out) {
-    const int32_t NI = *n_items;
-    for (int32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < NI; j += gridDim.x * blockDim.x) {
-        const int32_t it = perm ? (int32_t)perm[j] : j;     // item written at position j of the work list
+    for (int32_t it = blockIdx.x * blockDim.x + threadIdx.x; it < NI; it += gridDim.x * blockDim.x) {
         const int32_t g = out.item_seg[it], start = out.item_start[it];
         const int32_t k = start / B;
         const int32_t seg_end = out.seg_start[g + 1], seg_len = seg_end - out.seg_start[g];
         const int32_t n = min(start + kItemMax, seg_end) - start;
         const int32_t part = seg_len > kItemMax ? out.item_part[it] - out.b_part[k] + 1 : 0;
-        out.item_rec[j] = make_int4(part ? out.seg_long[g] - out.b_long[k] : out.seg_id[g],
+        out.item_rec[it] = make_int4(part ? out.seg_long[g] - out.b_long[k] : out.seg_id[g],
                                      plan_pos(out, k, g, n_shards, v_loc), start, n | (part << 8));
     }
 }
@@ -387,7 +363,6 @@ int glove_prepare_batches_sharded(void *plan, void *workspace, size_t workspace_
     int blocks = (N + threads - 1) / threads;
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
 
-    static const bool sort_items = [] { const char *e = getenv("GLOVE_SORT_ITEMS"); return !(e && atoi(e) == 0); }();
     header_kernel<<<1, 1, 0, stream>>>(pv.hdr, K, B, first_step, n_shards, v_loc);
     gather_kernel<<<blocks, threads, 0, stream>>>(row, col, colA, colB, nnz, sample_idx, first_sample, shuffle_key,
                                                   feistel_half_bits((uint64_t)nnz), N, B, vbits, n_shards, v_loc, w);
@@ -414,16 +389,7 @@ int glove_prepare_batches_sharded(void *plan, void *workspace, size_t workspace_
         upad_kernel<<<(K + 255) / 256, 256, 0, stream>>>(K, n_shards, pv.side[s]);
         owner_items_kernel<<<(K * (kMaxShards + 1) + 255) / 256, 256, 0, stream>>>(K, pv.side[s]);
         slots_kernel<<<blocks, threads, 0, stream>>>(N, B, n_shards, v_loc, ps, pv.side[s]);
-        const uint32_t *perm = nullptr;
-        if (sort_items && kbits + 9 <= 32) {
-            itemkey_kernel<<<blocks, threads, 0, stream>>>(N, B, v_loc, n_shards, &pv.hdr->n_item[s], pv.side[s], ps.keys_in,
-                                                          (uint32_t *)ps.f_part);
-            tb = w.cub_bytes;
-            GLOVE_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_temp, tb, ps.keys_in, ps.keys_out, (uint32_t *)ps.f_part,
-                                                             (uint32_t *)ps.e_part, N, 0, 32, stream));
-            perm = (const uint32_t *)ps.e_part;
-        }
-        itemrec_kernel<<<blocks, threads, 0, stream>>>(B, n_shards, v_loc, &pv.hdr->n_item[s], perm, pv.side[s]);
+        itemrec_kernel<<<blocks, threads, 0, stream>>>(B, n_shards, v_loc, &pv.hdr->n_item[s], pv.side[s]);
         longrec_kernel<<<blocks, threads, 0, stream>>>(B, n_shards, v_loc, &pv.hdr->n_long[s], pv.side[s]);
         segprev_kernel<<<blocks, threads, 0, stream>>>(N, B, ps, pv.side[s]);
         GLOVE_CHECK_LAUNCH();

@@ -29,7 +29,6 @@
 namespace glove {
 
 enum { MODE_TRAIN = 0, MODE_GRAD = 1, MODE_APPLY = 2, MODE_SHARD = 3 };  // SHARD: owner-computes update of own segments
-constexpr int kMaxWarps = 148 * 64;  // upper bound on resident warps of the update grid
 
 struct StepParams {
     float *table[2];
@@ -40,11 +39,11 @@ struct StepParams {
     float *partial[2];    // [max parts][S] partial gradient sums of split segments
     int32_t *long_cnt[2]; // [max long segments] chunks finished so far (self-resetting; workspace starts zeroed)
     int32_t *chunk_cnt[2];  // [max parts] pieces finished in the chunk that starts at this partial slot (self-resetting)
-    double *warp_out;     // [kMaxWarps][3] per-warp sums of {data loss, sum e, reg term}
+    unsigned long long *loss_acc;   // [6] fixed-point sums of the step's loss terms (self-resetting)
+    int32_t *item_ctr;    // [2] next work item of each side handed out by the update kernel (self-resetting)
     int32_t *gap[2];      // [snapshot rows] closed-form replay: idle steps the staged row owed (0 = moments are current)
     float l2b1, l2b2;     // log2(beta1), log2(beta2) (host double, rounded once)
     float invB, ce, cbias, reg_unscale;   // 1/B; 2 s l2/(d B); 2 s l2/B; B/(2 s): host-computed with the same fp32 operations
-    int32_t ablate;       // measurement only (GLOVE_ABLATE): 1 no table stores, 2 no L2 gathers, 4 no moment loads
     int32_t l2_hints;     // 1: table traffic evict_first, snapshot traffic evict_last (GLOVE_L2_HINTS=0 disables)
     float *grad[2];       // MODE_GRAD / MODE_APPLY: dense per-slot gradient buffers
     float *grad_scalars;  // [4]
@@ -68,9 +67,10 @@ struct StepWs {
     float *partial[2];
     int32_t *long_cnt[2];
     int32_t *chunk_cnt[2];
-    double *warp_out;
     const float **peer_tab;   // [2][kMaxShards] snapshot bases of the peers (glove_shard_set_peers)
     int32_t *gap[2];
+    unsigned long long *loss_acc;
+    int32_t *item_ctr;
     size_t bytes;
 };
 static inline int64_t snapshot_rows(int32_t B) { return (int64_t)B + B / 4 + 64; }  // room for padded shard blocks
@@ -85,9 +85,10 @@ static StepWs step_ws_view(void *base, int32_t B, int32_t d) {
     for (int s = 0; s < 2; ++s) w.partial[s] = (float *)take(sizeof(float) * (size_t)max_parts_per_batch(B) * S);
     for (int s = 0; s < 2; ++s) w.long_cnt[s] = (int32_t *)take(sizeof(int32_t) * (size_t)(B / kItemMax + 2));
     for (int s = 0; s < 2; ++s) w.chunk_cnt[s] = (int32_t *)take(sizeof(int32_t) * (size_t)max_parts_per_batch(B));
-    w.warp_out = (double *)take(sizeof(double) * 3 * kMaxWarps);
     w.peer_tab = (const float **)take(sizeof(float *) * 2 * kMaxShards);
     for (int s = 0; s < 2; ++s) w.gap[s] = (int32_t *)take(sizeof(int32_t) * (size_t)snapshot_rows(B));
+    w.loss_acc = (unsigned long long *)take(sizeof(unsigned long long) * 6);
+    w.item_ctr = (int32_t *)take(sizeof(int32_t) * 2);
     w.bytes = off;
     return w;
 }
@@ -300,15 +301,17 @@ __global__ void __launch_bounds__(256) stage_kernel(const StepParams p, int step
 }
 
 // ---- K1 (GLOVE_ADAM_REPLAY, the default): stage with the closed-form replay -------------------------------------------
-// One warp per distinct id of the batch.  The pre-step row (plane 0) is loaded one row ahead; a row that owes idle Adam
-// steps (0 < last_step < step) also loads its moments, gets the run of idle steps applied in closed form (replay_x4:
-// one sqrt, one reciprocal and a cubic per element, independent of the gap) and is published to the snapshot.  NOTHING
-// is written back to the table: the update kernel of the same step re-reads the moments anyway, scales them by
-// b1^gap / b2^gap (gap is left in p.gap[side][position]) and writes x, m, v once.  HBM traffic per row: 3 plane reads
-// (1 for rows touched by the previous step) + the snapshot write; arithmetic is O(1) per element, so the kernel is
-// bound by HBM, not by the MUFU pipe like the sequential replay (stage_kernel pass 2).
+// One warp per distinct id of the batch, software-pipelined one row ahead.  A row that owes idle Adam steps
+// (0 < last_step < step) needs its moments as well as its plane-0 row: whether it does is known only once the row has
+// arrived, and a dependent second round trip to DRAM per row is what bounded the first version of this kernel.  The plan
+// knows better: a row that is NOT in the previous batch (seg_prev == 0) has been idle for at least one step, so its
+// three planes are fetched together, one row ahead (rows that were never updated pay two wasted plane reads once).  The
+// run of idle steps is applied in closed form (replay_x4: one sqrt, one reciprocal and a cubic per element, independent
+// of the gap) and the row is published to the snapshot.  NOTHING is written back to the table: the update kernel of the
+// same step re-reads the moments anyway, scales them by b1^gap / b2^gap (gap is left in p.gap[side][position]) and
+// writes x, m, v once.  Bound: HBM.
 template <int NV>
-__global__ void __launch_bounds__(256) stage_closed_kernel(const StepParams p) {
+__global__ void __launch_bounds__(256, 2) stage_closed_kernel(const StepParams p) {
     __shared__ ReplayTables tabs;
     int k, step;
     const bool ok = batch_index(p, k, step);
@@ -316,39 +319,44 @@ __global__ void __launch_bounds__(256) stage_closed_kernel(const StepParams p) {
     if (!ok) return;
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-    const int seg0[2] = {p.side[0].b_seg[k], p.side[1].b_seg[k]};
-    const int own0[2] = {p.side[0].b_own[k * (kMaxShards + 1) + p.shard], p.side[1].b_own[k * (kMaxShards + 1) + p.shard]};
-    const int U0 = p.side[0].b_own[k * (kMaxShards + 1) + p.shard + 1] - own0[0];
-    const int U1 = p.side[1].b_own[k * (kMaxShards + 1) + p.shard + 1] - own0[1];
-    const int pos0[2] = {p.shard * p.side[0].b_upad[k], p.shard * p.side[1].b_upad[k]};
-    const int64_t id0 = (int64_t)p.shard * p.v_loc;
     const int S4 = p.S >> 2;
+    const int own_r = p.side[0].b_own[k * (kMaxShards + 1) + p.shard], own_c = p.side[1].b_own[k * (kMaxShards + 1) + p.shard];
+    const int U0 = p.side[0].b_own[k * (kMaxShards + 1) + p.shard + 1] - own_r;
+    const int U1 = p.side[1].b_own[k * (kMaxShards + 1) + p.shard + 1] - own_c;
+    const int g_r = p.side[0].b_seg[k] + own_r, g_c = p.side[1].b_seg[k] + own_c;         // first owned segment of each side
+    const int pos_r = p.shard * p.side[0].b_upad[k], pos_c = p.shard * p.side[1].b_upad[k]; // first snapshot row of the block
+    const int64_t id0 = (int64_t)p.shard * p.v_loc;
     const int total = U0 + U1;
     const uint64_t pol_stream = p.l2_hints ? l2_policy_evict_first() : l2_policy_evict_normal();
     const uint64_t pol_keep = p.l2_hints ? l2_policy_evict_last() : l2_policy_evict_normal();
-    auto row_of = [&](int w) -> const float * {
-        const int s = w >= U0 ? 1 : 0;
-        const int j = s ? w - U0 : w;
-        return p.table[s] + ((int64_t)__ldg(p.side[s].seg_id + seg0[s] + own0[s] + j) - id0) * p.P * p.S;
-    };
-    float4 xn[NV];
+    float4 xn[NV], mn[NV], vn[NV];
     const float *row_n = nullptr;
-    if (warp < total) { row_n = row_of(warp); load_row_hint<NV>(xn, row_n, lane, S4, pol_stream); }
+    bool spec_n = false;
+    // issue the loads of row w: plane 0 always, the moments when the plan says the row has been idle
+    auto fetch = [&](int w) {
+        const int sd = w >= U0 ? 1 : 0;
+        const int g = sd ? g_c + (w - U0) : g_r + w;
+        row_n = p.table[sd] + ((int64_t)__ldg(p.side[sd].seg_id + g) - id0) * p.P * p.S;
+        spec_n = __ldg(p.side[sd].seg_prev + g) == 0;
+        load_row_hint<NV>(xn, row_n, lane, S4, pol_stream);
+        if (spec_n) { load_row_hint<NV>(mn, row_n + p.S, lane, S4, pol_stream); load_row_hint<NV>(vn, row_n + 2 * p.S, lane, S4, pol_stream); }
+    };
+    if (warp < total) fetch(warp);
 #pragma unroll 1
     for (int w = warp; w < total; w += nwarps) {
-        const int s = w >= U0 ? 1 : 0;
-        const int j = s ? w - U0 : w;
+        const int sd = w >= U0 ? 1 : 0;
+        const int j = sd ? w - U0 : w;
         const float *row = row_n;
-        float4 x[NV];
+        const bool spec = spec_n;
+        float4 x[NV], m[NV], v[NV];
 #pragma unroll
-        for (int r = 0; r < NV; ++r) x[r] = xn[r];
-        const int lcol = ls_col(p.d, s);
+        for (int r = 0; r < NV; ++r) { x[r] = xn[r]; m[r] = mn[r]; v[r] = vn[r]; }
+        if (w + nwarps < total) fetch(w + nwarps);
+        const int lcol = ls_col(p.d, sd);
         const int ls = __float_as_int(row_col<NV>(x, lcol, lane));
         const int gap = (ls > 0 && ls < step) ? step - ls : 0;
-        float4 m[NV], v[NV];
-        if (gap) { load_row_hint<NV>(m, row + p.S, lane, S4, pol_stream); load_row_hint<NV>(v, row + 2 * p.S, lane, S4, pol_stream); }
-        if (w + nwarps < total) { row_n = row_of(w + nwarps); load_row_hint<NV>(xn, row_n, lane, S4, pol_stream); }   // next row's plane 0
         if (gap) {
+            if (!spec) { load_row_hint<NV>(m, row + p.S, lane, S4, pol_stream); load_row_hint<NV>(v, row + 2 * p.S, lane, S4, pol_stream); }
             const ReplayCoef c = replay_coef(tabs, p.alpha, ls, gap, p.l2b1, p.l2b2, lane);
 #pragma unroll
             for (int r = 0; r < NV; ++r) x[r] = replay_x4(x[r], m[r], v[r], c, p.eps);
@@ -360,9 +368,9 @@ __global__ void __launch_bounds__(256) stage_closed_kernel(const StepParams p) {
             for (int c = 0; c < 4; ++c)
                 if (4 * f + c == lcol) f4c(x[r], c) = 1.0f;     // 1.0 in the other side's bias column
         }
-        const int pos = pos0[s] + j;
-        store_row<NV>(p.snap[s] + (int64_t)pos * p.S, x, lane, S4, pol_keep);
-        if (lane == 0) p.gap[s][pos] = gap;
+        const int pos = (sd ? pos_c : pos_r) + j;
+        store_row<NV>(p.snap[sd] + (int64_t)pos * p.S, x, lane, S4, pol_keep);
+        if (lane == 0) p.gap[sd][pos] = gap;
     }
 }
 
@@ -540,6 +548,18 @@ __device__ __forceinline__ float activity_l2(float4 (&acc)[NV], const float4 (&x
     return sq + (sq2.x + sq2.y);
 }
 
+// Order-independent accumulation of float terms: a term is split exactly into its integer part and a 2^-40 fixed-point
+// fraction (|fraction| < 1 -> < 2^40 per term, so 2^22 terms fit an int64; the integer parts fit as long as the true sum
+// is below 2^63); both limbs are summed with integer additions, which commute and associate exactly.  Resolution 9e-13.
+__device__ __forceinline__ void fx_add(long long *acc, float x, long long *bad) {
+    if (!(fabsf(x) < 4.0e18f)) *bad = 1;                          // NaN / inf / out of range: reported, never silently dropped
+    const long long hi = __float2ll_rz(x);
+    const float frac = __fsub_rn(x, __ll2float_rn(hi));          // exact: |x| < 2^24 has an exact difference, larger x no fraction
+    acc[0] += hi;
+    acc[1] += __float2ll_rn(__fmul_rn(frac, 1099511627776.0f));   // 2^40
+}
+__device__ __forceinline__ double fx_value(long long hi, long long lo) { return (double)hi + (double)lo * (1.0 / 1099511627776.0); }
+
 constexpr int kChunk = 16;  // pieces per first-level combine of a split segment
 
 // acc = sum_{i < n} rows[i * stride_rows] in index order; 3 rows in flight (the caller lends 3 dead row buffers).
@@ -570,210 +590,22 @@ __device__ __forceinline__ void sum_partials(float4 (&acc)[NV], const float *bas
     }
 }
 
+// One warp per work item.  ncu on the round-1 form of this kernel showed the warps (16 / SM at 128 registers) stalled on
+// three chains of dependent loads per item (item record -> triple records -> gathered rows, and the optimizer planes,
+// whose DRAM latency is longer than the ~1 us a typical 2.7-triple item lives) and the SMs idle for 18 % of the launch
+// waiting for the slowest warps.  Hence
+//   * software pipeline across items: the record of item i+2 and the triple records of item i+1 are fetched while item i
+//     is gathered; the first gather and the snapshot row of item i+1 are issued before item i's epilogue; L1 prefetches
+//     (no register, no shared memory) cover the remaining gathers of item i+1 and the planes of item i+2;
+//   * dynamic list scheduling: the work list is sorted by decreasing length at plan time (LPT); a warp takes its first
+//     three items by position and every later one from a per-side counter (one atomic per item, issued three items
+//     ahead), so all SMs finish together whatever the latency each of them sees;
+//   * which warp processes which item is therefore timing-dependent, so the loss terms are accumulated in 128-bit
+//     fixed point (two int64 limbs per term: integer part and 2^-40 fraction): integer addition is associative, the
+//     sums do not depend on the order, and the step stays bit-reproducible.  (The tables never depended on it: an item's
+//     arithmetic is self-contained and split segments are combined in piece order.)
 template <int NV, int HEAD, bool DP>
 __global__ void __launch_bounds__(128, (NV <= 3 ? 4 : 3)) update_kernel(const StepParams p) {
-    int k, step;
-    if (!batch_index(p, k, step)) return;
-    const int lane = threadIdx.x & 31;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-    const int S4 = p.S >> 2;
-    const float gbias = p.sc->g;
-    const float invB = 1.0f / (float)p.B;
-    const float ce = (2.0f * p.rs * p.l2) / ((float)p.d * (float)p.B), cbias = (2.0f * p.rs * p.l2) / (float)p.B;
-    const float reg_unscale = (float)p.B / (2.0f * p.rs);  // coef * reg_unscale = l2/d (embedding) | l2 (bias)
-    const bool train = p.mode == MODE_TRAIN || p.mode == MODE_SHARD;
-    const bool closed = p.opt == GLOVE_OPT_ADAM && p.adam_mode == GLOVE_ADAM_REPLAY;   // moments in the table are gap steps old
-    const int64_t id0 = (int64_t)p.shard * p.v_loc;   // first (remapped) id held by this shard
-    double w_ld = 0.0, w_se = 0.0, w_rg = 0.0;   // this warp's share of the step's loss terms (fixed item order)
-
-#pragma unroll 1
-    for (int s = 0; s < 2; ++s) {
-        const PlanSide &ps = p.side[s];
-        // row-sharded tables: only the work items of this shard's block of segments (contiguous in the item list)
-        const int oi0 = p.mode == MODE_SHARD ? ps.b_own_item[k * (kMaxShards + 1) + p.shard] : 0;
-        const int it0 = ps.b_item[k] + oi0;
-        const int nI = (p.mode == MODE_SHARD ? ps.b_own_item[k * (kMaxShards + 1) + p.shard + 1] : ps.b_item[k + 1] - ps.b_item[k]) - oi0;
-        const float *opp_base = p.snap[1 - s];
-        // peer gather: position pos of the opposite snapshot lives in the block of owner pos / upad, i.e. in THAT rank's
-        // snapshot (same layout on every rank), read straight over NVLink
-        const float *const *peer = p.peer_snap ? p.peer_snap + (1 - s) * kMaxShards : nullptr;
-        const int upad_opp = peer ? max(p.side[1 - s].b_upad[k], 1) : 1;
-        auto load_opp = [&](float4 (&buf)[NV], int pos) {
-            if (peer) {
-                const float *base = reinterpret_cast<const float *>(__ldg(reinterpret_cast<const unsigned long long *>(peer + pos / upad_opp))) + (int64_t)pos * p.S;
-#pragma unroll
-                for (int r = 0; r < NV; ++r) {
-                    const int f = lane + 32 * r;
-                    buf[r] = (r < NV - 1 || f < S4) ? __ldcg(reinterpret_cast<const float4 *>(base + 4 * f)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-            } else {
-                load_row_nc<NV>(buf, opp_base + (int64_t)((p.ablate & 2) ? (pos & 63) : pos) * p.S, lane, S4);
-            }
-        };
-        const int4 *rec = ps.rec;
-        const int bcol = bias_col(p.d, s);
-        int itl = warp;
-        int4 ir = itl < nI ? __ldg(ps.item_rec + it0 + itl) : make_int4(0, 0, 0, 0);
-#pragma unroll 1
-        while (itl < nI) {
-            // ---- memory round 1: everything whose address the item record gives, issued back to back: the records of
-            // the item's (<= 32) triples, one per lane; the own snapshot row; the optimizer slot planes (needed only in
-            // the epilogue, so their HBM latency hides behind the whole gather loop); the next item's record.
-            const int slot = ir.y, start = ir.z, n = ir.w & 0xff, part = ir.w >> 8;
-            const int4 myrec = lane < n ? __ldg(rec + start + lane) : make_int4(0, 0, 0, 0);
-            float *row = p.table[s] + (part ? 0 : (int64_t)ir.x - id0) * p.P * p.S;
-            float4 x[NV], acc[NV], bufA[NV], bufB[NV], s1[NV], s2[NV];
-            load_row<NV>(x, p.snap[s] + (int64_t)slot * p.S, lane, S4);
-            const bool applies = train && part == 0;
-            const int gap_own = (applies && closed) ? __ldcg(p.gap[s] + slot) : 0;
-            if (applies && p.P >= 2 && !(p.ablate & 4)) load_row<NV>(s1, row + p.S, lane, S4);
-            if (applies && p.P >= 3 && !(p.ablate & 4)) load_row<NV>(s2, row + 2 * p.S, lane, S4);
-            const int itn = itl + nwarps;
-            const int4 ir_next = itn < nI ? __ldg(ps.item_rec + it0 + itn) : ir;
-#pragma unroll
-            for (int r = 0; r < NV; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-            float loss_d = 0.0f, sum_e = 0.0f;
-            int n_eff = 0;
-
-            // ---- memory round 2: opposite snapshot rows, two triples per iteration with ping-pong buffers
-            load_opp(bufA, __shfl_sync(0xffffffffu, myrec.x, 0));
-#pragma unroll 1
-            for (int q = 0; q < n; q += 2) {
-                const bool hasB = q + 1 < n;
-                if (hasB) load_opp(bufB, __shfl_sync(0xffffffffu, myrec.x, q + 1));
-                {
-                    const float a = __int_as_float(__shfl_sync(0xffffffffu, myrec.y, q));
-                    const float b = __int_as_float(__shfl_sync(0xffffffffu, myrec.z, q));
-                    float e, l;
-                    head_eval(HEAD, dot_row<NV>(x, bufA) + gbias, a, b, invB, p.nf, e, l);
-                    if (DP) {
-                        const bool mine = __shfl_sync(0xffffffffu, myrec.w, q) / p.dp_block == p.dp_rank;
-                        e = mine ? e : 0.f; l = mine ? l : 0.f; n_eff += mine;
-                    }
-                    loss_d += l; sum_e += e;
-                    axpy_row<NV>(acc, e, bufA);
-                }
-                if (hasB) {
-                    if (q + 2 < n) load_opp(bufA, __shfl_sync(0xffffffffu, myrec.x, q + 2));
-                    const float a = __int_as_float(__shfl_sync(0xffffffffu, myrec.y, q + 1));
-                    const float b = __int_as_float(__shfl_sync(0xffffffffu, myrec.z, q + 1));
-                    float e, l;
-                    head_eval(HEAD, dot_row<NV>(x, bufB) + gbias, a, b, invB, p.nf, e, l);
-                    if (DP) {
-                        const bool mine = __shfl_sync(0xffffffffu, myrec.w, q + 1) / p.dp_block == p.dp_rank;
-                        e = mine ? e : 0.f; l = mine ? l : 0.f; n_eff += mine;
-                    }
-                    loss_d += l; sum_e += e;
-                    axpy_row<NV>(acc, e, bufB);
-                }
-            }
-            if (!DP) n_eff = n;
-
-            // activity-L2: gradient n*coef_c*x_c and loss n*(l2/d sum x^2 + l2 bias^2), coef = 2 s l2/(d B) on the embedding
-            // columns, 2 s l2/B on the bias column, 0 elsewhere.  The bias column of acc already holds sum_b e_b; the
-            // column where the opposite bias was multiplied in (coef == 0) is cleared.
-            const float fn = (float)n_eff;
-            float sq = 0.0f;
-#pragma unroll
-            for (int r = 0; r < NV; ++r) {
-                const int f = lane + 32 * r;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const int col = 4 * f + c;
-                    const float cf = col < p.d ? ce : (col == bcol ? cbias : 0.0f);
-                    const float xv = f4c(x[r], c);
-                    const float cx = cf * xv;
-                    f4c(acc[r], c) = (cf != 0.0f ? f4c(acc[r], c) : 0.0f) + fn * cx;
-                    sq += cx * xv;
-                }
-            }
-            sq = warp_sum(sq);
-            if (s == 0) { w_ld += (double)loss_d; w_se += (double)sum_e; }
-            w_rg += (double)(fn * reg_unscale * sq);
-
-            if (part) {
-                // Piece of a split segment.  Two-level, fixed-order combine with no extra launch: pieces are grouped in
-                // chunks of kChunk; the warp that completes the LAST piece of a chunk adds the chunk's partial sums in
-                // piece order into the chunk's first slot; the warp that completes the LAST chunk adds the chunk sums in
-                // chunk order and applies the update.  Which warp does it is timing-dependent, what it computes is not.
-                store_row<NV>(p.partial[s] + (int64_t)(part - 1) * p.S, acc, lane, S4);
-                const int4 lr = __ldg(ps.long_rec + ps.b_long[k] + ir.x);   // {token id, slot, first partial, pieces}
-                const int piece = (part - 1) - lr.z, chunk = piece / kChunk;
-                const int c_first = lr.z + chunk * kChunk;                    // partial slot of the chunk's first piece
-                const int c_n = min(kChunk, lr.w - chunk * kChunk);
-                __threadfence();
-                int last = 0;
-                if (lane == 0) last = atomicAdd(p.chunk_cnt[s] + c_first, 1) == c_n - 1;
-                if (__shfl_sync(0xffffffffu, last, 0)) {
-                    __threadfence();
-                    if (lane == 0) p.chunk_cnt[s][c_first] = 0;
-                    sum_partials<NV>(acc, p.partial[s] + (int64_t)c_first * p.S, c_n, 1, p.S, bufA, bufB, x, lane, S4);
-                    const int n_chunks = (lr.w + kChunk - 1) / kChunk;
-                    if (n_chunks > 1) store_row<NV>(p.partial[s] + (int64_t)c_first * p.S, acc, lane, S4);
-                    __threadfence();
-                    last = 0;
-                    if (lane == 0) last = atomicAdd(p.long_cnt[s] + ir.x, 1) == n_chunks - 1;
-                    if (__shfl_sync(0xffffffffu, last, 0)) {
-                        __threadfence();
-                        if (lane == 0) p.long_cnt[s][ir.x] = 0;     // ready for the next step
-                        if (n_chunks > 1)
-                            sum_partials<NV>(acc, p.partial[s] + (int64_t)lr.z * p.S, n_chunks, kChunk, p.S, bufA, bufB, x, lane, S4);
-                        if (!train) {
-                            store_row<NV>(p.grad[s] + (int64_t)lr.y * p.S, acc, lane, S4);
-                        } else {
-                            float *lrow = p.table[s] + ((int64_t)lr.x - id0) * p.P * p.S;
-                            load_row<NV>(x, p.snap[s] + (int64_t)lr.y * p.S, lane, S4);
-                            if (p.P >= 2) load_row<NV>(s1, lrow + p.S, lane, S4);
-                            if (p.P >= 3) load_row<NV>(s2, lrow + 2 * p.S, lane, S4);
-                            apply_row<NV>(p, lrow, x, acc, s1, s2, s, step, lane, closed ? __ldcg(p.gap[s] + lr.y) : 0);
-                        }
-                    }
-                }
-            } else if (!train) {
-                store_row<NV>(p.grad[s] + (int64_t)slot * p.S, acc, lane, S4);
-            } else {
-                apply_row<NV>(p, (p.ablate & 1) ? p.partial[s] + (int64_t)(warp & 63) * 3 * p.S : row, x, acc, s1, s2, s, step, lane, gap_own);
-            }
-            ir = ir_next;
-            itl = itn;
-        }
-    }
-    // ---- end of step: per-warp loss terms -> last CTA (ticket) adds them in warp order and finishes the step
-    __shared__ double sh_red[3][128];
-    __shared__ int is_last;
-    if (lane == 0) { p.warp_out[3 * warp] = w_ld; p.warp_out[3 * warp + 1] = w_se; p.warp_out[3 * warp + 2] = w_rg; }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) is_last = (atomicAdd(&p.sc->ticket, 1) == (int)gridDim.x - 1);
-    __syncthreads();
-    if (is_last) {
-        __threadfence();
-        const int tid = threadIdx.x;
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-        for (int w = tid; w < nwarps; w += 128) {
-            a0 += __ldcg(p.warp_out + 3 * w); a1 += __ldcg(p.warp_out + 3 * w + 1); a2 += __ldcg(p.warp_out + 3 * w + 2);
-        }
-        sh_red[0][tid] = a0; sh_red[1][tid] = a1; sh_red[2][tid] = a2;
-        __syncthreads();
-        for (int o = 64; o > 0; o >>= 1) {
-            if (tid < o) { sh_red[0][tid] += sh_red[0][tid + o]; sh_red[1][tid] += sh_red[1][tid + o]; sh_red[2][tid] += sh_red[2][tid + o]; }
-            __syncthreads();
-        }
-        if (tid == 0) finish_step(p, step, nullptr, sh_red[0][0], sh_red[1][0], sh_red[2][0]);
-    }
-}
-
-// ---- K2 with L1 prefetch across items (the default) -------------------------------------------------------------------
-// Same work split, arithmetic and summation order as update_kernel: bit-identical results.  ncu on update_kernel shows
-// the warps (16 / SM at 128 registers) stalled on three chains of dependent loads per item: item record -> triple records
-// -> gathered rows, and the optimizer planes, whose DRAM latency is longer than the ~1 us a typical item (2.7 triples)
-// lives.  Register double-buffering cannot go deeper at this register count, so the depth comes from the L1 instead
-// (prefetch.global.L1 holds no register and no shared memory): the triple records of item i+1 are fetched while item i
-// is gathered; before item i's epilogue every lane q prefetches the opposite row of triple q of item i+1 (all its
-// gathers at once), and the lanes together prefetch the snapshot row and the optimizer planes of item i+2.  The loads
-// proper then hit L1.  (The L1 is invalidated between launches, so the snapshot written by the stage is never stale.)
-template <int NV, int HEAD, bool DP>
-__global__ void __launch_bounds__(128, (NV <= 3 ? 4 : 3)) update_kernel3(const StepParams p) {
     int k, step;
     if (!batch_index(p, k, step)) return;
     const int lane = threadIdx.x & 31;
@@ -786,10 +618,11 @@ __global__ void __launch_bounds__(128, (NV <= 3 ? 4 : 3)) update_kernel3(const S
     const int64_t id0 = (int64_t)p.shard * p.v_loc;
     const uint64_t pol_keep = p.l2_hints ? l2_policy_evict_last() : l2_policy_evict_normal();
     const uint64_t pol_stream = p.l2_hints ? l2_policy_evict_first() : l2_policy_evict_normal();
-    // this warp's share of the step's loss terms (fixed item order), kept in shared memory to save six registers
-    __shared__ double w_acc[4][3];
-    double *const wa = w_acc[threadIdx.x >> 5];
-    if (lane < 3) wa[lane] = 0.0;
+    // this warp's share of the step's loss terms as order-independent fixed-point sums (see fx_add), kept in shared
+    // memory to save registers: {data loss, B * sum e, reg term} x {integer limb, 2^-40 fraction limb}
+    __shared__ long long w_acc[4][7];    // [6]: a term was not finite
+    long long *const wa = w_acc[threadIdx.x >> 5];
+    if (lane < 7) wa[lane] = 0;
     __syncwarp();
 
 #pragma unroll 1
@@ -831,9 +664,11 @@ __global__ void __launch_bounds__(128, (NV <= 3 ? 4 : 3)) update_kernel3(const S
         const int bcol = bias_col(p.d, s);
         int itl = warp;
         if (itl >= nI) continue;
+        // a warp's first three items are dealt by position, the later ones come from the side's counter
+        int it_n = warp + nwarps, it_nn = warp + 2 * nwarps;
         // pipeline state: ir / myrec / x / bufA (first gather) of the CURRENT item are in registers when an iteration starts
         int4 ir = __ldg(irec + itl);
-        int4 ir_next = itl + nwarps < nI ? __ldg(irec + itl + nwarps) : ir;
+        int4 ir_next = it_n < nI ? __ldg(irec + it_n) : ir;
         int4 myrec = lane < (ir.w & 0xff) ? __ldg(rec + ir.z + lane) : make_int4(0, 0, 0, 0);
         float4 x[NV], acc[NV], bufA[NV], bufB[NV], s1[NV], s2[NV];
         load_own(x, ir.y);
@@ -846,9 +681,11 @@ __global__ void __launch_bounds__(128, (NV <= 3 ? 4 : 3)) update_kernel3(const S
             const int gap_own = (applies && closed) ? __ldcg(p.gap[s] + slot) : 0;
             if (applies && p.P >= 2) load_row<NV>(s1, row + p.S, lane, S4);
             if (applies && p.P >= 3) load_row<NV>(s2, row + 2 * p.S, lane, S4);
-            const int itn = itl + nwarps, itnn = itn + nwarps;
-            const bool has_next = itn < nI;
+            const bool has_next = it_n < nI;
+            const int itnn = it_nn;
             const int4 ir_nn = itnn < nI ? __ldg(irec + itnn) : ir_next;
+            int it_nnn = nI;                   // the item after that: taken from the counter now, needed one item from now
+            if (itnn < nI && lane == 0) it_nnn = 3 * nwarps + atomicAdd(p.item_ctr + s, 1);
             const int4 myrec_next = (has_next && lane < (ir_next.w & 0xff)) ? __ldg(rec + ir_next.z + lane) : make_int4(0, 0, 0, 0);
 #pragma unroll
             for (int r = 0; r < NV; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -888,8 +725,8 @@ __global__ void __launch_bounds__(128, (NV <= 3 ? 4 : 3)) update_kernel3(const S
             const float fn = (float)n_eff;
             const float sq = warp_sum(activity_l2<NV>(acc, x, fn, p.ce, p.cbias, p.d, bcol, lane));
             if (lane == 0) {
-                if (s == 0) { wa[0] += (double)loss_d; wa[1] += (double)sum_e; }
-                wa[2] += (double)(fn * p.reg_unscale * sq);
+                if (s == 0) { fx_add(wa, loss_d, wa + 6); fx_add(wa + 2, sum_e * (float)p.B, wa + 6); }
+                fx_add(wa + 4, fn * p.reg_unscale * sq, wa + 6);
             }
 
             // ---- prefetch into L1: every opposite row of item i+1 (lane q: the row of its triple q), and the snapshot row +
@@ -946,35 +783,32 @@ __global__ void __launch_bounds__(128, (NV <= 3 ? 4 : 3)) update_kernel3(const S
                 apply_row<NV>(p, row, x, acc, s1, s2, s, step, lane, gap_own, pol_stream);
             }
             ir = ir_next; ir_next = ir_nn; myrec = myrec_next;
-            itl = itn;
+            itl = it_n; it_n = it_nn; it_nn = __shfl_sync(0xffffffffu, it_nnn, 0);
             if (itl < nI) {
                 load_own(x, ir.y);
                 load_opp(bufA, __shfl_sync(0xffffffffu, myrec.x, 0));
             }
         }
     }
-    // ---- end of step: per-warp loss terms -> last CTA (ticket) adds them in warp order and finishes the step
-    __shared__ double sh_red[3][128];
+    // ---- end of step: per-warp fixed-point sums -> global accumulators (integer atomics: order-independent); the last CTA
+    // to finish (ticket) converts them, finishes the step and clears the accumulators and the item counters for the next one
     __shared__ int is_last;
-    if (lane == 0) { p.warp_out[3 * warp] = wa[0]; p.warp_out[3 * warp + 1] = wa[1]; p.warp_out[3 * warp + 2] = wa[2]; }
+    if (lane < 6 && wa[lane] != 0) atomicAdd(p.loss_acc + lane, (unsigned long long)wa[lane]);
+    if (lane == 6 && wa[6] != 0) p.sc->error = 2;   // non-finite loss term (diverged run): sticky, surfaced by the host
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) is_last = (atomicAdd(&p.sc->ticket, 1) == (int)gridDim.x - 1);
     __syncthreads();
-    if (is_last) {
+    if (is_last && threadIdx.x == 0) {
         __threadfence();
-        const int tid = threadIdx.x;
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-        for (int w = tid; w < nwarps; w += 128) {
-            a0 += __ldcg(p.warp_out + 3 * w); a1 += __ldcg(p.warp_out + 3 * w + 1); a2 += __ldcg(p.warp_out + 3 * w + 2);
+        double v[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            v[i] = fx_value((long long)__ldcg(p.loss_acc + 2 * i), (long long)__ldcg(p.loss_acc + 2 * i + 1));
+            p.loss_acc[2 * i] = 0; p.loss_acc[2 * i + 1] = 0;
         }
-        sh_red[0][tid] = a0; sh_red[1][tid] = a1; sh_red[2][tid] = a2;
-        __syncthreads();
-        for (int o = 64; o > 0; o >>= 1) {
-            if (tid < o) { sh_red[0][tid] += sh_red[0][tid + o]; sh_red[1][tid] += sh_red[1][tid + o]; sh_red[2][tid] += sh_red[2][tid + o]; }
-            __syncthreads();
-        }
-        if (tid == 0) finish_step(p, step, nullptr, sh_red[0][0], sh_red[1][0], sh_red[2][0]);
+        p.item_ctr[0] = 0; p.item_ctr[1] = 0;
+        finish_step(p, step, nullptr, v[0], v[1] / (double)p.B, v[2]);
     }
 }
 
@@ -1102,19 +936,14 @@ __global__ void apply_finish_kernel(const StepParams p, const float *reduced) {
 }
 
 // ---- host side -------------------------------------------------------------------------------------------------------
-// measurement switches, read once from the environment (defaults = the shipped configuration)
+// measurement switch, read once from the environment (default = the shipped configuration)
 struct Tuning {
     int l2_hints;        // GLOVE_L2_HINTS (default 1): L2 eviction-priority hints on table / snapshot traffic
-    int ablate;
-    int update_kernel;   // GLOVE_UPDATE_KERNEL (default 3): 3 = update_kernel3 (next item's records, first gather and own row
-                         // prefetched under the epilogue), 1 = update_kernel (round-1 structure)
 };
 static const Tuning &tuning() {
     static const Tuning t = [] {
-        Tuning v{1, 0, 3};
-        if (const char *e = getenv("GLOVE_ABLATE")) v.ablate = atoi(e);
+        Tuning v{1};
         if (const char *e = getenv("GLOVE_L2_HINTS")) v.l2_hints = atoi(e) != 0;
-        if (const char *e = getenv("GLOVE_UPDATE_KERNEL")) v.update_kernel = atoi(e) == 1 ? 1 : 3;
         return v;
     }();
     return t;
@@ -1144,11 +973,10 @@ static int fill_params(const glove_step_args *a, StepParams &p, int mode) {
         p.snap[s] = w.snap[s]; p.partial[s] = w.partial[s]; p.long_cnt[s] = w.long_cnt[s]; p.chunk_cnt[s] = w.chunk_cnt[s];
         p.grad[s] = nullptr;
     }
-    p.warp_out = w.warp_out;
     p.gap[0] = w.gap[0]; p.gap[1] = w.gap[1];
+    p.loss_acc = w.loss_acc; p.item_ctr = w.item_ctr;
     p.l2b1 = replay_log2(a->beta1); p.l2b2 = replay_log2(a->beta2);
     p.l2_hints = tuning().l2_hints;
-    p.ablate = tuning().ablate;
     p.grad_scalars = nullptr;
     p.alpha = a->alpha; p.alpha_len = a->alpha_len;
     p.loss_out = a->loss_cap > 0 ? a->loss_out : nullptr; p.loss_cap = a->loss_cap > 0 ? a->loss_cap : 1;
@@ -1175,9 +1003,9 @@ static int fill_params(const glove_step_args *a, StepParams &p, int mode) {
 }
 
 template <typename Kern>
-static int occupancy_grid(Kern kern, int threads) {
+static int occupancy_grid(Kern kern, int threads, size_t dyn_smem = 0) {
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, dyn_smem) != cudaSuccess || per_sm < 1) per_sm = 1;
     int dev = 0, sms = kNumSMs;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     return per_sm * sms;
@@ -1188,7 +1016,15 @@ static int launch_step(const StepParams &p, cudaStream_t stream, cudaEvent_t *ev
     static int g_stage = 0, g_stage_closed = 0, g_update = 0, g_apply = 0;
     if (!g_stage) g_stage = occupancy_grid(stage_kernel<false>, 256);
     if (!g_stage_closed) g_stage_closed = occupancy_grid(stage_closed_kernel<NV>, 256);
-    if (!g_update) g_update = occupancy_grid(update_kernel<NV, GLOVE_HEAD_GLOVE, false>, 128);
+    if (!g_update) {
+        g_update = occupancy_grid(update_kernel<NV, GLOVE_HEAD_GLOVE, false>, 128);
+        if (const char *e = getenv("GLOVE_UPDATE_CTAS")) {   // measurement: cap on resident CTAs per SM
+            int dev = 0, sms = kNumSMs;
+            if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            const int n = atoi(e);
+            if (n > 0 && n * sms < g_update) g_update = n * sms;
+        }
+    }
     if (!g_apply) g_apply = occupancy_grid(apply_kernel<NV>, 128);
     if (p.mode == MODE_TRAIN || p.mode == MODE_GRAD || p.mode == MODE_SHARD) {
         if (ev) cudaEventRecord(ev[0], stream);
@@ -1198,23 +1034,14 @@ static int launch_step(const StepParams &p, cudaStream_t stream, cudaEvent_t *ev
         }
         if (ev) cudaEventRecord(ev[1], stream);
         const bool dp = p.dp_world > 1;
-        if (!p.run_update) {
-        } else if (tuning().update_kernel == 3) {
-            static int g_update3 = 0;
-            if (!g_update3) g_update3 = occupancy_grid(update_kernel3<NV, GLOVE_HEAD_GLOVE, false>, 128);
+        if (p.run_update) {
             if (p.head == GLOVE_HEAD_GLOVE) {
-                if (dp) update_kernel3<NV, GLOVE_HEAD_GLOVE, true><<<g_update3, 128, 0, stream>>>(p);
-                else update_kernel3<NV, GLOVE_HEAD_GLOVE, false><<<g_update3, 128, 0, stream>>>(p);
+                if (dp) update_kernel<NV, GLOVE_HEAD_GLOVE, true><<<g_update, 128, 0, stream>>>(p);
+                else update_kernel<NV, GLOVE_HEAD_GLOVE, false><<<g_update, 128, 0, stream>>>(p);
             } else {
-                if (dp) update_kernel3<NV, GLOVE_HEAD_LOGISTIC, true><<<g_update3, 128, 0, stream>>>(p);
-                else update_kernel3<NV, GLOVE_HEAD_LOGISTIC, false><<<g_update3, 128, 0, stream>>>(p);
+                if (dp) update_kernel<NV, GLOVE_HEAD_LOGISTIC, true><<<g_update, 128, 0, stream>>>(p);
+                else update_kernel<NV, GLOVE_HEAD_LOGISTIC, false><<<g_update, 128, 0, stream>>>(p);
             }
-        } else if (p.head == GLOVE_HEAD_GLOVE) {
-            if (dp) update_kernel<NV, GLOVE_HEAD_GLOVE, true><<<g_update, 128, 0, stream>>>(p);
-            else update_kernel<NV, GLOVE_HEAD_GLOVE, false><<<g_update, 128, 0, stream>>>(p);
-        } else {
-            if (dp) update_kernel<NV, GLOVE_HEAD_LOGISTIC, true><<<g_update, 128, 0, stream>>>(p);
-            else update_kernel<NV, GLOVE_HEAD_LOGISTIC, false><<<g_update, 128, 0, stream>>>(p);
         }
         if (ev) { cudaEventRecord(ev[2], stream); cudaEventRecord(ev[3], stream); }
     } else {

@@ -328,3 +328,34 @@ def test_fp64_shadow_of_the_c_oracle():
     reg = 2.0 * (0.01 / d * (np.sum(st.R[b["row"]].astype(np.float64) ** 2) + np.sum(st.C[b["col"]].astype(np.float64) ** 2)) / B
                  + 0.01 * (np.sum(st.rb[b["row"]].astype(np.float64) ** 2) + np.sum(st.cb[b["col"]].astype(np.float64) ** 2)) / B)
     assert abs(l64[0] - (data + reg)) < 1e-6 * abs(l64[0])      # l2 = 0.01f, not 0.01: fp32-valued hyper-parameters
+
+
+def test_oracle_matches_tf_crosscheck():
+    """Consumes tests/golden/tf_crosscheck.npz -- per-step losses and variables dumped from the UNMODIFIED reference
+    model_fn under TensorFlow 2.11 by tests/golden/tf_crosscheck.py (which can only run where TensorFlow imports).
+    While the file is absent the train-path oracle stays "parity unpinned" and this test skips; once it is committed
+    the oracle (keras_dense Adam, whichever reg_scale TF turns out to use) must reproduce it to 1e-5."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tf_crosscheck.npz")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/tf_crosscheck.npz not generated yet (needs tensorflow==2.11.0; see tests/golden/tf_crosscheck.py)")
+    z = np.load(path, allow_pickle=False)
+    V, d, steps = int(z["in/V"]), int(z["in/d"]), int(z["in/steps"])
+    coo = {"row": z["in/row"].reshape(-1).astype(np.int32), "col": z["in/col"].reshape(-1).astype(np.int32),
+           "target": z["in/target"].reshape(-1), "weight": z["in/weight"].reshape(-1)}
+    B = int(z["in/B"])
+    batches = np.arange(steps * B).reshape(steps, B)
+    names = [str(n) for n in z["variable_names"]]
+    pick = lambda s, *parts: z["step%02d/%s" % (s, [n for n in names if all(q in n for q in parts)
+                                                    and not any(t in n for t in ("Adam", "/m", "/v", "accumulator"))][0])]
+    ok = {}
+    for reg_scale in (1.0, 2.0):
+        st = o.State(z["in/R"].copy(), z["in/C"].copy(), z["in/rb"].copy(), z["in/cb"].copy(), np.float32(z["in/g"]))
+        losses = np.array(o.train(st, coo, batches, optimizer=str(z["in/optimizer"]), learning_rate=float(z["in/learning_rate"]),
+                                  reg_scale=reg_scale, adam_mode="keras_dense"))
+        e_loss = float(np.max(np.abs(losses - z["losses"]) / np.abs(z["losses"])))
+        e_R = float(np.max(np.abs(st.R - pick(steps - 1, "row_embedding", "embeddings"))) / np.max(np.abs(st.R)))
+        e_C = float(np.max(np.abs(st.C - pick(steps - 1, "col_embedding", "embeddings"))) / np.max(np.abs(st.C)))
+        e_b = float(np.max(np.abs(st.rb - pick(steps - 1, "row_bias", "embeddings").reshape(-1))) / np.max(np.abs(st.rb)))
+        ok[reg_scale] = max(e_loss, e_R, e_C, e_b)
+    assert min(ok.values()) < 1e-5, ok
+    assert ok[2.0] < 1e-5, ("TensorFlow counts the activity losses ONCE: switch the default reg_scale to 1", ok)
