@@ -300,6 +300,8 @@ def main():
                     help="instead of really training %d steps first, start from a synthetic steady state (round-1 method)" % T0)
     ap.add_argument("--pretrain-steps", type=int, default=T0,
                     help="TRAIN steps run from the cold start before the timed region (default %d; profiling runs use fewer)" % T0)
+    ap.add_argument("--no-graph", action="store_true",
+                    help="launch every step's kernels one by one instead of one CUDA graph per plan chunk (N=1)")
     ap.add_argument("--no-topk", action="store_true", help="skip the cfg5 top-k record of the default N=1 run")
     ap.add_argument("--shard-exchange", default="peer", choices=["alltoall", "allgather", "peer", "peer-direct"],
                     help="N>1, row-sharded tables: how the snapshot rows reach the shards that need them (peer = one pull "
@@ -403,9 +405,19 @@ def main():
             eng.step()
     torch.cuda.synchronize()
 
+    eng.use_graph = (N == 1 and not args.no_graph)
+
+    def run_steps(n):
+        """exactly n TRAIN steps: whole plan chunks as one CUDA graph launch each (N = 1), single launches otherwise"""
+        while n:
+            k = eng.step_chunk_graph() if (eng.use_graph and n >= eng.K) else 0
+            if not k:
+                eng.step()
+                k = 1
+            n -= k
+
     # ---- warm-up ---------------------------------------------------------------------------------------------------
-    for _ in range(max(args.warmup, 3)):
-        eng.step()
+    run_steps(max(args.warmup, 3))
     torch.cuda.synchronize()
     # distinct ids per step for the roofline figure (outside the timed region)
     first_timed = eng.host_step
@@ -415,8 +427,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start = time.time()
     e0.record()
-    for _ in range(args.steps):
-        eng.step()
+    run_steps(args.steps)
     e1.record()
     torch.cuda.synchronize()
     if world > 1:

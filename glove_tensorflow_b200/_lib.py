@@ -66,6 +66,9 @@ SIGNATURES = {
     "glove_step_args_size": (c_size, []),
     "glove_step_workspace_bytes": (c_size, [c_i32, c_i32]),
     "glove_train_step": (ctypes.c_int, [ctypes.POINTER(StepArgs), c_void]),
+    "glove_step_graph_create": (ctypes.c_int, [ctypes.POINTER(StepArgs), c_i32, ctypes.POINTER(c_void)]),
+    "glove_step_graph_launch": (ctypes.c_int, [c_void, c_void]),
+    "glove_step_graph_destroy": (ctypes.c_int, [c_void]),
     "glove_catchup_step": (ctypes.c_int, [ctypes.POINTER(StepArgs), c_i32, c_void]),
     "glove_train_step_profiled": (ctypes.c_int, [ctypes.POINTER(StepArgs), c_void, ctypes.POINTER(c_f32)]),
     "glove_grad_step": (ctypes.c_int, [ctypes.POINTER(StepArgs), c_void, c_void, c_void, c_void]),

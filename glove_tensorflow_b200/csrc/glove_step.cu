@@ -24,6 +24,8 @@
 // Everything is deterministic: no floating-point atomics, fixed summation order given (B, kItemMax, grid size).
 #include <stdlib.h>
 
+#include <new>
+
 #include "glove_common.cuh"
 
 namespace glove {
@@ -773,7 +775,7 @@ __global__ void __launch_bounds__(128, (NV <= 3 ? 4 : 3)) update_kernel(const St
                             load_row<NV>(x, p.snap[s] + (int64_t)lr.y * p.S, lane, S4);
                             if (p.P >= 2) load_row<NV>(s1, lrow + p.S, lane, S4);
                             if (p.P >= 3) load_row<NV>(s2, lrow + 2 * p.S, lane, S4);
-                            apply_row<NV>(p, lrow, x, acc, s1, s2, s, step, lane, closed ? __ldcg(p.gap[s] + lr.y) : 0, pol_stream);
+                            apply_row<NV>(p, lrow, x, acc, s1, s2, s, step, lane, closed ? __ldcg(p.gap[s] + lr.y) : 0, lpol_stream);
                         }
                     }
                 }
@@ -1104,6 +1106,64 @@ int glove_train_step(const glove_step_args *args, void *stream) {
     int rc = fill_params(args, p, MODE_TRAIN);
     if (rc != GLOVE_OK) return rc;
     return dispatch(p, (cudaStream_t)stream);
+}
+
+// ---- K TRAIN steps as one CUDA graph ------------------------------------------------------------------------------------
+// The step index lives in device memory and every kernel derives its batch from it, so the launch sequence of a step does
+// not depend on WHICH step it is: n_steps x (stage, update) captured once replay correctly for any run of n_steps
+// consecutive steps served by the same plan buffer.  One graph launch replaces 2 n_steps kernel launches -- what keeps a
+// small-batch run (B = 1,024: ~10 us of kernel time per step) from being bound by launch overhead.
+struct glove_step_graph {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    int32_t n_steps = 0;
+};
+
+int glove_step_graph_create(const glove_step_args *args, int32_t n_steps, glove_step_graph **out) {
+    GLOVE_REQUIRE(out, "glove_step_graph_create: null output");
+    *out = nullptr;
+    GLOVE_REQUIRE(n_steps > 0 && n_steps <= 4096, "glove_step_graph_create: n_steps out of range");
+    StepParams p;
+    int rc = fill_params(args, p, MODE_TRAIN);
+    if (rc != GLOVE_OK) return rc;
+    {   // size the grids (occupancy queries, environment) outside the capture
+        StepParams q = p;
+        q.run_stage = q.run_update = 0;
+        rc = dispatch(q, nullptr);
+        if (rc != GLOVE_OK) return rc;
+    }
+    glove_step_graph *g = new (std::nothrow) glove_step_graph();
+    GLOVE_REQUIRE(g, "glove_step_graph_create: out of memory");
+    cudaStream_t cs = nullptr;
+    cudaError_t e = cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+    if (e == cudaSuccess) {
+        for (int32_t i = 0; i < n_steps && rc == GLOVE_OK; ++i) rc = dispatch(p, cs);
+        e = cudaStreamEndCapture(cs, &g->graph);
+    }
+    if (e == cudaSuccess && rc == GLOVE_OK) e = cudaGraphInstantiate(&g->exec, g->graph, 0);
+    if (cs) cudaStreamDestroy(cs);
+    if (e != cudaSuccess || rc != GLOVE_OK) {
+        glove_step_graph_destroy(g);
+        return rc != GLOVE_OK ? rc : set_error(GLOVE_ECUDA, "glove_step_graph_create: %s", cudaGetErrorString(e));
+    }
+    g->n_steps = n_steps;
+    *out = g;
+    return GLOVE_OK;
+}
+
+int glove_step_graph_launch(glove_step_graph *g, void *stream) {
+    GLOVE_REQUIRE(g && g->exec, "glove_step_graph_launch: null graph");
+    GLOVE_CHECK_CUDA(cudaGraphLaunch(g->exec, (cudaStream_t)stream));
+    return GLOVE_OK;
+}
+
+int glove_step_graph_destroy(glove_step_graph *g) {
+    if (!g) return GLOVE_OK;
+    if (g->exec) cudaGraphExecDestroy(g->exec);
+    if (g->graph) cudaGraphDestroy(g->graph);
+    delete g;
+    return GLOVE_OK;
 }
 
 int glove_catchup_step(const glove_step_args *args, int32_t step_index, void *stream) {

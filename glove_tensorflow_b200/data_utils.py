@@ -15,7 +15,10 @@ import numpy as np
 def read_vocab(vocab_txt):
     """One token per line, line number = id, no trailing newline (ref src/data/text8.py:149-150)."""
     with open(vocab_txt, encoding="utf8") as f:
-        return f.read().split("\n")
+        lines = f.read().split("\n")
+    if lines and lines[-1] == "":     # a file that ends with a newline has V lines, not V + 1 (TextLineDataset / file_lines)
+        lines.pop()
+    return lines
 
 
 def file_lines(fname):
@@ -31,6 +34,8 @@ def vocab_blob(vocab_txt):
     """vocab.txt as the ingest kernels want it: every line followed by one '\\n', plus the n+1 line offsets."""
     with open(vocab_txt, "rb") as f:
         lines = f.read().split(b"\n")
+    if lines and lines[-1] == b"":    # trailing newline: not an (empty) extra token -- n_vocab must equal file_lines()
+        lines.pop()
     blob = b"".join(t + b"\n" for t in lines)
     off = np.zeros(len(lines) + 1, np.int64)
     np.cumsum([len(t) + 1 for t in lines], out=off[1:])
@@ -198,16 +203,39 @@ def load_interaction_csv(train_csv, vocab_txt, row_name="row_token", col_name="c
     ``row_name`` / ``col_name`` may name string columns (resolved through vocab.txt, missing -> 0) or integer id columns
     (``row_token_id``: equal by construction).  Tokens like 'na' / 'null' / 'nan' are ordinary vocabulary
     words (ref README.md:54)."""
-    key = "|".join([row_name, col_name] + list(value_names))
+    # the cached ids were resolved through THIS vocab.txt: its size and mtime are part of the key (an edited or different
+    # vocabulary with the same csv must not reuse them)
+    vst = os.stat(vocab_txt)
+    n_vocab = file_lines(vocab_txt)
+    key = "|".join([row_name, col_name] + list(value_names) + ["vocab:%d:%d:%d" % (n_vocab, vst.st_size, vst.st_mtime_ns)])
     side = train_csv + ".coo.npz"
+    out = None
     if cache and os.path.exists(side) and os.path.getmtime(side) >= os.path.getmtime(train_csv):
-        z = np.load(side, allow_pickle=False)
-        if str(z["key"]) == key:
-            return {k: z[k] for k in z.files if k != "key"}
-    out = {k: v.cpu().numpy() for k, v in ingest_csv(train_csv, vocab_txt, row_name, col_name, value_names, device).items()}
-    if cache:
         try:
-            np.savez(side, key=np.array(key), **out)
-        except OSError:
-            pass
+            z = np.load(side, allow_pickle=False)
+            if str(z["key"]) == key:
+                out = {k: z[k] for k in z.files if k != "key"}
+        except Exception:   # unreadable sidecar: re-ingest
+            out = None
+    if out is None:
+        out = {k: v.cpu().numpy() for k, v in ingest_csv(train_csv, vocab_txt, row_name, col_name, value_names, device).items()}
+        if cache:
+            try:
+                tmp = side + ".tmp.npz"
+                np.savez(tmp, key=np.array(key), **out)
+                os.replace(tmp, side)
+            except OSError:
+                pass
+    check_ids(out["row"], out["col"], n_vocab, train_csv)
     return out
+
+
+def check_ids(row, col, n_vocab, what="COO"):
+    """0 <= id < V for every triple: nothing downstream bounds-checks ids (they index the packed tables and are packed
+    into vbits-wide sort keys), so a violation is refused here, once."""
+    for name, a in (("row", row), ("col", col)):
+        if len(a) == 0:
+            continue
+        lo, hi = int(a.min()), int(a.max())
+        if lo < 0 or hi >= n_vocab:
+            raise ValueError("%s: %s id out of range [0, %d): min %d, max %d" % (what, name, n_vocab, lo, hi))

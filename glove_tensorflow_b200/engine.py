@@ -114,8 +114,18 @@ class GloveEngine:
         self._keep = [None, None]
         self._norm_cache = None
         self.last_topk_fallbacks = None
+        # K steps as ONE CUDA graph launch (glove_step_graph_*): one graph per plan buffer, built on first use
+        self.use_graph = False
+        self._graphs = [None, None]
 
     def __del__(self):
+        for g in getattr(self, "_graphs", [None, None]):
+            if g is not None:
+                try:
+                    lib.glove_step_graph_destroy(g)
+                except Exception:
+                    pass
+        self._graphs = [None, None]
         pipe = getattr(self, "_host_pipe", None)
         if pipe is not None:
             try:
@@ -264,6 +274,13 @@ class GloveEngine:
             return t.to(device=self.device, dtype=dt).contiguous()
         self.coo = (dev(row, torch.int32), dev(col, torch.int32), dev(col_a, torch.float32), dev(col_b, torch.float32))
         self.nnz = int(self.coo[0].numel())
+        if self.nnz:
+            # ids index the packed tables and are packed into vbits-wide sort keys: refuse out-of-range ids here, once
+            lo = int(torch.minimum(self.coo[0].min(), self.coo[1].min()))
+            hi = int(torch.maximum(self.coo[0].max(), self.coo[1].max()))
+            if lo < 0 or hi >= self.V_global:
+                self.coo, self.nnz = None, 0
+                raise ValueError("set_coo: ids must lie in [0, %d): min %d, max %d" % (self.V_global, lo, hi))
         self.shuffle_key = int(shuffle_key) & 0xFFFFFFFF
         self.plan_first = [None, None]
 
@@ -400,6 +417,32 @@ class GloveEngine:
         self.host_step += 1
         if self.adam_mode == "dense":
             self.flush()
+
+    def step_chunk_graph(self) -> int:
+        """The K steps of the plan chunk that starts at the current step as ONE CUDA graph launch (captured once per plan
+        buffer, valid for every later chunk that buffer serves).  Returns the number of steps enqueued (K), or 0 when the
+        graph path does not apply here (not at a chunk boundary, fewer than K steps left, sharded / data-parallel /
+        exact-replay modes that interleave other streams with the steps): the caller then falls back to ``step()``."""
+        s = self.host_step
+        if (s % self.K or s + self.K > self.max_steps or self.sharded or self.dp_world > 1 or self._plan_override is not None
+                or self.adam_mode in ("replay_exact", "dense")):
+            return 0
+        if self.sample_idx is not None and s + self.K - self.sample_idx_first > self.sample_idx.shape[0]:
+            return 0
+        which = self._plan_for(s)
+        self._ev_catchup = None
+        if self.overlap:
+            self._prefetch_plan(s)
+        if self._graphs[which] is None:
+            g = ctypes.c_void_p(0)
+            check(lib.glove_step_graph_create(ctypes.byref(self._args[which]), self.K, ctypes.byref(g)), "glove_step_graph_create")
+            self._graphs[which] = g
+        check(lib.glove_step_graph_launch(self._graphs[which], _stream()), "glove_step_graph_launch")
+        self.host_step += self.K
+        if self.overlap:   # both completion slots: whichever parity a later catch-up asks about, the chunk has finished
+            self._ev_step_done[0].record(torch.cuda.current_stream())
+            self._ev_step_done[1].record(torch.cuda.current_stream())
+        return self.K
 
     def grad_step(self):
         """Data-parallel half-step 1: this rank's gradient partial sums for every global segment (dense, slot order).
@@ -702,8 +745,13 @@ class GloveEngine:
         done = 0
         while done < n_steps:
             chunk = min(n_steps - done, self.loss_cap)
-            for _ in range(chunk):
-                self.step()
+            left = chunk
+            while left:
+                k = self.step_chunk_graph() if (self.use_graph and left >= self.K) else 0
+                if not k:
+                    self.step()
+                    k = 1
+                left -= k
             torch.cuda.synchronize()
             idx = (torch.arange(start + done, start + done + chunk, device=self.device) % self.loss_cap)
             losses.append(self.loss_out[idx].cpu().numpy())
@@ -734,7 +782,10 @@ class GloveEngine:
             dist.all_gather_into_tensor(all_idx, idx.reshape(-1))
             return self.topk_shard_merge(all_sim.view(self.dp_world, n, kk), all_idx.view(self.dp_world, n, kk), k)
         self.flush()
-        q = torch.as_tensor(np.ascontiguousarray(query_ids, np.int32)).to(self.device)
+        qh = np.ascontiguousarray(query_ids, np.int64).reshape(-1)
+        if qh.size and (qh.min() < 0 or qh.max() >= self.V):      # the kernels index the table with these: refuse, never clamp
+            raise ValueError("topk: query ids must lie in [0, %d): min %d, max %d" % (self.V, qh.min(), qh.max()))
+        q = torch.as_tensor(qh.astype(np.int32)).to(self.device)
         n = int(q.numel())
         inv, nb = self._normalised_table()
         sim, idx = self._topk_call(inv, nb, self.row_table, self.P, nb, q, n, k, exact_fp32)

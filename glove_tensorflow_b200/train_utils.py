@@ -18,46 +18,94 @@ def checkpoint_path(job_dir, step):
     return os.path.join(job_dir, "model.ckpt-%d.npz" % step)
 
 
-def latest_checkpoint(job_dir):
-    best, best_step = None, -1
+KEEP_CHECKPOINT_MAX = 5   # tf.estimator.RunConfig default
+
+
+def _checkpoint_steps(job_dir):
+    out = []
     for path in glob.glob(os.path.join(job_dir, "model.ckpt-*.npz")):
         try:
-            step = int(os.path.basename(path)[len("model.ckpt-"):-len(".npz")])
+            out.append((int(os.path.basename(path)[len("model.ckpt-"):-len(".npz")]), path))
         except ValueError:
             continue
-        if step > best_step:
-            best, best_step = path, step
-    return best
+    return sorted(out)
 
 
-def save_checkpoint(engine, job_dir):
-    """Variables in the reference's layout (4 tables + global bias) + optimizer slots + global_step."""
+def latest_checkpoint(job_dir):
+    """The checkpoint named by the ``checkpoint`` index (written AFTER the file it names was renamed into place, so it
+    never points at a truncated file); without a usable index, the newest ``model.ckpt-N.npz`` that opens."""
+    index = os.path.join(job_dir, "checkpoint")
+    if os.path.exists(index):
+        try:
+            with open(index) as f:
+                path = os.path.join(job_dir, json.load(f)["model_checkpoint_path"])
+            if os.path.exists(path):
+                return path
+        except (ValueError, KeyError, OSError):
+            pass
+    for _, path in reversed(_checkpoint_steps(job_dir)):
+        try:
+            with np.load(path, allow_pickle=False) as z:
+                z["step"]
+            return path
+        except Exception:   # truncated / foreign file: try the one before
+            continue
+    return None
+
+
+def save_checkpoint(engine, job_dir, keep=KEEP_CHECKPOINT_MAX):
+    """Variables in the reference's layout (4 tables + global bias) + optimizer slots + global_step + the per-row
+    "ever updated" masks.  Written to a temporary file and renamed, index updated after the rename, older checkpoints
+    pruned to the last ``keep`` (tf.estimator keeps 5)."""
     state = engine.get_state(slots=True)  # flushes lazy Adam state: tables are exactly the dense-Keras values
     sc = engine.read_scalars()
-    path = checkpoint_path(job_dir, int(state["step"]))
-    np.savez(path, **{k.replace("/", "__"): v for k, v in state.items()}, g_s0=np.float32(sc["g_s0"]),
-             g_s1=np.float32(sc["g_s1"]), shuffle_key=np.int64(engine.shuffle_key))
-    with open(os.path.join(job_dir, "checkpoint"), "w") as f:
-        json.dump({"model_checkpoint_path": os.path.basename(path), "global_step": int(state["step"])}, f)
+    step = int(state["step"])
+    path = checkpoint_path(job_dir, step)
+    touched = {"touched_%s" % side: (engine.get_last_step(side) > 0).cpu().numpy() for side in ("row", "col")}
+    tmp = path + ".tmp.npz"
+    np.savez(tmp, **{k.replace("/", "__"): v for k, v in state.items()}, g_s0=np.float32(sc["g_s0"]),
+             g_s1=np.float32(sc["g_s1"]), shuffle_key=np.int64(engine.shuffle_key), **touched)
+    os.replace(tmp, path)
+    index_tmp = os.path.join(job_dir, "checkpoint.tmp")
+    with open(index_tmp, "w") as f:
+        json.dump({"model_checkpoint_path": os.path.basename(path), "global_step": step}, f)
+    os.replace(index_tmp, os.path.join(job_dir, "checkpoint"))
+    if keep and keep > 0:
+        for _, old in _checkpoint_steps(job_dir)[:-keep]:
+            try:
+                os.remove(old)
+            except OSError:
+                pass
     return path
 
 
 def load_checkpoint(engine, path):
     import torch
     z = np.load(path, allow_pickle=False)
-    engine.load_state(z["R"], z["C"], z["rb"], z["cb"], float(z["g"]))
     step = int(z["step"])
+    if step > engine.max_steps:
+        raise ValueError("checkpoint %s is at global_step %d, beyond this run's %d steps (--train-steps counts the steps "
+                         "already in the checkpoint: raise it to continue training)" % (path, step, engine.max_steps))
+    engine.load_state(z["R"], z["C"], z["rb"], z["cb"], float(z["g"]))
     dev = engine.device
     for side, (tab, bias) in (("row", ("R", "rb")), ("col", ("C", "cb"))):
+        slots = []
         for p in range(1, engine.P):
-            engine.set_plane(side, p, torch.from_numpy(z["%s__s%d" % (tab, p - 1)]).to(dev),
-                             torch.from_numpy(z["%s__s%d" % (bias, p - 1)]).to(dev))
-        # every row of a flushed checkpoint is current through `step` (0 = never touched is indistinguishable from
-        # "touched, then flushed" only when m = v = 0, where the idle step is a no-op anyway)
-        ls = torch.full((engine.V,), step, dtype=torch.int32, device=dev)
-        if engine.optimizer == "Adam":
-            m = torch.from_numpy(z["%s__s0" % tab]).to(dev)
-            ls = torch.where((m != 0).any(dim=1), ls, torch.zeros_like(ls))
+            e, b = z["%s__s%d" % (tab, p - 1)], z["%s__s%d" % (bias, p - 1)]
+            slots += [e, b.reshape(-1, 1)]
+            engine.set_plane(side, p, torch.from_numpy(e).to(dev), torch.from_numpy(b).to(dev))
+        # A flushed checkpoint holds every row current through `step`.  last_step = step on every row that was ever
+        # updated, 0 ("never touched": the stage skips it) on the others.  The mask is stored; for checkpoints written
+        # before it was, a row counts as touched when ANY of its slot values (embedding or bias, m or v) is non-zero --
+        # m alone underflows to 0 after ~900 idle steps while v is still decaying.
+        if "touched_%s" % side in z.files:
+            touched = torch.from_numpy(z["touched_%s" % side]).to(dev)
+        elif slots:
+            touched = torch.from_numpy(np.any(np.concatenate(slots, 1) != 0, axis=1)).to(dev)
+        else:
+            touched = torch.zeros(engine.V, dtype=torch.bool, device=dev)
+        ls = torch.where(touched, torch.full((engine.V,), step, dtype=torch.int32, device=dev),
+                         torch.zeros(engine.V, dtype=torch.int32, device=dev))
         engine.set_last_step(side, ls)
     engine._write_scalars(g_s0=float(z["g_s0"]), g_s1=float(z["g_s1"]))
     engine.set_step(step)

@@ -38,7 +38,7 @@ extern "C" {
 
 /* 2: glove_step_args starts with struct_size and ends with peer_gather (n_shards, shard, peer_gather were appended in
  *    round 1 without a bump); adam_mode gained GLOVE_ADAM_REPLAY_EXACT and GLOVE_ADAM_REPLAY became the closed-form
- *    replay; glove_train_steps_host takes a caller-owned glove_host_pipe; glove_train_steps_graph added. */
+ *    replay; glove_train_steps_host takes a caller-owned glove_host_pipe; glove_step_graph_* added. */
 #define GLOVE_B200_ABI_VERSION 2
 
 enum { GLOVE_OK = 0, GLOVE_EINVAL = -1, GLOVE_ECUDA = -2, GLOVE_EWORKSPACE = -3, GLOVE_EUNSUPPORTED = -4 };
@@ -158,6 +158,16 @@ size_t glove_step_args_size(void);
 size_t glove_step_workspace_bytes(int32_t B, int32_t d);
 /* one full TRAIN step; increments scalars->step */
 int glove_train_step(const glove_step_args *args, void *stream);
+/* n_steps consecutive TRAIN steps captured once as a CUDA graph (2 n_steps kernel nodes) and replayed with one launch:
+ * the step index and the batch derived from it are read from device memory, so a graph built on `args` is valid for ANY
+ * run of n_steps steps that this plan buffer serves (n_steps <= plan_K, starting where scalars->step stands).  Replaces the
+ * n_steps session.run(train_op) calls of the reference's hook-driven loop [ref src/models/train_utils.py:39-40] when the
+ * batch is small enough for launch overhead to matter (configs/app.ini: BATCH_SIZE = 1024).  The handle is caller-owned;
+ * results are bit-identical to n_steps glove_train_step calls. */
+typedef struct glove_step_graph glove_step_graph;
+int glove_step_graph_create(const glove_step_args *args, int32_t n_steps, glove_step_graph **out);
+int glove_step_graph_launch(glove_step_graph *graph, void *stream);
+int glove_step_graph_destroy(glove_step_graph *graph);
 /* Optional overlap aid for GLOVE_ADAM_REPLAY_EXACT: replays, ahead of time and on ANOTHER stream, the idle Adam steps of the
  * rows of step `step_index`'s batch that are not in the batch of step_index-1 (so the step in flight cannot touch
  * them).  Must be ordered after the completion of step_index-2 and before the start of step_index (events); a no-op

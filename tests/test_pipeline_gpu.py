@@ -1,4 +1,6 @@
 """GPU tests of the input pipeline (keyed shuffle), EVAL pass and the host-buffer entry point, against the oracle."""
+import os
+
 import numpy as np
 import pytest
 
@@ -203,3 +205,56 @@ def test_train_chunk_from_host_at_any_step_alignment():
     got2 = list(eng2.train(3)) + list(eng2.train_chunk_from_host(*pins[0])) + list(eng2.train_chunk_from_host(*pins[1]))
     assert np.array_equal(np.array(got2), np.array(got)) and np.array_equal(eng2.get_state()["R"], eng.get_state()["R"])
     assert np.all(np.isfinite(eng2.train(2)))
+
+
+def test_resume_after_long_idle_gaps_is_bit_identical(tmp_path):
+    """Checkpoint / resume with rows that have sat idle for > 1,000 steps (their Adam m has underflowed to exactly 0 while
+    v has not): the resumed run must continue bit for bit like the run that wrote the checkpoint and went on.  Rows
+    V-8 .. V-1 are touched in step 0 only, then again after the checkpoint; the checkpoint stores the per-row
+    "ever updated" mask, so their v keeps decaying across the restart."""
+    from glove_tensorflow_b200 import train_utils
+    from glove_tensorflow_b200.engine import GloveEngine
+    V, d, B, T_ckpt, T_end = 64, 8, 16, 1100, 1130
+    rng = np.random.default_rng(9)
+    n = T_end * B
+    row = rng.integers(0, V - 8, n).astype(np.int32)
+    col = rng.integers(0, V - 8, n).astype(np.int32)
+    row[:8] = np.arange(V - 8, V); col[8:16] = np.arange(V - 8, V)          # step 0 touches the rare rows ...
+    late = (T_ckpt + 20) * B
+    row[late:late + 8] = np.arange(V - 8, V); col[late + 8:late + 16] = np.arange(V - 8, V)   # ... and step T_ckpt+20 again
+    coo = dict(row=row, col=col, target=rng.normal(1.0, 0.5, n).astype(np.float32), weight=rng.uniform(0.1, 1, n).astype(np.float32))
+    batches = np.arange(n).reshape(T_end, B)
+
+    def engine():
+        e = GloveEngine(V, d, learning_rate=0.05, batch_size=B, plan_steps=8, max_steps=T_end + 8)
+        e.init_uniform(3)
+        e.set_coo(coo["row"], coo["col"], coo["target"], coo["weight"])
+        e.set_batches(batches)
+        return e
+
+    a = engine()
+    a.train(T_ckpt)
+    job = str(tmp_path)
+    path = train_utils.save_checkpoint(a, job)
+    m_rare = a.get_state(slots=True)["R/s0"][V - 8:]
+    assert not m_rare.any(), "the rare rows' first moment should have underflowed to 0 (the case the mask exists for)"
+    assert a.get_state(slots=True)["R/s1"][V - 8:].any()
+    la = a.train(T_end - T_ckpt)
+    sa = a.get_state(slots=True)
+
+    b = engine()
+    assert train_utils.latest_checkpoint(job) == path
+    assert train_utils.load_checkpoint(b, path) == T_ckpt
+    lb = b.train(T_end - T_ckpt)
+    sb = b.get_state(slots=True)
+    assert np.array_equal(la, lb)
+    for k in sa:
+        assert np.array_equal(np.asarray(sa[k]), np.asarray(sb[k])), k
+    # a truncated newer file must not be picked up, and a checkpoint beyond max_steps is refused with a clear message
+    open(os.path.join(job, "model.ckpt-999999.npz"), "wb").write(b"PK\x03\x04 truncated")
+    assert train_utils.latest_checkpoint(job) == path
+    os.remove(os.path.join(job, "checkpoint"))
+    assert train_utils.latest_checkpoint(job) == path
+    small = GloveEngine(V, d, batch_size=B, plan_steps=8, max_steps=100)
+    with pytest.raises(ValueError, match="beyond this run"):
+        train_utils.load_checkpoint(small, path)

@@ -183,6 +183,32 @@ def test_deterministic_rerun_bitwise():
         assert np.array_equal(g1[k], g2[k])
 
 
+@pytest.mark.parametrize("optimizer", ["Adam", "Adagrad"])
+def test_cuda_graph_replay_is_bit_identical(optimizer):
+    """K steps captured once as a CUDA graph (glove_step_graph_*) and replayed for every later chunk of the same plan buffer
+    give bit for bit the tables and losses of single glove_train_step launches: the step index and the batch are read
+    from device memory, so nothing step-specific is baked into the graph.  27 steps, K = 4: six graph launches (three per
+    plan buffer) and three single steps at the tail."""
+    from glove_tensorflow_b200.engine import GloveEngine
+    V, d, B, steps, K = 800, 48, 256, 27, 4
+    coo = make_coo(V, 4000, 11, hot=0.1)
+    batches = np.random.default_rng(12).integers(0, 4000, (steps, B))
+    st = o.init_state(V, d, 13)
+    out = []
+    for use_graph in (False, True):
+        eng = GloveEngine(V, d, optimizer=optimizer, learning_rate=0.01, batch_size=B, plan_steps=K, max_steps=steps + 8)
+        eng.load_state(st.R, st.C, st.rb, st.cb, st.g)
+        eng.set_coo(coo["row"], coo["col"], coo["target"], coo["weight"])
+        eng.set_batches(batches)
+        eng.use_graph = use_graph
+        losses = eng.train(steps)
+        assert (eng._graphs[0] is not None) == use_graph and (eng._graphs[1] is not None) == use_graph
+        out.append((losses, eng.get_state(slots=True)))
+    assert np.array_equal(out[0][0], out[1][0])
+    for k in out[0][1]:
+        assert np.array_equal(np.asarray(out[0][1][k]), np.asarray(out[1][1][k])), k
+
+
 def test_batch_size_one_and_single_id():
     ref, rl, got, l, _ = _run_pair(3, 4, 1, 10, zipf=False)
     _assert_close(ref, rl, got, l)
