@@ -775,7 +775,7 @@ __global__ void __launch_bounds__(128, (NV <= 3 ? 4 : 3)) update_kernel(const St
                             load_row<NV>(x, p.snap[s] + (int64_t)lr.y * p.S, lane, S4);
                             if (p.P >= 2) load_row<NV>(s1, lrow + p.S, lane, S4);
                             if (p.P >= 3) load_row<NV>(s2, lrow + 2 * p.S, lane, S4);
-                            apply_row<NV>(p, lrow, x, acc, s1, s2, s, step, lane, closed ? __ldcg(p.gap[s] + lr.y) : 0, lpol_stream);
+                            apply_row<NV>(p, lrow, x, acc, s1, s2, s, step, lane, closed ? __ldcg(p.gap[s] + lr.y) : 0, pol_stream);
                         }
                     }
                 }
