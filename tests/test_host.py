@@ -121,10 +121,25 @@ def test_ingest_host_helpers(tmp_path):
     # sidecar cache: a current <csv>.coo.npz with the same column key is returned without touching the GPU
     c2 = tmp_path / "i.csv"
     c2.write_text("x\n")
-    np.savez(str(c2) + ".coo.npz", key=np.array("r|c|a|b"), row=np.arange(3, dtype=np.int32), col=np.arange(3, dtype=np.int32),
-             a=np.ones(3, np.float32), b=np.ones(3, np.float32))
+    # (the key names the columns AND the vocabulary the ids were resolved through: line count, size, mtime)
+    vst = os.stat(voc)
+    key = "r|c|a|b|vocab:%d:%d:%d" % (61, vst.st_size, vst.st_mtime_ns)
+    side = dict(row=np.arange(3, dtype=np.int32), col=np.arange(3, dtype=np.int32), a=np.ones(3, np.float32), b=np.ones(3, np.float32))
+    np.savez(str(c2) + ".coo.npz", key=np.array(key), **side)
     got = data_utils.load_interaction_csv(str(c2), voc, "r", "c", ("a", "b"))
     assert list(got["row"]) == [0, 1, 2]
+    # cached ids beyond the vocabulary are refused (nothing downstream bounds-checks them) ...
+    np.savez(str(c2) + ".coo.npz", key=np.array(key), **dict(side, col=np.array([0, 61, 2], np.int32)))
+    with pytest.raises(ValueError, match="out of range"):
+        data_utils.load_interaction_csv(str(c2), voc, "r", "c", ("a", "b"))
+    # ... and a sidecar written for ANOTHER vocab.txt is not reused (here the re-ingest then fails on the dummy csv)
+    np.savez(str(c2) + ".coo.npz", key=np.array("r|c|a|b|vocab:60:1:1"), **side)
+    with pytest.raises(ValueError, match="not in the csv header"):
+        data_utils.load_interaction_csv(str(c2), voc, "r", "c", ("a", "b"))
+    # a vocab.txt that ends with a newline has the same number of lines
+    v2 = tmp_path / "vocab_nl.txt"
+    v2.write_bytes(open(voc, "rb").read() + b"\n")
+    assert data_utils.file_lines(str(v2)) == len(data_utils.read_vocab(str(v2))) == len(data_utils.vocab_blob(str(v2))[1]) - 1 == 61
 
 
 def test_export_embeddings_format(tmp_path):
