@@ -300,6 +300,8 @@ def main():
                     help="instead of really training %d steps first, start from a synthetic steady state (round-1 method)" % T0)
     ap.add_argument("--pretrain-steps", type=int, default=T0,
                     help="TRAIN steps run from the cold start before the timed region (default %d; profiling runs use fewer)" % T0)
+    ap.add_argument("--no-balance", action="store_true",
+                    help="N>1, row-sharded tables: keep owner = id %% N instead of the frequency-balanced owner map")
     ap.add_argument("--no-graph", action="store_true",
                     help="launch every step's kernels one by one instead of one CUDA graph per plan chunk (N=1)")
     ap.add_argument("--no-topk", action="store_true", help="skip the cfg5 top-k record of the default N=1 run")
@@ -393,8 +395,12 @@ def main():
             args.shard_exchange = eng.shard_exchange = "alltoall"
     elif world <= 1 or args.dp_mode != "sharded":
         args.shard_exchange = eng.shard_exchange = "alltoall"
-    eng.init_uniform(seed=1)                                   # same seed on every rank: replicas start identical
     row, col, tgt, wgt = gen_coo_device(V, nnz, 1234, dev)     # replicated COO (weak scaling: B grows with N)
+    row0, col0 = row, col
+    owner_load = None
+    if world > 1 and args.dp_mode == "sharded" and not args.no_balance:
+        owner_load = eng.balance_owners(row, col)              # frequency-balanced owner map (before any state is loaded)
+    eng.init_uniform(seed=1)                                   # same seed on every rank: replicas start identical
     eng.set_coo(row, col, tgt, wgt, shuffle_key=0xC0FFEE)
     if args.emulate_state and not args.cold_state:
         steady_state(eng, V, B, seed=99)
@@ -486,22 +492,28 @@ def main():
         KC = K * CALL
         n_chunks = max(1, args.steps // KC)
         pool = 2
-        hr = [torch.empty(KC * B, dtype=torch.int32).pin_memory() for _ in range(pool)]
-        hc = [torch.empty(KC * B, dtype=torch.int32).pin_memory() for _ in range(pool)]
-        ha = [torch.empty(KC * B, dtype=torch.float32).pin_memory() for _ in range(pool)]
-        hb = [torch.empty(KC * B, dtype=torch.float32).pin_memory() for _ in range(pool)]
+        # N > 1: every rank holds (and copies) only ITS share of each batch, [KC][B_local]; the ranks all-gather on the device
+        HB = B if N == 1 else B_local
+        hr = [torch.empty(KC * HB, dtype=torch.int32).pin_memory() for _ in range(pool)]
+        hc = [torch.empty(KC * HB, dtype=torch.int32).pin_memory() for _ in range(pool)]
+        ha = [torch.empty(KC * HB, dtype=torch.float32).pin_memory() for _ in range(pool)]
+        hb = [torch.empty(KC * HB, dtype=torch.float32).pin_memory() for _ in range(pool)]
         hl = torch.empty(KC, dtype=torch.float32).pin_memory()
         for i in range(pool):
-            sel = (torch.arange(KC * B, device=dev, dtype=torch.int64) + i * KC * B) % nnz
-            hr[i].copy_(row[sel]); hc[i].copy_(col[sel]); ha[i].copy_(tgt[sel]); hb[i].copy_(wgt[sel])
+            sel = torch.arange(KC * B, device=dev, dtype=torch.int64) + i * KC * B
+            if N > 1:
+                sel = sel.view(KC, N, B_local)[:, rank, :].reshape(-1)
+            sel = sel % nnz
+            hr[i].copy_(row0[sel]); hc[i].copy_(col0[sel]); ha[i].copy_(tgt[sel]); hb[i].copy_(wgt[sel])
         torch.cuda.synchronize()
 
         def chunk(i):
             if N == 1:
                 eng.train_steps_host(hr[i], hc[i], ha[i], hb[i], hl)      # one C-ABI call, HOST buffers in / losses out
             else:
-                KB = K * B
-                eng.train_chunks_from_host([tuple(t[i][j * KB:(j + 1) * KB] for t in (hr, hc, ha, hb)) for j in range(CALL)])
+                KB = K * HB
+                eng.train_chunks_from_host([tuple(t[i][j * KB:(j + 1) * KB] for t in (hr, hc, ha, hb)) for j in range(CALL)],
+                                           sliced=True)
         chunk(0)                                                          # warm
         torch.cuda.synchronize()
         if world > 1:
@@ -521,8 +533,9 @@ def main():
                "d2h_bytes_per_step": 4 + 4.0 / KC, "steps": n_chunks * KC,
                "path": ("glove_train_steps_host, %d steps per call: pinned host COO -> H2D -> plans -> steps -> D2H losses; inside a "
                         "call the copy + plan of chunk c+1 overlap the steps of chunk c" % KC if N == 1 else
-                        "GloveEngine.train_chunks_from_host on every rank, %d steps per call: pinned host COO (global batch) -> "
-                        "H2D -> plans -> sharded steps -> D2H losses; copy + plan of chunk c+1 overlap the steps of chunk c" % KC)}
+                        "GloveEngine.train_chunks_from_host(sliced) on every rank, %d steps per call: pinned host COO (this rank's "
+                        "1/N of every batch) -> H2D -> NCCL all-gather of the chunk -> plans -> sharded steps -> D2H losses; copy + "
+                        "gather + plan of chunk c+1 overlap the steps of chunk c; h2d bytes are the sum over ranks" % KC)}
 
     if rank != 0:
         if world > 1:

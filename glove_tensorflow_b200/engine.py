@@ -78,6 +78,10 @@ class GloveEngine:
         for side, t in enumerate((self.row_table, self.col_table)):
             check(lib.glove_table_init(_ptr(t), self.V_rows, self.d, self.opt_id, side, _stream()), "glove_table_init")
         self.V = self.V_rows   # every table-shaped operation below works on the rows held here
+        # row-sharded tables: optional frequency-balanced owner map (balance_owners).  label = the id the kernels see
+        # (owner = label % world, local row = label // world); None = identity (owner = id % world)
+        self._label = None      # device int64 [V_global]: original id -> label
+        self._unlabel = None    # numpy int64 [V_global]: label -> original id
         self.scalars = torch.zeros(8, dtype=torch.int32, device=self.device)
         if optimizer == "Adagrad":
             self._write_scalars(g_s0=0.1)
@@ -147,6 +151,32 @@ class GloveEngine:
         s = _lib.GloveScalars.from_buffer(host)
         return {k: getattr(s, k) for k, _ in _lib.GloveScalars._fields_}
 
+    def balance_owners(self, row, col, hot: int = 65536):
+        """Row-sharded tables: replace the ``id % world`` ownership by a frequency-balanced one.  With Zipf ids the owner of
+        id 0 carries ~1.45x the mean work at 8 shards; here the ``hot`` most frequent ids (by their triple counts in the
+        COO ``row`` / ``col``) are dealt greedily to the least loaded owner (cost of an id = expected triples per step +
+        the per-row cost of a touched row), the rest round-robin, every owner keeping exactly as many rows as before.
+        Inside an owner, ids keep their order, so ties in the top-k still break towards the lower ORIGINAL id.  It is a pure
+        relabelling applied at the engine boundary (COO ids in, tables / top-k ids out): no kernel sees it, and results are
+        bit-identical to the unbalanced sharding (an item's arithmetic does not depend on where its row lives; the loss is
+        an order-independent sum).  Must be called on every rank with the same COO, before set_coo / load_state /
+        init_uniform."""
+        assert self.sharded, "balance_owners is for row-sharded tables"
+        N, V = self.dp_world, self.V_global
+        r = torch.as_tensor(row).to(self.device).to(torch.int64)
+        c = torch.as_tensor(col).to(self.device).to(torch.int64)
+        freq = (torch.bincount(r, minlength=V) + torch.bincount(c, minlength=V)).cpu().numpy().astype(np.float64)
+        from .parallel import balanced_labels
+        label, self._unlabel, load = balanced_labels(freq, N, self.B, int(r.numel()), hot)
+        self._label = torch.from_numpy(label).to(self.device)
+        self._norm_cache = None
+        return load                                              # relative load of the hot part per owner (diagnostics)
+
+    def owned_ids(self) -> np.ndarray:
+        """Original ids of the table rows held by this rank, in local-row order (row-sharded tables)."""
+        lab = np.arange(self.dp_rank, self.V_global, self.dp_world, dtype=np.int64) if self.sharded else np.arange(self.V_global)
+        return lab if self._unlabel is None else self._unlabel[lab]
+
     def load_state(self, R, C, rb, cb, g=0.0):
         """Inject initial tables (reference layout: R, C [V,d]; rb, cb [V]; scalar g)."""
         self._join_side()
@@ -162,8 +192,8 @@ class GloveEngine:
         torch.cuda.synchronize()
 
     def _local_rows(self, a):
-        """Rows of a global [V, ...] array owned by this rank (id % world == rank), zero-padded to V_rows."""
-        loc = a[self.dp_rank::self.dp_world]
+        """Rows of a global [V, ...] array owned by this rank (owned_ids()), zero-padded to V_rows."""
+        loc = a[self.owned_ids()]
         if loc.shape[0] < self.V_rows:
             pad = np.zeros((self.V_rows - loc.shape[0],) + loc.shape[1:], loc.dtype)
             loc = np.concatenate([loc, pad], 0)
@@ -209,9 +239,9 @@ class GloveEngine:
             if self.sharded:
                 e2 = torch.zeros(self.V, self.d, dtype=torch.float32, device=self.device)
                 b2 = torch.zeros(self.V, dtype=torch.float32, device=self.device)
-                own = e[self.dp_rank::self.dp_world]
-                e2[: own.shape[0]] = own
-                b2[: own.shape[0]] = b[self.dp_rank::self.dp_world]
+                ids = torch.from_numpy(self.owned_ids()).to(self.device)
+                e2[: ids.numel()] = e[ids]
+                b2[: ids.numel()] = b[ids]
                 e, b = e2, b2
             check(lib.glove_pack_plane(_ptr(table), self.V, self.d, self.P, 0, side, _ptr(e), _ptr(b), _stream()), "glove_pack_plane")
         torch.cuda.synchronize()
@@ -274,6 +304,12 @@ class GloveEngine:
             return t.to(device=self.device, dtype=dt).contiguous()
         self.coo = (dev(row, torch.int32), dev(col, torch.int32), dev(col_a, torch.float32), dev(col_b, torch.float32))
         self.nnz = int(self.coo[0].numel())
+        if self.nnz and self._label is not None:       # balanced owner map: the kernels see labels (checked against V first)
+            for t in self.coo[:2]:
+                if int(t.min()) < 0 or int(t.max()) >= self.V_global:
+                    self.coo, self.nnz = None, 0
+                    raise ValueError("set_coo: ids must lie in [0, %d)" % self.V_global)
+            self.coo = (self._label[self.coo[0].long()].to(torch.int32), self._label[self.coo[1].long()].to(torch.int32)) + self.coo[2:]
         if self.nnz:
             # ids index the packed tables and are packed into vbits-wide sort keys: refuse out-of-range ids here, once
             lo = int(torch.minimum(self.coo[0].min(), self.coo[1].min()))
@@ -660,13 +696,26 @@ class GloveEngine:
         """One chunk of K*B explicit triples from pinned HOST tensors (see train_chunks_from_host)."""
         return self.train_chunks_from_host([(host_row, host_col, host_a, host_b)])
 
-    def train_chunks_from_host(self, chunks):
+    def train_chunks_from_host(self, chunks, sliced: bool = False):
         """End-to-end path for any world size (data-parallel aware): every chunk is K*B explicit triples in pinned HOST
         tensors (row, col, colA, colB); it is copied to a device staging COO, planned in file order and trained for K
         steps.  The copy + plan of chunk c+1 run on the side stream while the steps of chunk c run (two plan buffers, two
         staging sets).  Returns the losses of all steps (numpy; synchronises).  At world size 1 prefer train_steps_host
-        (the same pipeline behind one C-ABI call)."""
+        (the same pipeline behind one C-ABI call).
+
+        ``sliced`` (world > 1): every rank feeds only ITS share of each batch -- chunk tensors of K * B / world elements,
+        laid out [K][B / world], the triples [rank * B / world, (rank + 1) * B / world) of every step -- and the ranks
+        all-gather the chunk on the device (one NCCL all-gather per chunk on its own communicator, off the step stream):
+        1 / world of the bytes cross each rank's PCIe link instead of the whole global batch."""
         n = self.K * self.B
+        N = self.dp_world if sliced else 1
+        if sliced and N > 1:
+            import torch.distributed as dist
+            assert self.B % N == 0
+            if getattr(self, "_gather_group", None) is None:
+                self._gather_group = dist.new_group(backend="nccl") if dist.get_backend() == "nccl" else dist.group.WORLD
+                self._slice_buf = [torch.empty(4 * (n // N), dtype=torch.int32, device=self.device) for _ in range(2)]
+                self._gather_buf = torch.empty(N * 4 * (n // N), dtype=torch.int32, device=self.device)
         self._join_side()
         if getattr(self, "_stage_coo", None) is None:
             i32 = dict(dtype=torch.int32, device=self.device)
@@ -684,10 +733,25 @@ class GloveEngine:
             with torch.cuda.stream(self._prep_stream):
                 if done[which] is not None:           # plan + staging set `which` belonged to chunk c-2
                     self._prep_stream.wait_event(done[which])
-                for dst, src in zip(self._stage_coo[which], chunks[c]):
-                    assert src.numel() == n and not src.is_cuda
-                    dst.copy_(src, non_blocking=True)
+                if sliced and N > 1:
+                    import torch.distributed as dist
+                    m = n // N
+                    sl = self._slice_buf[which]
+                    for j, src in enumerate(chunks[c]):           # H2D of this rank's share only
+                        assert src.numel() == m and not src.is_cuda
+                        sl[j * m:(j + 1) * m].copy_(src.view(torch.int32), non_blocking=True)
+                    dist.all_gather_into_tensor(self._gather_buf, sl, group=self._gather_group)
+                    from .parallel import assemble_chunk
+                    g = assemble_chunk(self._gather_buf, N, self.K, self.B // N)          # [array][step][rank][triple]
+                    for j, dst in enumerate(self._stage_coo[which]):
+                        dst.view(torch.int32).view(self.K, N, self.B // N).copy_(g[j])
+                else:
+                    for dst, src in zip(self._stage_coo[which], chunks[c]):
+                        assert src.numel() == n and not src.is_cuda
+                        dst.copy_(src, non_blocking=True)
                 row, col, ca, cb = self._stage_coo[which]
+                if self._label is not None:                        # balanced owner map: the kernels see labels
+                    row.copy_(self._label[row.long()]); col.copy_(self._label[col.long()])
                 check(lib.glove_prepare_batches_sharded(_ptr(self.plans[which]), _ptr(self.prep_ws), self.prep_ws.numel(),
                                                         _ptr(row), _ptr(col), _ptr(ca), _ptr(cb), n, _ptr(self._stage_idx), 0, 0,
                                                         first0 + c * self.K, self.K, self.B, self.V_global,
@@ -821,6 +885,8 @@ class GloveEngine:
         """[n, S] fp32: the packed plane-0 rows of the queries this rank owns, zero elsewhere (sum over ranks = all rows)."""
         self.flush()
         q = torch.as_tensor(np.ascontiguousarray(query_ids, np.int64)).to(self.device)
+        if self._label is not None:
+            q = self._label[q]
         out = torch.zeros(q.numel(), self.S, dtype=torch.float32, device=self.device)
         mine = (q % self.dp_world) == self.dp_rank
         rows = self.row_table.view(self.V, self.P, self.S)[:, 0, :]
@@ -844,6 +910,9 @@ class GloveEngine:
         gid = idx.to(torch.int64) * self.dp_world + self.dp_rank
         bad = (idx < 0) | (gid >= self.V_global)
         sim = torch.where(bad, torch.full_like(sim, float("-inf")), sim)
+        if self._unlabel is not None:                  # labels -> original ids BEFORE the merge (ties -> lower original id)
+            un = torch.from_numpy(self._unlabel).to(self.device)
+            gid = un[torch.where(bad, torch.zeros_like(gid), gid)]
         gid = torch.where(bad, torch.full_like(gid, -1), gid).to(torch.int32)
         if kk < k + 1:                                                   # same list width on every rank
             pad = k + 1 - kk

@@ -53,3 +53,47 @@ def shard_requests(ids, opposite_ids, rank, world):
     ids, opposite_ids = np.asarray(ids), np.asarray(opposite_ids)
     need = np.unique(opposite_ids[shard_owner(ids, world) == rank])
     return [need[shard_owner(need, world) == k] for k in range(world)]
+
+
+# ---- frequency-balanced owner map (GloveEngine.balance_owners) ---------------------------------------------------------
+def balanced_labels(freq, world, batch_size, nnz, hot=65536):
+    """Relabelling ``label[id]`` (owner = label % world, local row = label // world) that spreads the work of a Zipf
+    vocabulary evenly: the ``hot`` costliest ids are dealt greedily to the least loaded owner (cost of an id = expected
+    triples per step and side + ~3 triples' worth of fixed work when its row is touched), the tail round-robin; every
+    owner keeps exactly the rows it has under ``id % world``, and inside an owner ids keep their order (top-k ties still
+    break towards the lower original id).  Returns (label, unlabel, relative load of the hot part per owner)."""
+    freq = np.asarray(freq, np.float64)
+    V, N = len(freq), int(world)
+    t = freq * (float(batch_size) / (2.0 * max(int(nnz), 1)))
+    cost = t + 3.0 * (1.0 - np.exp(-t))
+    order = np.argsort(-cost, kind="stable")
+    cap = np.array([(V - o + N - 1) // N for o in range(N)], np.int64)
+    owner = np.full(V, -1, np.int64)
+    load = np.zeros(N)
+    n_hot = int(min(hot, V))
+    for i in order[:n_hot]:
+        o = int(np.argmin(np.where(cap > 0, load, np.inf)))
+        owner[i] = o
+        load[o] += cost[i]
+        cap[o] -= 1
+    rest = order[n_hot:]
+    if rest.size:
+        slots = np.concatenate([np.stack([np.arange(cap[o]), np.full(cap[o], o)], 1) for o in range(N)])
+        slots = slots[np.lexsort((slots[:, 1], slots[:, 0]))]
+        owner[rest] = slots[:, 1]
+    label = np.empty(V, np.int64)
+    for o in range(N):
+        ids = np.flatnonzero(owner == o)                     # ascending original id
+        label[ids] = np.arange(ids.size, dtype=np.int64) * N + o
+    unlabel = np.empty(V, np.int64)
+    unlabel[label] = np.arange(V, dtype=np.int64)
+    return label, unlabel, load / max(load.mean(), 1e-30)
+
+
+# ---- host-fed chunks, one share per rank (GloveEngine.train_chunks_from_host(sliced=True)) -----------------------------
+def assemble_chunk(gathered, world, n_steps, b_local):
+    """``gathered`` = all-gather over ranks of [4 arrays][n_steps][b_local] (every rank's share of each batch of a chunk) ->
+    view [4][n_steps][world][b_local]: array j of the chunk in batch order (global batch = the ranks' shares in rank
+    order).  Works on torch tensors and numpy arrays alike."""
+    g = gathered.reshape(world, 4, n_steps, b_local)
+    return g.permute(1, 2, 0, 3) if hasattr(g, "permute") else g.transpose(1, 2, 0, 3)

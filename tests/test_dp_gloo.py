@@ -189,3 +189,55 @@ def test_sharded_owner_computes_equals_single_process_oracle(tmp_path):
         assert np.max(np.abs(got - getattr(ref, k))) <= 1e-5 * np.max(np.abs(getattr(ref, k))), k
     assert abs(float(parts[0]["g"]) - float(ref.g)) < 1e-6 and float(parts[0]["g"]) == float(parts[1]["g"])
     assert all(int(p["sent"]) > 0 for p in parts)          # the exchange really moved remote rows
+
+
+def _gather_worker(rank, world, port, tmp):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from glove_tensorflow_b200 import parallel
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    K, Bl = 3, 5
+    B = Bl * world
+    # the global chunk every rank must end up with: array j, step k, in-batch position p -> 1000 j + 100 k + p
+    full = torch.tensor([[[1000 * j + 100 * k + p for p in range(B)] for k in range(K)] for j in range(4)], dtype=torch.int32)
+    mine = full.view(4, K, world, Bl)[:, :, rank, :].contiguous().view(-1)          # this rank's share, [4][K][Bl]
+    out = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(out, mine)
+    got = parallel.assemble_chunk(torch.cat(out), world, K, Bl).reshape(4, K, B)
+    assert torch.equal(got, full)
+    np.save(os.path.join(tmp, "gather%d.npy" % rank), got.numpy())
+    dist.destroy_process_group()
+
+
+def test_sliced_host_chunks_assemble_to_the_global_batch(tmp_path):
+    """train_chunks_from_host(sliced=True): every rank feeds 1/world of each batch; the all-gathered shares must assemble
+    to the global chunk in batch order (world_size 2, gloo)."""
+    import torch.multiprocessing as mp
+    port = 29500 + (os.getpid() % 2000) + 7
+    mp.spawn(_gather_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a, b = np.load(tmp_path / "gather0.npy"), np.load(tmp_path / "gather1.npy")
+    assert np.array_equal(a, b)
+
+
+def test_balanced_owner_labels():
+    """balance_owners: a permutation of the vocabulary that keeps every owner's row count, keeps id order inside an owner
+    and evens out a Zipf head that puts 1.5x the mean work on owner 0 under id % world."""
+    sys.path.insert(0, ROOT)
+    from glove_tensorflow_b200 import parallel
+    V, world, B = 50_003, 8, 8 * 65_536
+    rng = np.random.default_rng(3)
+    p = 1.0 / np.arange(1, V + 1)
+    ids = rng.choice(V, 1_000_000, p=p / p.sum())
+    freq = np.bincount(ids, minlength=V).astype(np.float64)
+    label, unlabel, rel = parallel.balanced_labels(freq, world, B, len(ids) // 2, hot=4096)
+    assert sorted(label.tolist()) == list(range(V)) and np.array_equal(unlabel[label], np.arange(V))
+    for o in range(world):
+        mine = np.flatnonzero(label % world == o)
+        assert len(mine) == len(range(o, V, world))                       # same rows per owner as id % world
+        assert np.all(np.diff(label[mine]) > 0)                            # id order kept inside the owner
+    naive = np.bincount(np.arange(V) % world, weights=freq, minlength=world)
+    bal = np.bincount(label % world, weights=freq, minlength=world)
+    assert naive.max() / naive.mean() > 1.3 and bal.max() / bal.mean() < 1.03, (naive / naive.mean(), bal / bal.mean())
+    assert rel.max() < 1.02

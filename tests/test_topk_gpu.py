@@ -100,6 +100,9 @@ def test_row_sharded_topk_matches_oracle(world, V, d, k, exact):
     engs = []
     for r in range(world):
         e = GloveEngine(V, d, batch_size=64, plan_steps=1, max_steps=4, dp_rank=r, dp_world=world, dp_mode="sharded")
+        if world >= 4:                                         # frequency-balanced owner map: ids are relabelled inside the engine
+            rng = np.random.default_rng(5)
+            e.balance_owners(rng.integers(0, V, 4000) // 3, rng.integers(0, V, 4000) // 2, hot=50)
         e.load_state(T, T[::-1].copy(), np.zeros(V, np.float32) + 0.3, np.zeros(V, np.float32))
         engs.append(e)
     q = np.array([7, V // 2, V - 1, 0, 11, 3, V - 2] + list(range(20, 20 + 90)), np.int32) % V
