@@ -62,6 +62,12 @@ struct StepParams {
     // peer gather (row-sharded tables, NVLink): peer_snap[side * kMaxShards + owner] = snapshot base of side `side` in the
     // step workspace of rank `owner` (peer-mapped device memory); nullptr = opposite rows come from the local snapshot
     const float *const *peer_snap;
+    // device-side synchronisation of the row-sharded step over peer memory (peer_gather == 3): see sync_kernel
+    int32_t *sync;               // local sync area: [0..7] stage-done epoch of rank r, [8..15] update-done epoch, [16] epoch
+    float *peer_scal;            // local [kMaxShards][4]: loss scalars of rank r for the current step
+    char *const *peer_base;      // [kMaxShards] workspace bases of the peers
+    int64_t sync_off, scal_off;  // byte offsets of the two areas inside a workspace (same layout on every rank)
+    int32_t dev_sync;
 };
 
 struct StepWs {
@@ -73,6 +79,10 @@ struct StepWs {
     int32_t *gap[2];
     unsigned long long *loss_acc;
     int32_t *item_ctr;
+    int32_t *sync;            // [32]
+    float *peer_scal;         // [kMaxShards][4]
+    char **peer_base;         // [kMaxShards]
+    float *own_scal;          // [4] this rank's loss sums of the current step (one-call sharded step)
     size_t bytes;
 };
 static inline int64_t snapshot_rows(int32_t B) { return (int64_t)B + B / 4 + 64; }  // room for padded shard blocks
@@ -91,6 +101,10 @@ static StepWs step_ws_view(void *base, int32_t B, int32_t d) {
     for (int s = 0; s < 2; ++s) w.gap[s] = (int32_t *)take(sizeof(int32_t) * (size_t)snapshot_rows(B));
     w.loss_acc = (unsigned long long *)take(sizeof(unsigned long long) * 6);
     w.item_ctr = (int32_t *)take(sizeof(int32_t) * 2);
+    w.sync = (int32_t *)take(sizeof(int32_t) * 32);
+    w.peer_scal = (float *)take(sizeof(float) * 4 * kMaxShards);
+    w.peer_base = (char **)take(sizeof(char *) * kMaxShards);
+    w.own_scal = (float *)take(sizeof(float) * 4);
     w.bytes = off;
     return w;
 }
@@ -846,6 +860,20 @@ __global__ void __launch_bounds__(256) exchange_kernel(const StepParams p, float
     }
 }
 
+// device-side synchronisation over peer memory (see sync_staged_kernel / finish_sync_kernel below)
+enum { SYNC_STAGED = 0, SYNC_UPDATED = 8, SYNC_EPOCH = 16 };
+__device__ __forceinline__ int ld_acquire_sys(const int32_t *p) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(int32_t *p, int v) {
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int32_t *peer_sync(const StepParams &p, int q) {
+    return reinterpret_cast<int32_t *>(p.peer_base[q] + p.sync_off);
+}
+
 // PULL (peer-mapped workspaces): every row this shard's work items need from another owner is read ONCE from that owner's
 // snapshot over NVLink and written to the same position of the local snapshot -- pack + all-to-all + unpack in one launch,
 // with no send / receive buffers.  One warp per row, two rows in flight per warp.
@@ -881,9 +909,20 @@ __global__ void __launch_bounds__(256) pull_kernel(const StepParams p, const flo
         src = peer_tab[(1 - s) * kMaxShards + q] + (int64_t)pos * p.S;
         dst = p.snap[1 - s] + (int64_t)pos * p.S;
     };
+    const int epoch = p.dev_sync ? p.sync[SYNC_EPOCH] : 0;
+    // device-side sync: a row is read only after its owner has announced its block of this step (polling local memory)
+    auto wait_owner = [&](int i) {
+        if (!p.dev_sync) return;
+        int b = 0;
+#pragma unroll
+        for (int c = 1; c < 2 * kMaxShards; ++c) b += (i >= first[c]);
+        while (ld_acquire_sys(p.sync + SYNC_STAGED + (b >> 1)) < epoch + 1) __nanosleep(32);
+    };
     for (int i = 2 * warp; i < total; i += 2 * nwarps) {
         const float *sa, *sb = nullptr;
         float *da, *db = nullptr;
+        wait_owner(i);
+        if (i + 1 < total) wait_owner(i + 1);
         locate(i, sa, da);
         const bool two = i + 1 < total;
         if (two) locate(i + 1, sb, db);
@@ -900,6 +939,54 @@ __global__ void __launch_bounds__(256) pull_kernel(const StepParams p, const flo
             if (f < S4) st4(da + 4 * f, va[r]);
             if (two && f < S4) st4(db + 4 * f, vb[r]);
         }
+    }
+}
+
+// ---- device-side synchronisation of the row-sharded step (peer_gather == 3) --------------------------------------------
+// Every rank's step workspace is peer-mapped (NVLink / NVSwitch), so the two synchronisation points of a step need neither
+// the host nor NCCL: a rank announces "my snapshot block of this step is staged" / "my update of this step is done, here
+// are my three loss sums" by writing an epoch number (and the sums) straight into every peer's workspace with
+// system-scope release stores, and waits by polling ITS OWN memory.  Epochs count steps since the peers were registered
+// (monotonic, identical on every rank), so a fast rank's next announcement can never be mistaken for the current one.
+//   stage(t) -> sync_kernel<STAGED> -> pull_kernel (waits, owner by owner, for the blocks it reads) -> update(t)
+//            -> finish_sync_kernel (announce + wait for all + sum the loss scalars in rank order + finish the step)
+// The "update done" wait also protects the snapshots: a rank restages (t+1) only after every peer has finished the
+// update -- and hence the pull -- of step t.  Four + one tiny launches, no host round trip: graph-capturable.
+// one thread per peer: announce that this rank's snapshot block of the current step is complete (launched behind the
+// stage kernel on the same stream: the kernel boundary orders its writes before this one)
+__global__ void sync_staged_kernel(const StepParams p) {
+    const int q = threadIdx.x;
+    if (q >= p.n_shards) return;
+    const int epoch = p.sync[SYNC_EPOCH];
+    __threadfence_system();
+    st_release_sys(peer_sync(p, q) + SYNC_STAGED + p.shard, epoch + 1);
+}
+
+// end of a row-sharded step without the host: publish this rank's loss sums to every peer, wait for everybody's, add them
+// in rank order (the same order on every rank: identical, deterministic totals) and finish the step
+__global__ void finish_sync_kernel(const StepParams p, const float *mine) {
+    int k, step;
+    const bool ok = batch_index(p, k, step);
+    const int q = threadIdx.x;
+    const int epoch = p.sync[SYNC_EPOCH];
+    __shared__ float tot[3];
+    if (q < p.n_shards) {
+        float *dst = reinterpret_cast<float *>(p.peer_base[q] + p.scal_off) + 4 * p.shard;
+        dst[0] = mine[0]; dst[1] = mine[1]; dst[2] = mine[2];
+        __threadfence_system();
+        st_release_sys(peer_sync(p, q) + SYNC_UPDATED + p.shard, epoch + 1);
+        while (ld_acquire_sys(p.sync + SYNC_UPDATED + q) < epoch + 1) __nanosleep(64);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+        for (int r = 0; r < p.n_shards; ++r) {
+            const volatile float *src = p.peer_scal + 4 * r;
+            a0 += src[0]; a1 += src[1]; a2 += src[2];
+        }
+        tot[0] = a0; tot[1] = a1; tot[2] = a2;
+        if (ok) finish_step(p, step, tot);
+        p.sync[SYNC_EPOCH] = epoch + 1;
     }
 }
 
@@ -977,6 +1064,9 @@ static int fill_params(const glove_step_args *a, StepParams &p, int mode) {
     }
     p.gap[0] = w.gap[0]; p.gap[1] = w.gap[1];
     p.loss_acc = w.loss_acc; p.item_ctr = w.item_ctr;
+    p.sync = w.sync; p.peer_scal = w.peer_scal; p.peer_base = w.peer_base;
+    p.sync_off = (char *)w.sync - (char *)a->workspace; p.scal_off = (char *)w.peer_scal - (char *)a->workspace;
+    p.dev_sync = (a->peer_gather == 3 && a->n_shards > 1) ? 1 : 0;
     p.l2b1 = replay_log2(a->beta1); p.l2b2 = replay_log2(a->beta2);
     p.l2_hints = tuning().l2_hints;
     p.grad_scalars = nullptr;
@@ -1097,6 +1187,10 @@ int glove_shard_set_peers(const glove_step_args *args, const void *const *peer_w
         for (int s = 0; s < 2; ++s) tab[s * kMaxShards + r] = pw.snap[s];
     }
     GLOVE_CHECK_CUDA(cudaMemcpyAsync(w.peer_tab, tab, sizeof(tab), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    const char *bases[kMaxShards] = {};
+    for (int r = 0; r < n_peers; ++r) bases[r] = (const char *)peer_workspaces[r];
+    GLOVE_CHECK_CUDA(cudaMemcpyAsync(w.peer_base, bases, sizeof(bases), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    GLOVE_CHECK_CUDA(cudaMemsetAsync(w.sync, 0, sizeof(int32_t) * 32, (cudaStream_t)stream));   // epochs restart with the registration
     GLOVE_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     return GLOVE_OK;
 }
@@ -1123,8 +1217,10 @@ int glove_step_graph_create(const glove_step_args *args, int32_t n_steps, glove_
     GLOVE_REQUIRE(out, "glove_step_graph_create: null output");
     *out = nullptr;
     GLOVE_REQUIRE(n_steps > 0 && n_steps <= 4096, "glove_step_graph_create: n_steps out of range");
+    const bool shard = args && args->n_shards > 1;     // row-sharded tables: the one-call step with device-side synchronisation
+    GLOVE_REQUIRE(!shard || args->peer_gather == 3, "glove_step_graph_create: row-sharded steps are capturable only with peer_gather == 3");
     StepParams p;
-    int rc = fill_params(args, p, MODE_TRAIN);
+    int rc = fill_params(args, p, shard ? MODE_SHARD : MODE_TRAIN);
     if (rc != GLOVE_OK) return rc;
     {   // size the grids (occupancy queries, environment) outside the capture
         StepParams q = p;
@@ -1138,7 +1234,7 @@ int glove_step_graph_create(const glove_step_args *args, int32_t n_steps, glove_
     cudaError_t e = cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
     if (e == cudaSuccess) {
-        for (int32_t i = 0; i < n_steps && rc == GLOVE_OK; ++i) rc = dispatch(p, cs);
+        for (int32_t i = 0; i < n_steps && rc == GLOVE_OK; ++i) rc = shard ? glove_shard_train_step(args, cs) : dispatch(p, cs);
         e = cudaStreamEndCapture(cs, &g->graph);
     }
     if (e == cudaSuccess && rc == GLOVE_OK) e = cudaGraphInstantiate(&g->exec, g->graph, 0);
@@ -1253,6 +1349,42 @@ int glove_shard_pull_step(const glove_step_args *args, void *stream) {
     pull_kernel<<<kNumSMs * 4, 256, 0, (cudaStream_t)stream>>>(p, w.peer_tab);
     GLOVE_CHECK_LAUNCH();
     return GLOVE_OK;
+}
+
+// device-side synchronisation (peer_gather == 3): the two announcements of a step as separate tiny launches (what the
+// one-call step below strings together; exposed for callers that drive the phases themselves, e.g. N shards emulated
+// on one GPU, where every shard must have announced before any shard waits)
+int glove_shard_signal_staged(const glove_step_args *args, void *stream) {
+    StepParams p;
+    int rc = fill_params(args, p, MODE_SHARD);
+    if (rc != GLOVE_OK) return rc;
+    GLOVE_REQUIRE(p.dev_sync, "glove_shard_signal_staged: needs peer_gather == 3 and registered peers");
+    sync_staged_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(p);
+    GLOVE_CHECK_LAUNCH();
+    return GLOVE_OK;
+}
+
+int glove_shard_finish_sync(const glove_step_args *args, const float *loss_scalars, void *stream) {
+    StepParams p;
+    int rc = fill_params(args, p, MODE_APPLY);
+    if (rc != GLOVE_OK) return rc;
+    GLOVE_REQUIRE(p.dev_sync && loss_scalars, "glove_shard_finish_sync: needs peer_gather == 3, registered peers and the scalar buffer");
+    finish_sync_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(p, loss_scalars);
+    GLOVE_CHECK_LAUNCH();
+    return GLOVE_OK;
+}
+
+// One row-sharded TRAIN step with no host involvement between its phases: stage -> announce -> pull -> update ->
+// announce + wait + finish (this rank's loss sums travel through a scratch slot of the workspace).
+int glove_shard_train_step(const glove_step_args *args, void *stream) {
+    GLOVE_REQUIRE(args && args->workspace, "glove_shard_train_step: null args");
+    float *scal = step_ws_view(args->workspace, args->B, args->d).own_scal;
+    int rc = glove_shard_stage_step(args, stream);
+    if (rc == GLOVE_OK) rc = glove_shard_signal_staged(args, stream);
+    if (rc == GLOVE_OK) rc = glove_shard_pull_step(args, stream);
+    if (rc == GLOVE_OK) rc = glove_shard_update_step(args, scal, stream);
+    if (rc == GLOVE_OK) rc = glove_shard_finish_sync(args, scal, stream);
+    return rc;
 }
 
 int glove_shard_unpack_step(const glove_step_args *args, const float *recv_buf, void *stream) {

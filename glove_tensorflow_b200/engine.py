@@ -457,12 +457,18 @@ class GloveEngine:
     def step_chunk_graph(self) -> int:
         """The K steps of the plan chunk that starts at the current step as ONE CUDA graph launch (captured once per plan
         buffer, valid for every later chunk that buffer serves).  Returns the number of steps enqueued (K), or 0 when the
-        graph path does not apply here (not at a chunk boundary, fewer than K steps left, sharded / data-parallel /
-        exact-replay modes that interleave other streams with the steps): the caller then falls back to ``step()``."""
+        graph path does not apply here (not at a chunk boundary, fewer than K steps left, data-parallel modes whose steps
+        need host-side collectives -- everything but 'peer-sync' sharding --, exact-replay modes that interleave other
+        streams with the steps): the caller then falls back to ``step()``."""
         s = self.host_step
-        if (s % self.K or s + self.K > self.max_steps or self.sharded or self.dp_world > 1 or self._plan_override is not None
+        shard_ok = self.sharded and self.shard_exchange == "peer-sync"
+        if (s % self.K or s + self.K > self.max_steps or (self.dp_world > 1 and not shard_ok) or self._plan_override is not None
                 or self.adam_mode in ("replay_exact", "dense")):
             return 0
+        if shard_ok:      # the host-side check of the padded block sizes, once per chunk instead of once per step
+            for t in range(s, s + self.K):
+                if self.dp_world * max(self._shard_info(t)[1]) > lib.glove_step_snapshot_rows(self.B):
+                    raise _lib.GloveError("shard blocks too unbalanced for the snapshot buffer")
         if self.sample_idx is not None and s + self.K - self.sample_idx_first > self.sample_idx.shape[0]:
             return 0
         which = self._plan_for(s)
@@ -540,21 +546,35 @@ class GloveEngine:
         check(lib.glove_shard_stage_step(ctypes.byref(self._args[which]), _stream()), "glove_shard_stage_step")
         return upad
 
-    def set_peer_workspaces(self, ptrs, direct: bool = False):
+    def set_peer_workspaces(self, ptrs, direct: bool = False, sync: bool = False):
         """Row-sharded tables over peer memory: ``ptrs[r]`` = base of rank r's step workspace as mapped in THIS process.
         From now on the requested snapshot rows are pulled from their owners by one kernel (``shard_exchange='peer'``) or,
-        with ``direct``, read by the update kernel itself while it computes (``'peer-direct'``); no NCCL data movement."""
+        with ``direct``, read by the update kernel itself while it computes (``'peer-direct'``); no NCCL data movement.
+        ``sync`` (``'peer-sync'``): the pull variant with the step's two synchronisation points done on the device through
+        the same peer memory (epoch flags + the loss sums): no barrier, no all-reduce, one C call (or one graph node
+        sequence) per step."""
         arr = (ctypes.c_void_p * len(ptrs))(*[int(p) for p in ptrs])
         check(lib.glove_shard_set_peers(ctypes.byref(self._args[0]), arr, len(ptrs), _stream()), "glove_shard_set_peers")
         for a in self._args:
-            a.peer_gather = 1 if direct else 2
-        self.shard_exchange = "peer-direct" if direct else "peer"
+            a.peer_gather = 1 if direct else (3 if sync else 2)
+        self.shard_exchange = "peer-direct" if direct else ("peer-sync" if sync else "peer")
+
+    def shard_signal_staged(self):
+        which = self._plan_for(self.host_step)
+        check(lib.glove_shard_signal_staged(ctypes.byref(self._args[which]), _stream()), "glove_shard_signal_staged")
+
+    def shard_finish_sync(self):
+        """peer-sync: announce this rank's loss sums, wait for every peer's, finish the step (device-side all-reduce)."""
+        which = self._plan_for(self.host_step)
+        check(lib.glove_shard_finish_sync(ctypes.byref(self._args[which]), _ptr(self._shard_scalars()), _stream()), "glove_shard_finish_sync")
+        self._after_step()
+        self.host_step += 1
 
     def shard_pull(self):
         which = self._plan_for(self.host_step)
         check(lib.glove_shard_pull_step(ctypes.byref(self._args[which]), _stream()), "glove_shard_pull_step")
 
-    def enable_peer_gather(self, group=None, direct: bool = False):
+    def enable_peer_gather(self, group=None, direct: bool = False, sync: bool = False):
         """Collective: moves the step workspace into symmetric (peer-mapped) memory and registers every rank's mapping."""
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
@@ -566,7 +586,7 @@ class GloveEngine:
         self._symm = symm_mem.rendezvous(ws, group if group is not None else dist.group.WORLD)
         self.step_ws = ws
         self._args = [self._make_args(i) for i in range(2)]
-        self.set_peer_workspaces(list(self._symm.buffer_ptrs), direct)
+        self.set_peer_workspaces(list(self._symm.buffer_ptrs), direct, sync)
         torch.cuda.synchronize()
         self._symm.barrier()
 
@@ -616,6 +636,18 @@ class GloveEngine:
         plan, one all_to_all_single with uneven splits); 'allgather' sends every block to everyone (equal-sized native);
         'peer' (after enable_peer_gather) moves nothing ahead of time: the update kernel reads remote rows over NVLink."""
         import torch.distributed as dist
+        if self.shard_exchange == "peer-sync":
+            # the whole step is device work: stage -> announce -> pull (waits owner by owner) -> update -> announce + wait +
+            # finish, with flags and loss sums exchanged through the peer-mapped workspaces
+            which = self._plan_for(self.host_step)
+            self._before_step(which)
+            own, upad = self._shard_info(self.host_step)
+            if self.dp_world * max(upad) > lib.glove_step_snapshot_rows(self.B):
+                raise _lib.GloveError("shard blocks too unbalanced for the snapshot buffer (%d x %d rows)" % (self.dp_world, max(upad)))
+            check(lib.glove_shard_train_step(ctypes.byref(self._args[which]), _stream()), "glove_shard_train_step")
+            self._after_step()
+            self.host_step += 1
+            return
         upad = self.shard_stage()
         N, r = self.dp_world, self.dp_rank
         if self.shard_exchange in ("peer", "peer-direct"):

@@ -148,7 +148,8 @@ typedef struct glove_step_args {
     /* row-sharded tables (n_shards > 1): this process holds the rows with id % n_shards == shard (local row id /
      * n_shards, V_local = ceil(V / n_shards)); the plan must come from glove_prepare_batches_sharded.  0 / 1 = not sharded. */
     int32_t n_shards, shard;
-    /* row-sharded tables with peer-mapped workspaces (glove_shard_set_peers): 2 = the requested rows are pulled into the
+    /* row-sharded tables with peer-mapped workspaces (glove_shard_set_peers): 3 = pull + device-side synchronisation (see
+     * glove_shard_train_step); 2 = the requested rows are pulled into the
      * local snapshot by glove_shard_pull_step; 1 = no pull, glove_shard_update_step gathers every opposite row straight
      * from its owner's workspace over NVLink; 0 = rows arrive through a collective (pack / unpack or all-gather). */
     int32_t peer_gather;
@@ -207,6 +208,16 @@ int glove_apply_step(const glove_step_args *args, const float *grad_rows, const 
  * it to the same position of the local snapshot (pack + all-to-all + unpack in one launch, no staging buffers);
  * peer_gather = 1: no pull; the update kernel loads each opposite row from the snapshot of its owner (position / padded
  * block size) while it computes -- one launch fewer, but a row is fetched once per triple instead of once per step. */
+/* peer_gather = 3: as 2, and the step synchronises ON THE DEVICE: a rank announces "my snapshot block is staged" / "my
+ * update is done, here are my loss sums" by writing an epoch (and the sums) into every peer's workspace with system-scope
+ * release stores and waits by polling its own memory -- no symmetric-memory barrier, no NCCL all-reduce, no host round
+ * trip between the phases (the pull waits owner by owner, the finish adds the ranks' sums in rank order).  A step is
+ *   glove_shard_train_step = stage -> glove_shard_signal_staged -> pull -> update -> glove_shard_finish_sync
+ * five launches, capturable by glove_step_graph_create.  The two announcements are exposed for callers that drive the phases
+ * themselves (N shards emulated on one GPU: every shard must have announced before any shard waits). */
+int glove_shard_signal_staged(const glove_step_args *args, void *stream);
+int glove_shard_finish_sync(const glove_step_args *args, const float *loss_scalars, void *stream);
+int glove_shard_train_step(const glove_step_args *args, void *stream);
 int glove_shard_pull_step(const glove_step_args *args, void *stream);
 int glove_shard_set_peers(const glove_step_args *args, const void *const *peer_workspaces, int32_t n_peers, void *stream);
 int glove_shard_stage_step(const glove_step_args *args, void *stream);
