@@ -411,7 +411,9 @@ def main():
             eng.step()
     torch.cuda.synchronize()
 
-    eng.use_graph = (not args.no_graph) and (N == 1 or (args.dp_mode == "sharded" and eng.shard_exchange == "peer-sync"))
+    # N > 1: the peer-sync step is graph-capturable too, but measured slower as a graph than launched step by step at N = 2
+    # (0.282 vs 0.254 ms/step: profiles/r02_scaling.md), so the multi-GPU arm launches its steps one C call at a time
+    eng.use_graph = (not args.no_graph) and N == 1
 
     def run_steps(n):
         """exactly n TRAIN steps: whole plan chunks as one CUDA graph launch each (N = 1), single launches otherwise"""

@@ -909,20 +909,21 @@ __global__ void __launch_bounds__(256) pull_kernel(const StepParams p, const flo
         src = peer_tab[(1 - s) * kMaxShards + q] + (int64_t)pos * p.S;
         dst = p.snap[1 - s] + (int64_t)pos * p.S;
     };
-    const int epoch = p.dev_sync ? p.sync[SYNC_EPOCH] : 0;
-    // device-side sync: a row is read only after its owner has announced its block of this step (polling local memory)
-    auto wait_owner = [&](int i) {
-        if (!p.dev_sync) return;
-        int b = 0;
-#pragma unroll
-        for (int c = 1; c < 2 * kMaxShards; ++c) b += (i >= first[c]);
-        while (ld_acquire_sys(p.sync + SYNC_STAGED + (b >> 1)) < epoch + 1) __nanosleep(32);
-    };
+    // device-side sync: rows are read only after their owners have announced their blocks of this step.  ONE thread per
+    // CTA polls (its own memory, system-scope acquire) and the CTA waits at a barrier: thousands of warps polling the same
+    // line delay the very store they are waiting for
+    if (p.dev_sync) {
+        if (threadIdx.x == 0) {
+            const int epoch = p.sync[SYNC_EPOCH];
+            for (int q = 0; q < N; ++q)
+                if (q != me && first[2 * q + 2] > first[2 * q])
+                    while (ld_acquire_sys(p.sync + SYNC_STAGED + q) < epoch + 1) __nanosleep(100);
+        }
+        __syncthreads();
+    }
     for (int i = 2 * warp; i < total; i += 2 * nwarps) {
         const float *sa, *sb = nullptr;
         float *da, *db = nullptr;
-        wait_owner(i);
-        if (i + 1 < total) wait_owner(i + 1);
         locate(i, sa, da);
         const bool two = i + 1 < total;
         if (two) locate(i + 1, sb, db);

@@ -13,6 +13,7 @@ PyTorch is used only for device memory, streams and ``torch.distributed`` plumbi
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Dict, Optional
 
 import numpy as np
