@@ -305,7 +305,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true",
                     help="launch every step's kernels one by one instead of one CUDA graph per plan chunk (N=1)")
     ap.add_argument("--no-topk", action="store_true", help="skip the cfg5 top-k record of the default N=1 run")
-    ap.add_argument("--shard-exchange", default="peer-sync", choices=["alltoall", "allgather", "peer", "peer-direct", "peer-sync"],
+    ap.add_argument("--shard-exchange", default="peer-push", choices=["alltoall", "allgather", "peer", "peer-direct", "peer-sync", "peer-push"],
                     help="N>1, row-sharded tables: how the snapshot rows reach the shards that need them (peer = one pull "
                          "kernel over NVLink peer memory; falls back to alltoall when symmetric memory is unavailable)")
     ap.add_argument("--dp-mode", default="sharded", choices=["sharded", "replicated"],
@@ -389,7 +389,9 @@ def main():
     eng.shard_exchange = args.shard_exchange
     if args.shard_exchange.startswith("peer") and world > 1 and args.dp_mode == "sharded":
         try:
-            eng.enable_peer_gather(direct=args.shard_exchange == "peer-direct", sync=args.shard_exchange == "peer-sync")
+            eng.enable_peer_gather(direct=args.shard_exchange == "peer-direct", sync=args.shard_exchange == "peer-sync",
+                                   push=args.shard_exchange == "peer-push")
+            args.shard_exchange = eng.shard_exchange
         except Exception as exc:   # no peer-mapped memory on this box: same exchange through NCCL
             print("bench: peer memory unavailable (%s); using the all-to-all exchange" % exc, file=sys.stderr)
             args.shard_exchange = eng.shard_exchange = "alltoall"
@@ -566,7 +568,7 @@ def main():
     if N == 1:
         per_step_launches = 2
     elif args.dp_mode == "sharded":
-        per_step_launches = 3 + {"peer": 1, "peer-direct": 0, "alltoall": 2, "allgather": 0, "peer-sync": 2}[args.shard_exchange]
+        per_step_launches = 3 + {"peer": 1, "peer-direct": 0, "alltoall": 2, "allgather": 0, "peer-sync": 2, "peer-push": 2}[args.shard_exchange]
     else:
         per_step_launches = 4
     per_step_launches += 2 if args.adam_mode in ("replay_exact", "dense") else 0

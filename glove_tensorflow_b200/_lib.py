@@ -76,6 +76,7 @@ SIGNATURES = {
     "glove_shard_set_peers": (ctypes.c_int, [ctypes.POINTER(StepArgs), ctypes.POINTER(c_void), c_i32, c_void]),
     "glove_shard_pull_step": (ctypes.c_int, [ctypes.POINTER(StepArgs), c_void]),
     "glove_shard_signal_staged": (ctypes.c_int, [ctypes.POINTER(StepArgs), c_void]),
+    "glove_shard_wait_staged": (ctypes.c_int, [ctypes.POINTER(StepArgs), c_void]),
     "glove_shard_finish_sync": (ctypes.c_int, [ctypes.POINTER(StepArgs), c_void, c_void]),
     "glove_shard_train_step": (ctypes.c_int, [ctypes.POINTER(StepArgs), c_void]),
     "glove_shard_stage_step": (ctypes.c_int, [ctypes.POINTER(StepArgs), c_void]),

@@ -274,6 +274,20 @@ __global__ void need_compact_kernel(int32_t N, uint32_t posmask, const uint32_t 
         if (q == N - 1) *n_uniq = excl[q] + flag[q];
     }
 }
+// seg_push of the OPPOSITE side from the request lists of this side: block (k, r) walks the rows shard r needs in batch k
+// and sets bit r on the segment that owns each of them (rows r owns itself are not requests)
+__global__ void push_mask_kernel(int32_t n_shards, PlanSide need, PlanSide target) {
+    const int32_t k = blockIdx.x / n_shards, r = blockIdx.x % n_shards;
+    constexpr int W = kMaxShards + 1;
+    const int32_t *off = need.need_off + ((int64_t)k * kMaxShards + r) * W;
+    const int32_t upad = max(target.b_upad[k], 1);
+    for (int32_t e = off[0] + threadIdx.x; e < off[n_shards]; e += blockDim.x) {
+        const int32_t pos = need.need_pos[e], owner = pos / upad;
+        if (owner == r || owner >= n_shards) continue;
+        const int32_t g = target.b_seg[k] + target.b_own[k * W + owner] + (pos - owner * upad);
+        atomicOr(target.seg_push + g, 1 << r);
+    }
+}
 __global__ void need_offsets_kernel(int32_t K, int32_t n_shards, int pbits, const uint32_t *__restrict__ uniq,
                                     const int32_t *__restrict__ n_uniq, const int32_t *__restrict__ upad_other, int32_t *need_off) {
     const int32_t total = K * kMaxShards * (kMaxShards + 1);
@@ -415,6 +429,9 @@ int glove_prepare_batches_sharded(void *plan, void *workspace, size_t workspace_
             need_offsets_kernel<<<(K * kMaxShards * (kMaxShards + 1) + 255) / 256, 256, 0, stream>>>(
                 K, n_shards, pbits, ps.keys_in, ps.f_long, pv.side[1 - s].b_upad, pv.side[s].need_off);
         }
+        // the same lists seen from the owners: which shards does each staged row have to be pushed to
+        for (int s = 0; s < 2; ++s) GLOVE_CHECK_CUDA(cudaMemsetAsync(pv.side[s].seg_push, 0, sizeof(int32_t) * (size_t)N, stream));
+        for (int s = 0; s < 2; ++s) push_mask_kernel<<<K * n_shards, 256, 0, stream>>>(n_shards, pv.side[s], pv.side[1 - s]);
         GLOVE_CHECK_LAUNCH();
     }
     return GLOVE_OK;

@@ -68,6 +68,7 @@ struct StepParams {
     char *const *peer_base;      // [kMaxShards] workspace bases of the peers
     int64_t sync_off, scal_off;  // byte offsets of the two areas inside a workspace (same layout on every rank)
     int32_t dev_sync;
+    float *const *push_snap;     // peer_gather == 4: [2][kMaxShards] snapshot bases of the peers the stage pushes rows to
 };
 
 struct StepWs {
@@ -387,6 +388,16 @@ __global__ void __launch_bounds__(256, 2) stage_closed_kernel(const StepParams p
         const int pos = (sd ? pos_c : pos_r) + j;
         store_row<NV>(p.snap[sd] + (int64_t)pos * p.S, x, lane, S4, pol_keep);
         if (lane == 0) p.gap[sd][pos] = gap;
+        if (p.push_snap) {
+            // fused exchange: the row goes straight from these registers into the snapshot of every shard whose work items
+            // read it (request mask from the plan), as posted NVLink writes that overlap the staging of the next rows
+            unsigned mask = (unsigned)__ldg(p.side[sd].seg_push + (sd ? g_c + (w - U0) : g_r + w));
+            while (mask) {
+                const int r = __ffs(mask) - 1;
+                mask &= mask - 1;
+                store_row<NV>(p.push_snap[sd * kMaxShards + r] + (int64_t)pos * p.S, x, lane, S4);
+            }
+        }
     }
 }
 
@@ -963,6 +974,14 @@ __global__ void sync_staged_kernel(const StepParams p) {
     st_release_sys(peer_sync(p, q) + SYNC_STAGED + p.shard, epoch + 1);
 }
 
+// peer_gather == 4 (rows are pushed by their owners' stage kernels): wait until every owner has announced
+__global__ void wait_staged_kernel(const StepParams p) {
+    const int q = threadIdx.x;
+    if (q >= p.n_shards) return;
+    const int epoch = p.sync[SYNC_EPOCH];
+    while (ld_acquire_sys(p.sync + SYNC_STAGED + q) < epoch + 1) __nanosleep(64);
+}
+
 // end of a row-sharded step without the host: publish this rank's loss sums to every peer, wait for everybody's, add them
 // in rank order (the same order on every rank: identical, deterministic totals) and finish the step
 __global__ void finish_sync_kernel(const StepParams p, const float *mine) {
@@ -1067,7 +1086,8 @@ static int fill_params(const glove_step_args *a, StepParams &p, int mode) {
     p.loss_acc = w.loss_acc; p.item_ctr = w.item_ctr;
     p.sync = w.sync; p.peer_scal = w.peer_scal; p.peer_base = w.peer_base;
     p.sync_off = (char *)w.sync - (char *)a->workspace; p.scal_off = (char *)w.peer_scal - (char *)a->workspace;
-    p.dev_sync = (a->peer_gather == 3 && a->n_shards > 1) ? 1 : 0;
+    p.dev_sync = (a->peer_gather >= 3 && a->n_shards > 1) ? 1 : 0;
+    p.push_snap = (a->peer_gather == 4 && a->n_shards > 1) ? (float *const *)w.peer_tab : nullptr;
     p.l2b1 = replay_log2(a->beta1); p.l2b2 = replay_log2(a->beta2);
     p.l2_hints = tuning().l2_hints;
     p.grad_scalars = nullptr;
@@ -1219,7 +1239,7 @@ int glove_step_graph_create(const glove_step_args *args, int32_t n_steps, glove_
     *out = nullptr;
     GLOVE_REQUIRE(n_steps > 0 && n_steps <= 4096, "glove_step_graph_create: n_steps out of range");
     const bool shard = args && args->n_shards > 1;     // row-sharded tables: the one-call step with device-side synchronisation
-    GLOVE_REQUIRE(!shard || args->peer_gather == 3, "glove_step_graph_create: row-sharded steps are capturable only with peer_gather == 3");
+    GLOVE_REQUIRE(!shard || args->peer_gather >= 3, "glove_step_graph_create: row-sharded steps are capturable only with peer_gather >= 3");
     StepParams p;
     int rc = fill_params(args, p, shard ? MODE_SHARD : MODE_TRAIN);
     if (rc != GLOVE_OK) return rc;
@@ -1359,8 +1379,18 @@ int glove_shard_signal_staged(const glove_step_args *args, void *stream) {
     StepParams p;
     int rc = fill_params(args, p, MODE_SHARD);
     if (rc != GLOVE_OK) return rc;
-    GLOVE_REQUIRE(p.dev_sync, "glove_shard_signal_staged: needs peer_gather == 3 and registered peers");
+    GLOVE_REQUIRE(p.dev_sync, "glove_shard_signal_staged: needs peer_gather >= 3 and registered peers");
     sync_staged_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(p);
+    GLOVE_CHECK_LAUNCH();
+    return GLOVE_OK;
+}
+
+int glove_shard_wait_staged(const glove_step_args *args, void *stream) {
+    StepParams p;
+    int rc = fill_params(args, p, MODE_SHARD);
+    if (rc != GLOVE_OK) return rc;
+    GLOVE_REQUIRE(p.dev_sync, "glove_shard_wait_staged: needs peer_gather >= 3 and registered peers");
+    wait_staged_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(p);
     GLOVE_CHECK_LAUNCH();
     return GLOVE_OK;
 }
@@ -1369,7 +1399,7 @@ int glove_shard_finish_sync(const glove_step_args *args, const float *loss_scala
     StepParams p;
     int rc = fill_params(args, p, MODE_APPLY);
     if (rc != GLOVE_OK) return rc;
-    GLOVE_REQUIRE(p.dev_sync && loss_scalars, "glove_shard_finish_sync: needs peer_gather == 3, registered peers and the scalar buffer");
+    GLOVE_REQUIRE(p.dev_sync && loss_scalars, "glove_shard_finish_sync: needs peer_gather >= 3, registered peers and the scalar buffer");
     finish_sync_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(p, loss_scalars);
     GLOVE_CHECK_LAUNCH();
     return GLOVE_OK;
@@ -1382,7 +1412,7 @@ int glove_shard_train_step(const glove_step_args *args, void *stream) {
     float *scal = step_ws_view(args->workspace, args->B, args->d).own_scal;
     int rc = glove_shard_stage_step(args, stream);
     if (rc == GLOVE_OK) rc = glove_shard_signal_staged(args, stream);
-    if (rc == GLOVE_OK) rc = glove_shard_pull_step(args, stream);
+    if (rc == GLOVE_OK) rc = args->peer_gather == 4 ? glove_shard_wait_staged(args, stream) : glove_shard_pull_step(args, stream);
     if (rc == GLOVE_OK) rc = glove_shard_update_step(args, scal, stream);
     if (rc == GLOVE_OK) rc = glove_shard_finish_sync(args, scal, stream);
     return rc;

@@ -462,7 +462,7 @@ class GloveEngine:
         need host-side collectives -- everything but 'peer-sync' sharding --, exact-replay modes that interleave other
         streams with the steps): the caller then falls back to ``step()``."""
         s = self.host_step
-        shard_ok = self.sharded and self.shard_exchange == "peer-sync"
+        shard_ok = self.sharded and self.shard_exchange in ("peer-sync", "peer-push")
         if (s % self.K or s + self.K > self.max_steps or (self.dp_world > 1 and not shard_ok) or self._plan_override is not None
                 or self.adam_mode in ("replay_exact", "dense")):
             return 0
@@ -547,7 +547,7 @@ class GloveEngine:
         check(lib.glove_shard_stage_step(ctypes.byref(self._args[which]), _stream()), "glove_shard_stage_step")
         return upad
 
-    def set_peer_workspaces(self, ptrs, direct: bool = False, sync: bool = False):
+    def set_peer_workspaces(self, ptrs, direct: bool = False, sync: bool = False, push: bool = False):
         """Row-sharded tables over peer memory: ``ptrs[r]`` = base of rank r's step workspace as mapped in THIS process.
         From now on the requested snapshot rows are pulled from their owners by one kernel (``shard_exchange='peer'``) or,
         with ``direct``, read by the update kernel itself while it computes (``'peer-direct'``); no NCCL data movement.
@@ -556,9 +556,16 @@ class GloveEngine:
         sequence) per step."""
         arr = (ctypes.c_void_p * len(ptrs))(*[int(p) for p in ptrs])
         check(lib.glove_shard_set_peers(ctypes.byref(self._args[0]), arr, len(ptrs), _stream()), "glove_shard_set_peers")
+        # 'peer-push' (the stage kernel writes each row straight into the snapshots of the shards that read it; needs the
+        # closed-form Adam stage) falls back to the pull for the other optimizers
+        push = push and self.optimizer == "Adam" and self.adam_mode == "replay"
         for a in self._args:
-            a.peer_gather = 1 if direct else (3 if sync else 2)
-        self.shard_exchange = "peer-direct" if direct else ("peer-sync" if sync else "peer")
+            a.peer_gather = 1 if direct else (4 if push else 3 if sync else 2)
+        self.shard_exchange = "peer-direct" if direct else ("peer-push" if push else "peer-sync" if sync else "peer")
+
+    def shard_wait_staged(self):
+        which = self._plan_for(self.host_step)
+        check(lib.glove_shard_wait_staged(ctypes.byref(self._args[which]), _stream()), "glove_shard_wait_staged")
 
     def shard_signal_staged(self):
         which = self._plan_for(self.host_step)
@@ -575,7 +582,7 @@ class GloveEngine:
         which = self._plan_for(self.host_step)
         check(lib.glove_shard_pull_step(ctypes.byref(self._args[which]), _stream()), "glove_shard_pull_step")
 
-    def enable_peer_gather(self, group=None, direct: bool = False, sync: bool = False):
+    def enable_peer_gather(self, group=None, direct: bool = False, sync: bool = False, push: bool = False):
         """Collective: moves the step workspace into symmetric (peer-mapped) memory and registers every rank's mapping."""
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
@@ -587,7 +594,7 @@ class GloveEngine:
         self._symm = symm_mem.rendezvous(ws, group if group is not None else dist.group.WORLD)
         self.step_ws = ws
         self._args = [self._make_args(i) for i in range(2)]
-        self.set_peer_workspaces(list(self._symm.buffer_ptrs), direct, sync)
+        self.set_peer_workspaces(list(self._symm.buffer_ptrs), direct, sync or push, push)
         torch.cuda.synchronize()
         self._symm.barrier()
 
@@ -637,7 +644,7 @@ class GloveEngine:
         plan, one all_to_all_single with uneven splits); 'allgather' sends every block to everyone (equal-sized native);
         'peer' (after enable_peer_gather) moves nothing ahead of time: the update kernel reads remote rows over NVLink."""
         import torch.distributed as dist
-        if self.shard_exchange == "peer-sync":
+        if self.shard_exchange in ("peer-sync", "peer-push"):
             # the whole step is device work: stage -> announce -> pull (waits owner by owner) -> update -> announce + wait +
             # finish, with flags and loss sums exchanged through the peer-mapped workspaces
             which = self._plan_for(self.host_step)

@@ -148,8 +148,8 @@ typedef struct glove_step_args {
     /* row-sharded tables (n_shards > 1): this process holds the rows with id % n_shards == shard (local row id /
      * n_shards, V_local = ceil(V / n_shards)); the plan must come from glove_prepare_batches_sharded.  0 / 1 = not sharded. */
     int32_t n_shards, shard;
-    /* row-sharded tables with peer-mapped workspaces (glove_shard_set_peers): 3 = pull + device-side synchronisation (see
-     * glove_shard_train_step); 2 = the requested rows are pulled into the
+    /* row-sharded tables with peer-mapped workspaces (glove_shard_set_peers): 4 = rows pushed by the owners' stage kernels +
+     * device-side synchronisation; 3 = pull + device-side synchronisation (see glove_shard_train_step); 2 = the requested rows are pulled into the
      * local snapshot by glove_shard_pull_step; 1 = no pull, glove_shard_update_step gathers every opposite row straight
      * from its owner's workspace over NVLink; 0 = rows arrive through a collective (pack / unpack or all-gather). */
     int32_t peer_gather;
@@ -215,6 +215,12 @@ int glove_apply_step(const glove_step_args *args, const float *grad_rows, const 
  *   glove_shard_train_step = stage -> glove_shard_signal_staged -> pull -> update -> glove_shard_finish_sync
  * five launches, capturable by glove_step_graph_create.  The two announcements are exposed for callers that drive the phases
  * themselves (N shards emulated on one GPU: every shard must have announced before any shard waits). */
+/* peer_gather = 4 (Adam with the closed-form replay): as 3, and the exchange is FUSED INTO THE STAGE: an owner writes every
+ * row it stages straight from registers into the snapshot of each shard whose work items read it (request mask per segment,
+ * built at plan time) -- posted NVLink writes that overlap the staging of the following rows; there is no pull kernel,
+ * glove_shard_wait_staged only waits for the owners' announcements:
+ *   glove_shard_train_step = stage(+push) -> glove_shard_signal_staged -> glove_shard_wait_staged -> update -> finish_sync */
+int glove_shard_wait_staged(const glove_step_args *args, void *stream);
 int glove_shard_signal_staged(const glove_step_args *args, void *stream);
 int glove_shard_finish_sync(const glove_step_args *args, const float *loss_scalars, void *stream);
 int glove_shard_train_step(const glove_step_args *args, void *stream);

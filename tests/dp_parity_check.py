@@ -24,7 +24,7 @@ def main():
     from conftest import make_coo
     from glove_tensorflow_b200.engine import GloveEngine
     from oracle import c_oracle, glove_oracle as o
-    exchange = sys.argv[1] if len(sys.argv) > 1 else "peer-sync"
+    exchange = sys.argv[1] if len(sys.argv) > 1 else "peer-push"
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", rank)))
     torch.cuda.set_device(dev)
@@ -39,12 +39,12 @@ def main():
                       dp_rank=rank, dp_world=world, dp_mode="sharded")
     eng.shard_exchange = exchange
     if exchange.startswith("peer"):
-        eng.enable_peer_gather(direct=exchange == "peer-direct", sync=exchange == "peer-sync")
+        eng.enable_peer_gather(direct=exchange == "peer-direct", sync=exchange == "peer-sync", push=exchange == "peer-push")
     eng.balance_owners(coo["row"], coo["col"], hot=2048)
     eng.load_state(st.R, st.C, st.rb, st.cb, st.g)
     eng.set_coo(coo["row"], coo["col"], coo["target"], coo["weight"])
     eng.set_batches(batches)
-    eng.use_graph = exchange == "peer-sync"
+    eng.use_graph = exchange in ("peer-sync", "peer-push") and len(sys.argv) > 2 and sys.argv[2] == "graph"
     losses = eng.train(steps)
     got = eng.get_state()
     ids = torch.from_numpy(eng.owned_ids()).to(dev)

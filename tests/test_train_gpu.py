@@ -298,7 +298,7 @@ def test_overlap_streams_do_not_change_results(adam_mode):
         assert np.array_equal(out[0][1][k], out[1][1][k]), k
 
 
-@pytest.mark.parametrize("exchange", ["alltoall", "allgather", "peer", "peer-direct", "peer-sync"])
+@pytest.mark.parametrize("exchange", ["alltoall", "allgather", "peer", "peer-direct", "peer-sync", "peer-push"])
 @pytest.mark.parametrize("world,adam_mode,optimizer,V", [(2, "replay", "Adam", 601), (4, "replay", "Adam", 1000),
                                                          (3, "lazy", "Adam", 333), (2, "replay", "Adagrad", 64),
                                                          (8, "replay", "Adam", 5000)])
@@ -327,7 +327,8 @@ def test_row_sharded_tables_on_one_gpu(world, adam_mode, optimizer, V, exchange)
         engs.append(e)
     if exchange.startswith("peer"):                                # on one GPU every "peer" workspace is plain device memory
         for e in engs:
-            e.set_peer_workspaces([x.step_ws.data_ptr() for x in engs], direct=exchange == "peer-direct", sync=exchange == "peer-sync")
+            e.set_peer_workspaces([x.step_ws.data_ptr() for x in engs], direct=exchange == "peer-direct",
+                                  sync=exchange in ("peer-sync", "peer-push"), push=exchange == "peer-push")
     side_streams = [torch.cuda.Stream() for _ in engs]
     losses = []
     for s in range(steps):
@@ -336,11 +337,14 @@ def test_row_sharded_tables_on_one_gpu(world, adam_mode, optimizer, V, exchange)
         torch.cuda.synchronize()
         if exchange == "peer-direct":
             pass                                                   # the update kernels read each other's snapshots directly
-        elif exchange == "peer-sync":
+        elif exchange in ("peer-sync", "peer-push"):
             for e in engs:
                 e.shard_signal_staged()                            # every shard announces its block ...
-            for e in engs:
-                e.shard_pull()                                     # ... before any pull waits for the owners' announcements
+            for e in engs:                                         # ... before any shard waits for the owners' announcements
+                if e.shard_exchange == "peer-push":
+                    e.shard_wait_staged()                          # (the stage kernels have pushed the rows already)
+                else:
+                    e.shard_pull()
         elif exchange == "peer":
             for e in engs:
                 e.shard_pull()                                     # one kernel: requested rows, owner's snapshot -> mine
@@ -367,7 +371,7 @@ def test_row_sharded_tables_on_one_gpu(world, adam_mode, optimizer, V, exchange)
         for e in engs:
             e.shard_update()                                   # owner-computes: no gradient exchange
         torch.cuda.synchronize()
-        if exchange == "peer-sync":
+        if exchange in ("peer-sync", "peer-push"):
             # device-side all-reduce: every shard's finish kernel announces its sums, then waits for all the others --
             # the kernels must be able to run side by side, so each goes on its own stream (they are one warp each)
             for e, st_ in zip(engs, side_streams):
