@@ -9,14 +9,13 @@ torch.cuda.set_device(dev); dist.init_process_group("nccl", device_id=dev)
 V, d, Bl = 400000, 300, 65536; B = Bl * world
 row, col, t, w = bench.gen_coo_device(V, 1 << 24, 1234, dev)
 eng = GloveEngine(V, d, batch_size=B, plan_steps=16, max_steps=8192, device=dev, dp_rank=rank, dp_world=world, dp_mode="sharded")
-eng.enable_peer_gather(sync=True)
+eng.enable_peer_gather(sync=True, push=True)
 eng.balance_owners(row, col); eng.init_uniform(1); eng.set_coo(row, col, t, w, shuffle_key=1)
 for _ in range(400): eng.step()
 n = 128
-for name, ex, var, graph in (("peer", "peer", "0", False), ("peer-sync", "peer-sync", "0", False), ("peer-sync graph", "peer-sync", "0", True)):
-    os.environ["GLOVE_SYNC_VARIANT"] = var
+for name, ex, graph in (("peer", "peer", False), ("peer-sync", "peer-sync", False), ("peer-push", "peer-push", False), ("peer-push graph", "peer-push", True)):
     eng.shard_exchange = ex
-    for a in eng._args: a.peer_gather = 3 if ex == "peer-sync" else 2
+    for a in eng._args: a.peer_gather = {"peer": 2, "peer-sync": 3, "peer-push": 4}[ex]
     eng.use_graph = graph
     eng._graphs = [None, None] if not graph else eng._graphs
     while eng.host_step % eng.K: eng.step()
