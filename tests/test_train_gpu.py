@@ -132,6 +132,41 @@ def test_heavy_hitters_long_segments():
     assert counts[2] > counts[0] and counts[3] > counts[1]  # more items than segments => split segments exist
 
 
+def test_split_segment_protocol_stress():
+    """compute-sanitizer is closed on the GPU pool (racecheck / memcheck cannot be run), so the hand-rolled synchronisation
+    of the update kernel -- partial sums of split segments published with __threadfence + chunk / segment tickets, work
+    items handed out by atomic counters in a timing-dependent order, fixed-point loss atomics, the last-CTA ticket -- is
+    hammered instead: 60 steps at B = 16,384 with 60 % of every batch on one row id and one col id (~300 pieces, 20 chunks
+    and a three-level combine per side and step, d = 300 so a row spans all three float4 chunks of a lane), three
+    independent runs.  A lost update, a stale partial or a double count shows up as a difference between runs or against the
+    oracle; every run must be bit-identical to the others and within tolerance of the C oracle."""
+    from glove_tensorflow_b200.engine import GloveEngine
+    from oracle import c_oracle
+    V, d, B, steps = 2000, 300, 16384, 60
+    coo = make_coo(V, 200_000, 91, hot=0.6)
+    batches = np.random.default_rng(92).integers(0, 200_000, (steps, B))
+    st = o.init_state(V, d, 93)
+    runs = []
+    for _ in range(3):
+        eng = GloveEngine(V, d, learning_rate=0.01, batch_size=B, plan_steps=6, max_steps=steps + 8)
+        eng.load_state(st.R, st.C, st.rb, st.cb, st.g)
+        eng.set_coo(coo["row"], coo["col"], coo["target"], coo["weight"])
+        eng.set_batches(batches)
+        losses = eng.train(steps)
+        runs.append((losses, eng.get_state(slots=True)))
+        c = eng.batch_counts(steps - 1)
+        assert c[2] - c[0] > 250 and c[3] - c[1] > 250        # hundreds of pieces per side
+    for losses, state in runs[1:]:
+        assert np.array_equal(losses, runs[0][0])
+        for k in state:
+            assert np.array_equal(np.asarray(state[k]), np.asarray(runs[0][1][k])), k
+    c32 = c_oracle.COracle(st.R, st.C, st.rb, st.cb)
+    l32 = c32.train(coo, batches, learning_rate=0.01)
+    assert np.max(np.abs(runs[0][0] - l32) / np.abs(l32)) < RTOL
+    for k in ("R", "C", "rb", "cb"):
+        assert _rel(runs[0][1][k], getattr(c32, k)) < 3e-5, k
+
+
 def test_lazy_mode_matches_lazy_oracle():
     ref, rl, got, l, _ = _run_pair(2000, 32, 256, 40, adam_mode="lazy", zipf=False)
     _assert_close(ref, rl, got, l)
