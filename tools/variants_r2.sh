@@ -1,3 +1,8 @@
-timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
-for G in "" "--no-graph"; do timeout 200 python bench.py --workload text8 --batch 1024 --plan-steps 64 --steps 4096 --warmup 128 --pretrain-steps 1024 --no-topk --no-cpu-baseline --no-e2e $G < /dev/null > gpurun_out/r2_b1024$G.json 2>gpurun_out/r2_b1024$G.err; python tools/benchline.py "b1024$G" gpurun_out/r2_b1024$G.json; done
-bash tools/ncu_r2.sh
+timeout 100 python tools/state_hash.py 20000 300 8192 40 Adam 2>&1 | tail -1
+timeout 100 python tools/state_hash.py 3000 100 1024 20 Adagrad 2>&1 | tail -1
+timeout 400 python -m pytest tests/test_train_gpu.py tests/test_pipeline_gpu.py tests/test_contract_configs_gpu.py -x -q -k "not topk" 2>&1 | tail -3
+B="python bench.py --steps 200 --warmup 20 --no-topk --no-cpu-baseline --no-e2e"
+pick() { python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$1', round(d['ms_per_step']*1e3,1), 'us  stage', round(d['roofline']['kernels_ms']['stage']*1e3,1), 'update', round(d['roofline']['kernels_ms']['update']*1e3,1), 'frac', round(d['roofline']['frac'],3), 'loss', d['final_loss'])"; }
+timeout 120 $B < /dev/null | pick pipe2
+GLOVE_UPDATE_CTAS=3 timeout 120 $B < /dev/null | pick pipe2_c3
+timeout 120 python bench.py --workload text8 --steps 192 --warmup 16 --no-topk --no-cpu-baseline --no-e2e < /dev/null | pick text8
