@@ -279,6 +279,15 @@ class GloveEngine:
         self.flush()
         return self._unpack(self.row_table, 0)[0]
 
+    def bias_vectors(self):
+        """(row biases, col biases) of the rows held here as numpy [V] (after replaying lazy Adam state): what the
+        reference's summaries histogram [ref src/models/model_utils.py:116-118]."""
+        self.flush()
+        out = []
+        for side, t in enumerate((self.row_table, self.col_table)):
+            out.append(t.view(self.V, self.P, self.S)[:, 0, self.d + side].cpu().numpy())
+        return out[0], out[1]
+
     def _join_side(self):
         """Order the current stream after everything in flight on the side streams (catch-up, plan prefetch): required
         before the tables are read or written from outside the step sequence."""

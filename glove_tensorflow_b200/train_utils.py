@@ -116,22 +116,41 @@ def train_and_evaluate(engine, train_steps, job_dir, eval_fn=None, save_checkpoi
     """tf.estimator.train_and_evaluate for the local case (ref src/models/estimator.py:95): train to ``train_steps``
     (``max_steps`` semantics: counts steps already in the checkpoint), checkpoint + evaluate every <= 300 s and at the
     end.  Returns the list of (step, metrics)."""
+    from .summary import EventWriter
     history = []
     last_ckpt = time.time()
     t0, s0 = time.time(), engine.host_step
-    while engine.host_step < train_steps:
-        n = min(log_every, train_steps - engine.host_step)
-        losses = engine.train(n)
-        if not np.all(np.isfinite(losses)):
-            raise FloatingPointError("NaN loss at step %d" % engine.host_step)
-        logger.info("step %d loss %.6f (%.1f steps/s)", engine.host_step, float(losses[-1]),
-                    (engine.host_step - s0) / max(time.time() - t0, 1e-9))
-        if time.time() - last_ckpt >= min(save_checkpoints_secs, 300) or engine.host_step >= train_steps:
-            save_checkpoint(engine, job_dir)
-            last_ckpt = time.time()
-            if eval_fn is not None:
-                metrics = eval_fn(engine)
-                metrics["global_step"] = engine.host_step
-                history.append((engine.host_step, metrics))
-                logger.info("eval @%d: %s", engine.host_step, metrics)
+    # TensorBoard summaries, as model_fn's add_summary + tf.estimator write them [ref src/models/model_utils.py:113-118]:
+    # every `log_every` (save_summary_steps = 100) TRAIN steps `loss`, `global_step/sec`, `mf/global_bias` and the
+    # histograms `mf/row_biases`, `mf/col_biases` into <job_dir>; the EVAL metrics into <job_dir>/eval
+    train_writer, eval_writer = EventWriter(job_dir), None
+    try:
+        while engine.host_step < train_steps:
+            n = min(log_every, train_steps - engine.host_step)
+            t1 = time.time()
+            losses = engine.train(n)
+            if not np.all(np.isfinite(losses)):
+                raise FloatingPointError("NaN loss at step %d" % engine.host_step)
+            rate = n / max(time.time() - t1, 1e-9)
+            logger.info("step %d loss %.6f (%.1f steps/s)", engine.host_step, float(losses[-1]),
+                        (engine.host_step - s0) / max(time.time() - t0, 1e-9))
+            rb, cb = engine.bias_vectors()
+            train_writer.add(engine.host_step, scalars={"loss": float(losses[-1]), "global_step/sec": rate,
+                                                        "mf/global_bias": float(engine.read_scalars()["g"])},
+                             histograms={"mf/row_biases": rb, "mf/col_biases": cb})
+            if time.time() - last_ckpt >= min(save_checkpoints_secs, 300) or engine.host_step >= train_steps:
+                save_checkpoint(engine, job_dir)
+                last_ckpt = time.time()
+                if eval_fn is not None:
+                    metrics = eval_fn(engine)
+                    metrics["global_step"] = engine.host_step
+                    history.append((engine.host_step, metrics))
+                    logger.info("eval @%d: %s", engine.host_step, metrics)
+                    if eval_writer is None:
+                        eval_writer = EventWriter(os.path.join(job_dir, "eval"))
+                    eval_writer.add(engine.host_step, scalars={k: v for k, v in metrics.items() if k != "global_step"})
+    finally:
+        train_writer.close()
+        if eval_writer is not None:
+            eval_writer.close()
     return history

@@ -63,6 +63,18 @@ def test_cli_train_resume_export_matches_oracle(tmp_path):
     want = o.eval_metrics(st, ocoo, 256)
     assert abs(hist2[-1][1]["loss"] - want["loss"]) <= 1e-4 * want["loss"]
 
+    # TensorBoard summaries: the reference's tags [ref src/models/model_utils.py:113-118] in <job_dir>, EVAL metrics in <job_dir>/eval
+    import glob
+    from glove_tensorflow_b200 import summary
+    ev = [e for f in sorted(glob.glob(os.path.join(job, "events.out.tfevents.*"))) for e in summary.read_events(f)]
+    last = [e for e in ev if e["step"] == 25][-1]
+    assert set(last["scalars"]) == {"loss", "global_step/sec", "mf/global_bias"}
+    assert abs(last["scalars"]["mf/global_bias"] - float(got["g"])) < 1e-7
+    h = last["histograms"]["mf/row_biases"]
+    assert h["num"] == 61 and abs(h["sum"] - float(got["rb"].astype(np.float64).sum())) < 1e-5 and "mf/col_biases" in last["histograms"]
+    ee = [e for f in glob.glob(os.path.join(job, "eval", "events.out.tfevents.*")) for e in summary.read_events(f)]
+    assert any(e["step"] == 25 and abs(e["scalars"]["loss"] - hist2[-1][1]["loss"]) < 1e-6 * abs(hist2[-1][1]["loss"]) for e in ee)
+
     # export: same json the reference writes (row table, <UNK> skipped, indent 2)
     out = export_embeddings.main(job, str(tmp_path / "embeddings.json"))
     emb = json.load(open(out))

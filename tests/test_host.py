@@ -203,3 +203,32 @@ def test_preprocess_defaults_are_the_references():
     assert text8.VOCAB_SIZE is None and text8.CONTEXT_SIZE == 5
     v = text8.create_vocabulary(["a", "b", "a", "c", "b", "a", "d"], None, 0.9)     # no cap: every token above the cut-off
     assert list(v["token"]) == ["a", "b", "c", "d", "<UNK>"] and list(v["count"]) == [3, 2, 1, 1, 0]
+
+
+def test_tensorboard_event_files_round_trip(tmp_path):
+    """summary.EventWriter writes what tf.summary.FileWriter would (TFRecord framing, masked CRC-32C, Event / Summary /
+    HistogramProto) with the reference's tags [ref src/models/model_utils.py:113-118]; read_events checks the CRCs and
+    decodes it again.  CRC-32C known answers: RFC 3720 B.4."""
+    from glove_tensorflow_b200 import summary
+    assert summary.crc32c(b"123456789") == 0xE3069283
+    assert summary.crc32c(bytes(32)) == 0x8A9136AA and summary.crc32c(bytes([0xFF] * 32)) == 0x62A8AB43
+    w = summary.EventWriter(str(tmp_path))
+    rng = np.random.default_rng(0)
+    rb = rng.normal(0, 0.05, 1000).astype(np.float32)
+    w.add(100, scalars={"loss": 1.25, "global_step/sec": 4321.0, "mf/global_bias": -0.5},
+          histograms={"mf/row_biases": rb, "mf/col_biases": np.zeros(7, np.float32)})
+    w.add(200, scalars={"loss": 1.0})
+    w.close()
+    assert os.path.basename(w.path).startswith("events.out.tfevents.")
+    ev = summary.read_events(w.path)
+    assert ev[0]["file_version"] == "brain.Event:2" and [e["step"] for e in ev] == [0, 100, 200]
+    assert ev[1]["scalars"] == {"loss": 1.25, "global_step/sec": 4321.0, "mf/global_bias": -0.5}
+    h = ev[1]["histograms"]["mf/row_biases"]
+    assert h["num"] == 1000 and abs(h["sum"] - float(rb.astype(np.float64).sum())) < 1e-9
+    assert h["min"] == float(rb.min()) and h["max"] == float(rb.max()) and h["bucket"].sum() == 1000
+    assert np.all(np.diff(h["bucket_limit"]) > 0) and h["bucket_limit"][-1] >= h["max"]
+    inside = (rb[:, None] < h["bucket_limit"][None, :]).argmax(1)           # first limit above each value = its bucket
+    assert np.array_equal(np.bincount(inside, minlength=len(h["bucket"])), h["bucket"].astype(np.int64))
+    z = ev[1]["histograms"]["mf/col_biases"]
+    assert z["num"] == 7 and z["bucket"].sum() == 7 and z["min"] == z["max"] == 0.0
+    assert ev[2]["scalars"] == {"loss": 1.0}
