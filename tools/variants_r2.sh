@@ -1,5 +1,9 @@
-timeout 100 python tools/state_hash.py 20000 300 8192 40 Adam 2>&1 | tail -1
-timeout 400 python -m pytest tests/test_train_gpu.py tests/test_pipeline_gpu.py -x -q 2>&1 | tail -3
-B="python bench.py --steps 200 --warmup 20 --no-topk --no-cpu-baseline --no-e2e"
-pick() { python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$1', round(d['ms_per_step']*1e3,1), 'us  stage', round(d['roofline']['kernels_ms']['stage']*1e3,1), 'update', round(d['roofline']['kernels_ms']['update']*1e3,1), 'frac', round(d['roofline']['frac'],3), 'loss', d['final_loss'])"; }
-timeout 120 $B < /dev/null | pick atomic4
+set -x
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+cp gpurun_out/parity_maxima.json gpurun_out/r02_parity_maxima.json
+timeout 200 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+( time timeout 600 python bench.py > gpurun_out/r02_bench_default.json 2> gpurun_out/r02_bench_default.err < /dev/null ) 2>&1 | grep real
+python tools/benchline.py default gpurun_out/r02_bench_default.json
+( time timeout 300 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/r02_bench_reference.json 2>&1 < /dev/null ) 2>&1 | grep real
+tail -c 600 gpurun_out/r02_bench_reference.json
+timeout 300 python bench.py --workload text8 --no-topk > gpurun_out/r02_bench_text8.json 2>/dev/null < /dev/null; python tools/benchline.py text8 gpurun_out/r02_bench_text8.json
