@@ -13,6 +13,11 @@ on; it fits one GPU.  ``--workload text8`` is configs[1] (V=10,001, d=64, B=65,5
 shape (V=2.2M; row-sharded tables at N>1); ``topk`` is configs[4] alone (cosine top-k over a 2.2M x 300 table, k=10,
 65,536 queries per call, tensor-core roofline) -- the default run also appends it as the ``topk`` record at N=1.
 
+N = 1: whole plan chunks (16 steps) go out as one CUDA-graph launch each (``--no-graph``: step by step); the timed region
+starts after 2,048 real TRAIN steps.  N > 1: row-sharded tables with a frequency-balanced owner map, exchange fused into
+the stage kernel over NVLink peer memory and device-side synchronisation (``--shard-exchange peer-push``; no NCCL on the
+step path); the e2e leg feeds every rank 1/N of each batch from pinned host memory.
+
 One JSON line is printed by rank 0 (see DESIGN.md "Measurement" for every key).
 """
 import argparse
