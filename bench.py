@@ -307,6 +307,9 @@ def main():
                     help="TRAIN steps run from the cold start before the timed region (default %d; profiling runs use fewer)" % T0)
     ap.add_argument("--no-balance", action="store_true",
                     help="N>1, row-sharded tables: keep owner = id %% N instead of the frequency-balanced owner map")
+    ap.add_argument("--no-plan-sharing", action="store_true",
+                    help="N>1, row-sharded tables: every rank builds the plan of every chunk itself (round-2 behaviour) instead "
+                         "of taking turns and pulling slices over peer memory")
     ap.add_argument("--no-graph", action="store_true",
                     help="launch every step's kernels one by one instead of one CUDA graph per plan chunk (N=1)")
     ap.add_argument("--no-topk", action="store_true", help="skip the cfg5 top-k record of the default N=1 run")
@@ -387,7 +390,7 @@ def main():
         return
     K = args.plan_steps
     steps = (args.steps + K - 1) // K * K if not args.no_e2e else args.steps
-    total_steps = args.warmup + args.steps + 3 * K + 64 + 2 * 8 * K      # + warm and timed e2e calls of up to 8 chunks
+    total_steps = args.warmup + args.steps + 3 * K + 64 + 2 * 16 * K     # + warm and timed e2e calls of up to 16 chunks
     eng = GloveEngine(V, d, optimizer="Adam", learning_rate=0.001, l2_reg=0.01, reg_scale=2.0, head="glove",
                       adam_mode=args.adam_mode, batch_size=B, plan_steps=K, max_steps=2 * T0 + 2 * total_steps + steps,
                       device=dev, dp_rank=rank, dp_world=N, dp_mode=args.dp_mode)
@@ -402,6 +405,18 @@ def main():
             args.shard_exchange = eng.shard_exchange = "alltoall"
     elif world <= 1 or args.dp_mode != "sharded":
         args.shard_exchange = eng.shard_exchange = "alltoall"
+    plan_sharing = False
+    if world > 1 and args.dp_mode == "sharded" and eng.shard_exchange.startswith("peer") and not args.no_plan_sharing:
+        ok = torch.ones(1, device=dev)
+        try:
+            eng.enable_plan_sharing()       # rank c % N builds the plan of chunk c, everyone pulls its slice over NVLink
+        except Exception as exc:
+            print("bench: shared plan construction unavailable (%s); every rank builds every plan" % exc, file=sys.stderr)
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        plan_sharing = bool(ok.item())
+        if not plan_sharing:
+            eng._ring = None
     row, col, tgt, wgt = gen_coo_device(V, nnz, 1234, dev)     # replicated COO (weak scaling: B grows with N)
     row0, col0 = row, col
     owner_load = None
@@ -497,7 +512,7 @@ def main():
     e2e = None
     if not args.no_e2e:
         # one call = CALL plan chunks (N == 1: pipelined inside glove_train_steps_host); host buffers of `pool` calls rotate
-        CALL = 8 if N == 1 else 4
+        CALL = 8 if N == 1 else (2 * N if plan_sharing else 4)   # shared plans: whole rounds of N chunks, two per call
         KC = K * CALL
         n_chunks = max(1, args.steps // KC)
         pool = 2
@@ -544,7 +559,12 @@ def main():
                         "call the copy + plan of chunk c+1 overlap the steps of chunk c" % KC if N == 1 else
                         "GloveEngine.train_chunks_from_host(sliced) on every rank, %d steps per call: pinned host COO (this rank's "
                         "1/N of every batch) -> H2D -> NCCL all-gather of the chunk -> plans -> sharded steps -> D2H losses; copy + "
-                        "gather + plan of chunk c+1 overlap the steps of chunk c; h2d bytes are the sum over ranks" % KC)}
+                        "gather + plan of chunk c+1 overlap the steps of chunk c; h2d bytes are the sum over ranks" % KC
+                        if not plan_sharing else
+                        "GloveEngine.train_chunks_from_host(sliced) on every rank, %d steps per call: pinned host COO (this rank's "
+                        "1/N of every batch) -> H2D -> one NCCL all-to-all per round of N chunks (rank q receives chunk q) -> rank q "
+                        "plans chunk q -> every rank pulls its slice of each plan over NVLink -> sharded steps -> D2H losses; copies, "
+                        "exchange and planning of round R+1 overlap the steps of round R; h2d bytes are the sum over ranks" % KC)}
 
     if rank != 0:
         if world > 1:
@@ -581,6 +601,8 @@ def main():
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": make_config(),
+            "plans": ("shared: rank c %% %d builds the plan of chunk c, every rank pulls its slice over NVLink" % N) if plan_sharing
+                     else "every rank builds every plan",
             "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * per_step_launches + n_prep * 20,
             "roofline": roofline, "cpu_baseline": cpu, "final_loss": float(final_loss)}
     if topk is not None:

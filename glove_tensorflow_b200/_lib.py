@@ -83,6 +83,7 @@ SIGNATURES = {
     "glove_shard_pack_step": (ctypes.c_int, [ctypes.POINTER(StepArgs), c_void, c_void]),
     "glove_shard_unpack_step": (ctypes.c_int, [ctypes.POINTER(StepArgs), c_void, c_void]),
     "glove_plan_need_info": (ctypes.c_int, [c_void, c_i32, c_i32, ctypes.POINTER(c_i32), c_void]),
+    "glove_plan_pull_slice": (ctypes.c_int, [c_void, c_void, c_i32, c_i32, c_i32, c_i32, c_void]),
     "glove_shard_update_step": (ctypes.c_int, [ctypes.POINTER(StepArgs), c_void, c_void]),
     "glove_shard_finish_step": (ctypes.c_int, [ctypes.POINTER(StepArgs), c_void, c_void]),
     "glove_step_snapshot_rows": (c_i64, [c_i32]),

@@ -308,6 +308,66 @@ __global__ void need_offsets_kernel(int32_t K, int32_t n_shards, int pbits, cons
     }
 }
 
+// ---- shared plan construction (row-sharded tables): pull one shard's slice of a plan built by another rank -------------
+// A plan of K steps of the GLOBAL batch costs O(K * B_global) to build and every rank needs only the ~1/n_shards of it that
+// describes the segments it owns.  Ranks therefore take turns building whole plans (rank c % n_shards builds the plan of
+// chunk c into peer-mapped memory) and everybody copies its own slice into a local plan buffer of the same layout, so all
+// indices stay valid and the step kernels do not know the difference: per rank the construction cost no longer grows with
+// the number of GPUs.  Slice of shard r = the per-batch offset tables and request offsets (whole: they are tiny), and of
+// every batch the segment records, triple records, work-item records, long-segment records and request-list entries of
+// r's block (what the stage / update / exchange kernels of shard r dereference).
+struct PullArgs {
+    const PlanHeader *src_hdr;
+    PlanHeader *dst_hdr;
+    PlanSide src[2], dst[2];
+    int32_t K, n_shards, shard;
+};
+__device__ __forceinline__ void copy_i32(int32_t *dst, const int32_t *src, int64_t n) {
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+}
+__global__ void __launch_bounds__(256) plan_pull_head_kernel(const PullArgs a) {
+    constexpr int W = kMaxShards + 1;
+    if (blockIdx.x == 0) copy_i32((int32_t *)a.dst_hdr, (const int32_t *)a.src_hdr, sizeof(PlanHeader) / 4);
+    const int s = blockIdx.x & 1;
+    const PlanSide &S = a.src[s], &D = a.dst[s];
+    switch (blockIdx.x >> 1) {
+        case 0: copy_i32(D.b_seg, S.b_seg, a.K + 1); copy_i32(D.b_item, S.b_item, a.K + 1); break;
+        case 1: copy_i32(D.b_long, S.b_long, a.K + 1); copy_i32(D.b_part, S.b_part, a.K + 1); copy_i32(D.b_upad, S.b_upad, a.K); break;
+        case 2: copy_i32(D.b_own, S.b_own, (int64_t)a.K * W); copy_i32(D.b_own_item, S.b_own_item, (int64_t)a.K * W); break;
+        default: copy_i32(D.need_off, S.need_off, (int64_t)a.K * kMaxShards * W); break;
+    }
+}
+template <typename T>
+__device__ __forceinline__ void copy_part(T *dst, const T *src, int lo, int hi, int part, int nparts) {
+    for (int i = lo + part * blockDim.x + threadIdx.x; i < hi; i += nparts * blockDim.x) dst[i] = src[i];
+}
+// grid = K * 2 * nparts CTAs: CTA (k, side, part) copies every nparts-th 256-element block of each range of batch k
+__global__ void __launch_bounds__(256) plan_pull_body_kernel(const PullArgs a, int nparts) {
+    constexpr int W = kMaxShards + 1;
+    const int part = blockIdx.x % nparts, t = blockIdx.x / nparts, k = t >> 1, s = t & 1;
+    const PlanSide &S = a.src[s], &D = a.dst[s];
+    const int r = a.shard;
+    // offsets come from the local copy (written by the head kernel, one launch earlier on the same stream)
+    const int g0 = D.b_seg[k] + D.b_own[k * W + r], g1 = D.b_seg[k] + D.b_own[k * W + r + 1];
+    if (g1 > g0) {
+        copy_part(D.seg_id, S.seg_id, g0, g1, part, nparts);
+        copy_part(D.seg_prev, S.seg_prev, g0, g1, part, nparts);
+        copy_part(D.seg_push, S.seg_push, g0, g1, part, nparts);
+        copy_part(D.seg_long, S.seg_long, g0, g1, part, nparts);
+        copy_part(D.seg_start, S.seg_start, g0, g1 + 1, part, nparts);
+        const int q0 = S.seg_start[g0], q1 = S.seg_start[g1];
+        copy_part(D.rec, S.rec, q0, q1, part, nparts);
+    }
+    copy_part(D.item_rec, S.item_rec, D.b_item[k] + D.b_own_item[k * W + r], D.b_item[k] + D.b_own_item[k * W + r + 1], part, nparts);
+    copy_part(D.long_rec, S.long_rec, D.b_long[k], D.b_long[k + 1], part, nparts);
+    // request lists: the rows shard r needs (from every owner), and the rows every other shard needs from owner r
+    const int32_t *off = D.need_off + (int64_t)k * kMaxShards * W;
+    for (int q = 0; q < a.n_shards; ++q) {
+        if (q == r) copy_part(D.need_pos, S.need_pos, off[r * W], off[r * W + a.n_shards], part, nparts);
+        else copy_part(D.need_pos, S.need_pos, off[q * W + r], off[q * W + r + 1], part, nparts);
+    }
+}
+
 __global__ void header_kernel(PlanHeader *hdr, int32_t K, int32_t B, int32_t first_step, int32_t n_shards, int32_t v_loc) {
     hdr->magic = kPlanMagic;
     hdr->K = K;
@@ -434,6 +494,25 @@ int glove_prepare_batches_sharded(void *plan, void *workspace, size_t workspace_
         for (int s = 0; s < 2; ++s) push_mask_kernel<<<K * n_shards, 256, 0, stream>>>(n_shards, pv.side[s], pv.side[1 - s]);
         GLOVE_CHECK_LAUNCH();
     }
+    return GLOVE_OK;
+}
+
+int glove_plan_pull_slice(void *dst_plan, const void *src_plan, int32_t K, int32_t B, int32_t n_shards, int32_t shard,
+                          void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    GLOVE_REQUIRE(dst_plan && src_plan && K > 0 && B > 0, "glove_plan_pull_slice: bad arguments");
+    GLOVE_REQUIRE(n_shards > 1 && n_shards <= kMaxShards && shard >= 0 && shard < n_shards,
+                  "glove_plan_pull_slice: bad shard %d of %d", shard, n_shards);
+    PlanView sv = plan_view(const_cast<void *>(src_plan), K, B), dv = plan_view(dst_plan, K, B);
+    PullArgs a;
+    a.src_hdr = sv.hdr; a.dst_hdr = dv.hdr;
+    for (int s = 0; s < 2; ++s) { a.src[s] = sv.side[s]; a.dst[s] = dv.side[s]; }
+    a.K = K; a.n_shards = n_shards; a.shard = shard;
+    plan_pull_head_kernel<<<8, 256, 0, stream>>>(a);
+    int nparts = (2 * kNumSMs + 2 * K - 1) / (2 * K);
+    if (nparts < 1) nparts = 1;
+    plan_pull_body_kernel<<<2 * K * nparts, 256, 0, stream>>>(a, nparts);
+    GLOVE_CHECK_LAUNCH();
     return GLOVE_OK;
 }
 

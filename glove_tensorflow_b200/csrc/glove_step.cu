@@ -330,6 +330,8 @@ __global__ void __launch_bounds__(256) stage_kernel(const StepParams p, int step
 template <int NV>
 __global__ void __launch_bounds__(256, 2) stage_closed_kernel(const StepParams p) {
     __shared__ ReplayTables tabs;
+    extern __shared__ __align__(16) float push_smem[];   // peer-push only: [8 warps][2 buffers][S] rows on their way to the peers
+    uint32_t n_pushed = 0;                               // rows this warp has handed to the copy engine
     int k, step;
     const bool ok = batch_index(p, k, step);
     replay_tables_init(tabs, p.b1, p.b2);
@@ -391,14 +393,33 @@ __global__ void __launch_bounds__(256, 2) stage_closed_kernel(const StepParams p
         if (p.push_snap) {
             // fused exchange: the row goes straight from these registers into the snapshot of every shard whose work items
             // read it (request mask from the plan), as posted NVLink writes that overlap the staging of the next rows
+            //
+            // The row is parked in a per-warp shared-memory buffer and ONE bulk asynchronous copy per destination
+            // (cp.async.bulk shared -> global: 1,216 bytes each) does the rest: the warp does not wait on NVLink, and the
+            // link sees whole rows instead of 16-byte stores.  Two buffers per warp: a buffer is rewritten only after the
+            // copies of the row before last have read it (wait_group.read 1).
             unsigned mask = (unsigned)__ldg(p.side[sd].seg_push + (sd ? g_c + (w - U0) : g_r + w));
-            while (mask) {
-                const int r = __ffs(mask) - 1;
-                mask &= mask - 1;
-                store_row<NV>(p.push_snap[sd * kMaxShards + r] + (int64_t)pos * p.S, x, lane, S4);
+            if (mask) {
+                float *buf = push_smem + ((threadIdx.x >> 5) * 2 + (n_pushed & 1u)) * p.S;
+                if (lane == 0) bulk_wait_read_1();
+                __syncwarp();
+                store_row<NV>(buf, x, lane, S4);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    const uint32_t src = smem_addr(buf), bytes = (uint32_t)p.S * 4u;
+                    while (mask) {
+                        const int r = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        bulk_s2g(p.push_snap[sd * kMaxShards + r] + (int64_t)pos * p.S, src, bytes);
+                    }
+                    bulk_commit();
+                }
+                ++n_pushed;
             }
         }
     }
+    if (p.push_snap && lane == 0) bulk_wait_all();   // every pushed row has left before the kernel (and its announcement) ends
 }
 
 // second half of the catch-up: mark the pre-replayed rows current (same predicate as stage_kernel<true>)
@@ -1127,7 +1148,11 @@ static int launch_step(const StepParams &p, cudaStream_t stream, cudaEvent_t *ev
     if (p.mode == MODE_TRAIN || p.mode == MODE_GRAD || p.mode == MODE_SHARD) {
         if (ev) cudaEventRecord(ev[0], stream);
         if (p.run_stage) {
-            if (p.opt == GLOVE_OPT_ADAM && p.adam_mode == GLOVE_ADAM_REPLAY) stage_closed_kernel<NV><<<g_stage_closed, 256, 0, stream>>>(p);
+            if (p.opt == GLOVE_OPT_ADAM && p.adam_mode == GLOVE_ADAM_REPLAY) {
+                // peer-push: per-warp row buffers for the bulk copies to the peers (2.4 KB per warp at d = 300)
+                const size_t push_smem = p.push_snap ? (size_t)8 * 2 * p.S * sizeof(float) : 0;
+                stage_closed_kernel<NV><<<g_stage_closed, 256, push_smem, stream>>>(p);
+            }
             else stage_kernel<false><<<g_stage, 256, 0, stream>>>(p, 0);
         }
         if (ev) cudaEventRecord(ev[1], stream);

@@ -122,6 +122,8 @@ class GloveEngine:
         # K steps as ONE CUDA graph launch (glove_step_graph_*): one graph per plan buffer, built on first use
         self.use_graph = False
         self._graphs = [None, None]
+        self._ring = None       # shared plan construction over peer memory (enable_plan_sharing)
+        self._ev_coo = None     # the COO / injected batch order are complete on the device
 
     def __del__(self):
         for g in getattr(self, "_graphs", [None, None]):
@@ -206,6 +208,7 @@ class GloveEngine:
         self._write_scalars(step=int(step))
         self.host_step = int(step)
         self.plan_first = [None, None]
+        self._ring_reset()
 
     def set_plane(self, side: str, plane: int, emb: torch.Tensor, bias: torch.Tensor):
         """Write optimizer slot plane ``plane`` (1 = Adam m / Adagrad acc, 2 = Adam v) of ``side`` in {'row','col'}."""
@@ -294,6 +297,8 @@ class GloveEngine:
         main = torch.cuda.current_stream()
         main.wait_stream(self._side)
         main.wait_stream(self._prep_stream)
+        if self._ring is not None:
+            main.wait_stream(self._ring["pull_stream"])
         self._ev_catchup = None
 
     def flush(self):
@@ -329,6 +334,9 @@ class GloveEngine:
                 raise ValueError("set_coo: ids must lie in [0, %d): min %d, max %d" % (self.V_global, lo, hi))
         self.shuffle_key = int(shuffle_key) & 0xFFFFFFFF
         self.plan_first = [None, None]
+        self._ev_coo = torch.cuda.Event()
+        self._ev_coo.record(torch.cuda.current_stream())
+        self._ring_reset()
 
     def set_batches(self, sample_idx):
         """Inject an explicit batch order: int64 [n_steps, B] indices into the COO, used from the current step on."""
@@ -337,6 +345,9 @@ class GloveEngine:
         self.sample_idx = idx.contiguous()
         self.sample_idx_first = self.host_step
         self.plan_first = [None, None]
+        self._ev_coo = torch.cuda.Event()
+        self._ev_coo.record(torch.cuda.current_stream())
+        self._ring_reset()
 
     def _make_args(self, which):
         a = _lib.StepArgs()
@@ -356,8 +367,9 @@ class GloveEngine:
         a.dp_rank, a.dp_world = self.dp_rank, self.dp_world
         return a
 
-    def prepare(self, first_step: int, which: int):
-        """Build the plan for steps [first_step, first_step + K) into plan buffer ``which``."""
+    def prepare(self, first_step: int, which: int, dst: Optional[int] = None):
+        """Build the plan for steps [first_step, first_step + K) into plan buffer ``which`` (or, with ``dst``, into the
+        device address ``dst`` -- a build buffer of the shared plan construction -- leaving the buffer bookkeeping alone)."""
         assert self.coo is not None, "set_coo() first"
         sidx = None
         if self.sample_idx is not None:
@@ -370,11 +382,14 @@ class GloveEngine:
                 chunk = torch.cat([chunk, chunk[-1:].expand(self.K - chunk.shape[0], -1)], 0)
             sidx = chunk.contiguous().view(-1)
         row, col, ca, cb = self.coo
-        check(lib.glove_prepare_batches_sharded(_ptr(self.plans[which]), _ptr(self.prep_ws), self.prep_ws.numel(),
+        check(lib.glove_prepare_batches_sharded(ctypes.c_void_p(dst) if dst is not None else _ptr(self.plans[which]),
+                                                _ptr(self.prep_ws), self.prep_ws.numel(),
                                                 _ptr(row), _ptr(col), _ptr(ca), _ptr(cb), self.nnz, _ptr(sidx),
                                                 int(first_step) * self.B, self.shuffle_key, int(first_step), self.K,
                                                 self.B, self.V_global, self.dp_world if self.sharded else 1, _stream()),
               "glove_prepare_batches")
+        if dst is not None:
+            return sidx       # the caller keeps the index chunk alive until the stream has consumed it
         self._keep[which] = sidx  # keep the index chunk alive until the stream has consumed it
         self.plan_first[which] = first_step
         self._plan_counts[which] = None
@@ -391,6 +406,9 @@ class GloveEngine:
         if self.sample_idx is not None and nxt_first - self.sample_idx_first >= self.sample_idx.shape[0]:
             return
         main = torch.cuda.current_stream()
+        if self._ring is not None:
+            self._ring_pull_chunk(nxt_first // self.K, which)
+            return
         # the buffer being overwritten belonged to the chunk before the current one: every step of it has completed
         # before the current chunk's first step was enqueued on `main`, so ordering after `main` here is sufficient
         self._prep_stream.wait_stream(main)
@@ -406,7 +424,10 @@ class GloveEngine:
             return ov[0]
         first = (step // self.K) * self.K
         which = (step // self.K) & 1
-        if self.plan_first[which] != first:
+        if self.plan_first[which] != first and self._ring is not None:
+            self._ring_pull_chunk(first // self.K, which)
+            torch.cuda.current_stream().wait_event(self._ev_plan[which])
+        elif self.plan_first[which] != first:
             torch.cuda.current_stream().wait_stream(self._prep_stream)   # one prepare at a time (shared workspace)
             self.prepare(first, which)
             ev = torch.cuda.Event()                                     # the catch-up stream reads the plan too
@@ -443,6 +464,120 @@ class GloveEngine:
     def _after_step(self):
         if self.overlap:
             self._ev_step_done[self.host_step & 1].record(torch.cuda.current_stream())
+
+    # ---- shared plan construction (row-sharded tables over peer memory) ------------------------------------------------
+    # Every rank of a row-sharded job needs the plan of the GLOBAL batch but dereferences only the ~1/world of it that
+    # describes its own segments, and building it (two radix sorts + ~30 passes over K * B_global elements) costs as much as
+    # the steps themselves from 4 GPUs on.  With plan sharing the chunks are dealt round-robin: in "round" R (chunks
+    # R*world .. R*world + world - 1) rank q builds ONLY chunk R*world + q, into one of two build buffers in symmetric
+    # memory, a whole round ahead of its use and at the same time as every other rank builds its own; when the round
+    # opens (one barrier over the peer-mapped signal pads, off the step stream) every rank copies its slice of each chunk
+    # out of the builder's buffer over NVLink (glove_plan_pull_slice) into its local double-buffered plans.  Per rank and
+    # step the construction cost is that of ONE GPU's batch, whatever the world size.
+    #   build stream:  [wait: last barrier -- everyone has left the buffer]  prepare(my chunk of round R+1) -> built[R+1]
+    #   pull stream:   [wait: built[R]]  barrier  | per chunk: [wait: steps of chunk c-2 done]  pull slice -> plan ready
+    def enable_plan_sharing(self, group=None, _emulate=None):
+        """Collective (call on every rank, after enable_peer_gather): allocates the two build buffers in symmetric memory and
+        switches plan construction to the shared scheme.  ``_emulate`` = (peer base pointers, barrier callable) lets N
+        engines on ONE GPU stand in for N ranks (tests)."""
+        assert self.sharded, "plan sharing is for row-sharded tables"
+        self._join_side()
+        torch.cuda.synchronize()
+        if _emulate is None:
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm_mem
+            buf = symm_mem.empty(2 * self.plan_bytes, dtype=torch.uint8, device=self.device)
+            hdl = symm_mem.rendezvous(buf, group if group is not None else dist.group.WORLD)
+            ptrs, barrier = [int(p) for p in hdl.buffer_ptrs], hdl.barrier
+        else:
+            buf = torch.empty(2 * self.plan_bytes, dtype=torch.uint8, device=self.device)
+            hdl, (ptrs, barrier) = None, _emulate
+        self._ring = dict(buf=buf, hdl=hdl, ptrs=ptrs, barrier=barrier, built={}, opened=set(), ev_barrier=None, keep={},
+                          build_stream=torch.cuda.Stream(device=self.device), pull_stream=torch.cuda.Stream(device=self.device),
+                          builder=self._ring_build_resident)
+        self.plan_first = [None, None]
+        torch.cuda.synchronize()
+        if _emulate is None:
+            barrier()
+            torch.cuda.synchronize()
+
+    def _ring_reset(self):
+        """Forget every built / opened round (the batch order changed).  A peer may still be copying out of this rank's build
+        buffers: nothing is rebuilt before every rank has passed the barrier enqueued here."""
+        ring = self._ring
+        if ring is None:
+            return
+        ring["built"].clear(); ring["opened"].clear(); ring["keep"].clear()
+        ps = ring["pull_stream"]
+        ps.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(ps):
+            ring["barrier"]()
+            ring["ev_barrier"] = torch.cuda.Event()
+            ring["ev_barrier"].record(ps)
+
+    def _ring_build_resident(self, R, dst):
+        """builder of the device-resident COO: my chunk of round R (steps [c*K, (c+1)*K), c = R*world + rank)"""
+        first = (R * self.dp_world + self.dp_rank) * self.K
+        if first >= self.max_steps:
+            return None
+        if self.sample_idx is not None and not 0 <= first - self.sample_idx_first < self.sample_idx.shape[0]:
+            return None
+        return self.prepare(first, 0, dst=dst)
+
+    def _ring_build(self, R):
+        ring = self._ring
+        if R in ring["built"]:
+            return
+        bs = ring["build_stream"]
+        if self._ev_coo is not None:
+            bs.wait_event(self._ev_coo)
+        if ring["ev_barrier"] is not None:      # every rank has finished copying out of the buffer this build overwrites
+            bs.wait_event(ring["ev_barrier"])
+        with torch.cuda.stream(bs):
+            ring["keep"][R & 1] = ring["builder"](R, ring["buf"].data_ptr() + (R & 1) * self.plan_bytes)
+            ev = torch.cuda.Event()
+            ev.record(bs)
+        ring["built"][R] = ev
+        ring["built"].pop(R - 2, None)
+
+    def _ring_open(self, R):
+        ring = self._ring
+        if R in ring["opened"]:
+            return
+        self._ring_build(R)                      # cold start (or after a reset); otherwise built one round ago
+        ps = ring["pull_stream"]
+        ps.wait_event(ring["built"][R])
+        with torch.cuda.stream(ps):
+            ring["barrier"]()                    # every rank's chunk of round R is complete ...
+            ring["ev_barrier"] = torch.cuda.Event()
+            ring["ev_barrier"].record(ps)        # ... and nobody reads the buffers of round R-1 any more
+        ring["opened"].add(R)
+        ring["opened"].discard(R - 2)
+        self._ring_build(R + 1)                  # look-ahead: a whole round of training hides it
+
+    def _ring_pull(self, R, j, which, first_step, after=None):
+        """Copy this rank's slice of chunk j of round R (built by rank j) into plan buffer ``which``."""
+        ring = self._ring
+        self._ring_open(R)
+        ps = ring["pull_stream"]
+        if after is not None:
+            ps.wait_event(after)                 # the steps that read plan buffer `which` before have finished
+        with torch.cuda.stream(ps):
+            src = ring["ptrs"][j] + (R & 1) * self.plan_bytes
+            check(lib.glove_plan_pull_slice(_ptr(self.plans[which]), ctypes.c_void_p(src), self.K, self.B, self.dp_world,
+                                            self.dp_rank, ctypes.c_void_p(ps.cuda_stream)), "glove_plan_pull_slice")
+            ev = torch.cuda.Event()
+            ev.record(ps)
+        self.plan_first[which] = first_step
+        self._plan_counts[which] = self._plan_shards[which] = self._plan_need[which] = None
+        self._ev_plan[which] = ev
+        return ev
+
+    def _ring_pull_chunk(self, c, which):
+        """device-resident COO: chunk c = steps [c*K, (c+1)*K) of the keyed shuffle / the injected batch order"""
+        # plan buffer `which` belonged to chunk c-2, whose steps were all enqueued before this call
+        self._ring["pull_stream"].wait_stream(torch.cuda.current_stream())
+        self._ring_pull(c // self.dp_world, c % self.dp_world, which, c * self.K)
 
     # ---- train ---------------------------------------------------------------------------------------------------
     def step(self):
@@ -758,6 +893,10 @@ class GloveEngine:
         1 / world of the bytes cross each rank's PCIe link instead of the whole global batch."""
         n = self.K * self.B
         N = self.dp_world if sliced else 1
+        if sliced and N > 1 and self._ring is not None and self._ring["hdl"] is not None and len(chunks) % N == 0:
+            return self._train_chunks_shared_plans(chunks)
+        if self._ring is not None:
+            self._ring_reset()      # the build buffers are about to be bypassed: plans of the resident COO are rebuilt afterwards
         if sliced and N > 1:
             import torch.distributed as dist
             assert self.B % N == 0
@@ -842,6 +981,83 @@ class GloveEngine:
         self.plan_first = [None, None]
         main.wait_stream(self._prep_stream)
         idx = torch.arange(first0, first0 + len(chunks) * self.K, device=self.device) % self.loss_cap
+        return self.loss_out[idx].cpu().numpy()      # D2H of the losses (synchronises)
+
+    def _train_chunks_shared_plans(self, chunks):
+        """train_chunks_from_host(sliced=True) with shared plan construction: the chunks are taken in rounds of `world`; of
+        every round each rank copies its shares of all chunks to the device, ONE all-to-all hands rank q every share of
+        chunk q (instead of all-gathering every chunk to everyone), rank q plans that chunk alone, and the ranks pull their
+        slices of the plans as the steps reach them.  Copies, exchange and planning of round R+1 run under the steps of
+        round R."""
+        import torch.distributed as dist
+        from .parallel import assemble_chunk
+        ring, N, K, me = self._ring, self.dp_world, self.K, self.dp_rank
+        assert self.B % N == 0
+        n, m = K * self.B, K * self.B // N
+        self._join_side()
+        if getattr(self, "_gather_group", None) is None:
+            self._gather_group = dist.new_group(backend="nccl") if dist.get_backend() == "nccl" else dist.group.WORLD
+        if getattr(self, "_ring_io", None) is None:
+            i32 = dict(dtype=torch.int32, device=self.device)
+            self._ring_io = [(torch.empty(N * 4 * m, **i32), torch.empty(N * 4 * m, **i32)) for _ in range(2)]   # send, recv
+            self._ring_coo = [tuple(torch.empty(n, dtype=dt, device=self.device) for dt in (torch.int32, torch.int32, torch.float32, torch.float32))
+                              for _ in range(2)]
+            self._stage_idx = torch.arange(n, dtype=torch.int64, device=self.device)
+        first0 = self.host_step
+        main = torch.cuda.current_stream()
+        self._ring_reset()
+
+        def build(R, dst):
+            if R * N >= len(chunks):
+                return None
+            send, recv = self._ring_io[R & 1]
+            sv = send.view(N, 4, m)
+            for q in range(N):                                     # H2D of this rank's share of every chunk of the round
+                for j, src in enumerate(chunks[R * N + q]):
+                    assert src.numel() == m and not src.is_cuda
+                    sv[q, j].copy_(src.view(torch.int32), non_blocking=True)
+            dist.all_to_all_single(recv, send, group=self._gather_group)    # rank q receives every rank's share of chunk q
+            g = assemble_chunk(recv, N, K, self.B // N)            # [array][step][rank][triple]
+            coo = self._ring_coo[R & 1]
+            for j, t in enumerate(coo):
+                t.view(torch.int32).view(K, N, self.B // N).copy_(g[j])
+            row, col, ca, cb = coo
+            if self._label is not None:                            # balanced owner map: the kernels see labels
+                row.copy_(self._label[row.long()]); col.copy_(self._label[col.long()])
+            check(lib.glove_prepare_batches_sharded(ctypes.c_void_p(dst), _ptr(self.prep_ws), self.prep_ws.numel(), _ptr(row), _ptr(col),
+                                                    _ptr(ca), _ptr(cb), n, _ptr(self._stage_idx), 0, 0, first0 + (R * N + me) * K, K,
+                                                    self.B, self.V_global, N, _stream()), "glove_prepare_batches")
+            return None
+
+        ring["builder"] = build
+        ready, done = [None, None], [None, None]
+        ring["pull_stream"].wait_stream(main)            # earlier steps may still read the plan buffers
+
+        def pull(c):
+            ready[c & 1] = self._ring_pull(c // N, c % N, c & 1, first0 + c * K, after=done[c & 1])
+
+        try:
+            pull(0)
+            for c in range(len(chunks)):
+                if c + 1 < len(chunks):
+                    pull(c + 1)
+                which, first = c & 1, first0 + c * K
+                main.wait_event(ready[which])
+                self.plan_first = [None, None]
+                self.plan_first[which] = first
+                self._plan_override = (which, first)
+                for _ in range(K):
+                    self._step_sharded()
+                done[which] = torch.cuda.Event()
+                done[which].record(main)
+        finally:
+            self._plan_override = None
+            self.plan_first = [None, None]
+            ring["builder"] = self._ring_build_resident
+        main.wait_stream(ring["pull_stream"])
+        main.wait_stream(ring["build_stream"])
+        self._ring_reset()
+        idx = torch.arange(first0, first0 + len(chunks) * K, device=self.device) % self.loss_cap
         return self.loss_out[idx].cpu().numpy()      # D2H of the losses (synchronises)
 
     def batch_counts(self, step: int):

@@ -232,6 +232,15 @@ int glove_shard_unpack_step(const glove_step_args *args, const float *recv_buf, 
 /* Host copy of the request-list offsets of a whole plan: out[side][K][8][9] ints; the rows shard r needs from owner q in
  * batch k (for the work items of `side`) number out[side][k][r][q+1] - out[side][k][r][q].  Synchronises the stream. */
 int glove_plan_need_info(const void *plan, int32_t K, int32_t B, int32_t *out, void *stream);
+/* Shared plan construction (row-sharded tables): a plan of K steps of the GLOBAL batch is built by ONE rank
+ * (glove_prepare_batches_sharded into peer-mapped memory) and every rank copies the slice that describes its own block of
+ * segments -- offset tables, segment / triple / work-item / long-segment records, request lists of shard `shard` -- from
+ * `src_plan` (the builder's buffer as mapped in this process) into the same offsets of `dst_plan` (a local buffer of
+ * glove_plan_bytes(K, B)).  The step entry points of shard `shard` then run on `dst_plan` exactly as on a plan built
+ * locally (same results bit for bit); per rank the cost of plan construction stops growing with the number of shards.
+ * The caller orders the copy after the builder has finished (and the next build after every reader has). */
+int glove_plan_pull_slice(void *dst_plan, const void *src_plan, int32_t K, int32_t B, int32_t n_shards, int32_t shard,
+                          void *stream);
 int glove_shard_update_step(const glove_step_args *args, float *loss_scalars, void *stream);
 int glove_shard_finish_step(const glove_step_args *args, const float *loss_scalars, void *stream);
 int64_t glove_step_snapshot_rows(int32_t B);

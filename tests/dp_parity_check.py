@@ -1,6 +1,6 @@
 """Real multi-process parity of the row-sharded path (test infrastructure; run under torchrun on >= 2 GPUs):
 
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tests/dp_parity_check.py [exchange]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tests/dp_parity_check.py [exchange[+shared-plans]] [graph]
 
 Every rank owns 1/N of the rows (frequency-balanced owner map), steps run through the real exchange -- by default the
 peer-memory pull with device-side synchronisation ('peer-sync', as CUDA graphs), or 'peer' / 'alltoall' / 'allgather'
@@ -25,6 +25,8 @@ def main():
     from glove_tensorflow_b200.engine import GloveEngine
     from oracle import c_oracle, glove_oracle as o
     exchange = sys.argv[1] if len(sys.argv) > 1 else "peer-push"
+    shared = exchange.endswith("+shared-plans")      # rank c % N builds the plan of chunk c, every rank pulls its slice
+    exchange = exchange.split("+")[0]
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", rank)))
     torch.cuda.set_device(dev)
@@ -40,6 +42,8 @@ def main():
     eng.shard_exchange = exchange
     if exchange.startswith("peer"):
         eng.enable_peer_gather(direct=exchange == "peer-direct", sync=exchange == "peer-sync", push=exchange == "peer-push")
+    if shared:
+        eng.enable_plan_sharing()
     eng.balance_owners(coo["row"], coo["col"], hot=2048)
     eng.load_state(st.R, st.C, st.rb, st.cb, st.g)
     eng.set_coo(coo["row"], coo["col"], coo["target"], coo["weight"])
@@ -63,7 +67,7 @@ def main():
         l32 = c32.train(coo, batches, learning_rate=0.01)
         l64 = c64.train(coo, batches, learning_rate=0.01)
         rel = lambda a, b: float(np.max(np.abs(np.asarray(a, np.float64) - b)) / np.max(np.abs(b)))
-        res = {"world": world, "exchange": exchange, "graph": bool(eng.use_graph), "steps": steps, "global_batch": B,
+        res = {"world": world, "exchange": exchange, "shared_plans": shared, "graph": bool(eng.use_graph), "steps": steps, "global_batch": B,
                "loss_vs_oracle32": float(np.max(np.abs(losses - l32) / np.abs(l32))),
                "loss_vs_shadow64": float(np.max(np.abs(losses - l64) / np.abs(l64))),
                "ranks_agree_on_losses": all(bool(torch.equal(all_losses[0], t)) for t in all_losses)}

@@ -333,7 +333,8 @@ def test_overlap_streams_do_not_change_results(adam_mode):
         assert np.array_equal(out[0][1][k], out[1][1][k]), k
 
 
-@pytest.mark.parametrize("exchange", ["alltoall", "allgather", "peer", "peer-direct", "peer-sync", "peer-push"])
+@pytest.mark.parametrize("exchange", ["alltoall", "allgather", "peer", "peer-direct", "peer-sync", "peer-push",
+                                      "alltoall+shared-plans", "peer-sync+shared-plans", "peer-push+shared-plans"])
 @pytest.mark.parametrize("world,adam_mode,optimizer,V", [(2, "replay", "Adam", 601), (4, "replay", "Adam", 1000),
                                                          (3, "lazy", "Adam", 333), (2, "replay", "Adagrad", 64),
                                                          (8, "replay", "Adam", 5000)])
@@ -343,6 +344,10 @@ def test_row_sharded_tables_on_one_gpu(world, adam_mode, optimizer, V, exchange)
     hand; every owner runs the fused update of its own segments.  The union of the shards must match the single-process oracle."""
     import torch
     from glove_tensorflow_b200.engine import GloveEngine
+    # "+shared-plans": the plan of chunk c is built by engine c % world alone and every engine copies its slice out of the
+    # builder's buffer (glove_plan_pull_slice) -- results must not change by a bit (compared with the oracle like the rest)
+    shared = exchange.endswith("+shared-plans")
+    exchange = exchange.split("+")[0]
     d, B, steps, n = 40, 512 if world != 3 else 510, 14, 20000
     coo = make_coo(V, n, 51, hot=0.1)
     batches = np.random.default_rng(52).integers(0, n, (steps, B))
@@ -357,9 +362,15 @@ def test_row_sharded_tables_on_one_gpu(world, adam_mode, optimizer, V, exchange)
         if world in (3, 8):                                        # frequency-balanced owner map instead of id % world
             e.balance_owners(coo["row"], coo["col"], hot=64)       # (the balance itself is checked in tests/test_dp_gloo.py)
         e.load_state(st.R, st.C, st.rb, st.cb, st.g)
+        if shared:                                                 # one GPU: the "barrier" is a device synchronisation
+            e.enable_plan_sharing(_emulate=(None, torch.cuda.synchronize))
         e.set_coo(coo["row"], coo["col"], coo["target"], coo["weight"])
         e.set_batches(batches)
         engs.append(e)
+    if shared:
+        for e in engs:
+            e._ring["ptrs"] = [x._ring["buf"].data_ptr() for x in engs]
+            e.plans[0].fill_(0xAB); e.plans[1].fill_(0xAB)         # whatever is not pulled stays garbage
     if exchange.startswith("peer"):                                # on one GPU every "peer" workspace is plain device memory
         for e in engs:
             e.set_peer_workspaces([x.step_ws.data_ptr() for x in engs], direct=exchange == "peer-direct",
@@ -367,6 +378,13 @@ def test_row_sharded_tables_on_one_gpu(world, adam_mode, optimizer, V, exchange)
     side_streams = [torch.cuda.Stream() for _ in engs]
     losses = []
     for s in range(steps):
+        if shared:
+            # real ranks meet at a barrier before a round of chunks is pulled; engines called one after the other cannot, so
+            # the builds of the rounds that this step (and its plan prefetch) may pull from are issued up front
+            for c in (s // 5, s // 5 + 1):
+                for e in engs:
+                    e._ring_build(c // world)
+            torch.cuda.synchronize()
         upads = [e.shard_stage() for e in engs]
         assert all(u == upads[0] for u in upads)
         torch.cuda.synchronize()
