@@ -310,6 +310,7 @@ def main():
     ap.add_argument("--no-plan-sharing", action="store_true",
                     help="N>1, row-sharded tables: every rank builds the plan of every chunk itself (round-2 behaviour) instead "
                          "of taking turns and pulling slices over peer memory")
+    ap.add_argument("--step-priority", action="store_true", help="run the steps on a high-priority CUDA stream (experiment)")
     ap.add_argument("--no-graph", action="store_true",
                     help="launch every step's kernels one by one instead of one CUDA graph per plan chunk (N=1)")
     ap.add_argument("--no-topk", action="store_true", help="skip the cfg5 top-k record of the default N=1 run")
@@ -375,6 +376,10 @@ def main():
 
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    if args.step_priority:
+        # the step kernels run on a high-priority stream: when a plan-construction kernel (side streams, default priority)
+        # and a step kernel both have blocks pending, the SMs take the step's first
+        torch.cuda.set_stream(torch.cuda.Stream(device=dev, priority=-1))
     sampler = ClockSampler(local_rank)          # started early: nvidia-smi takes a while to deliver its first sample
     if rank == 0:
         sampler.start()

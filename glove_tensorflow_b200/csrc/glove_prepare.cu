@@ -337,9 +337,28 @@ __global__ void __launch_bounds__(256) plan_pull_head_kernel(const PullArgs a) {
         default: copy_i32(D.need_off, S.need_off, (int64_t)a.K * kMaxShards * W); break;
     }
 }
+// element range [lo, hi) of an array, this CTA's share: 4 independent loads per thread in flight (remote reads over
+// NVLink cost ~2-3 us each; the copy is bound by how many of them are outstanding)
 template <typename T>
 __device__ __forceinline__ void copy_part(T *dst, const T *src, int lo, int hi, int part, int nparts) {
-    for (int i = lo + part * blockDim.x + threadIdx.x; i < hi; i += nparts * blockDim.x) dst[i] = src[i];
+    const int stride = nparts * blockDim.x;
+    int i = lo + part * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < hi; i += 4 * stride) {
+        const T a = src[i], b = src[i + stride], c = src[i + 2 * stride], d = src[i + 3 * stride];
+        dst[i] = a; dst[i + stride] = b; dst[i + 2 * stride] = c; dst[i + 3 * stride] = d;
+    }
+    for (; i < hi; i += stride) dst[i] = src[i];
+}
+// int32 arrays: source and destination have the same layout (same offset from a 256-byte aligned base), so the 16-byte
+// aligned middle of the range goes as int4
+__device__ __forceinline__ void copy_part32(int32_t *dst, const int32_t *src, int lo, int hi, int part, int nparts) {
+    const int lo4 = (lo + 3) & ~3, hi4 = hi & ~3;
+    if (lo4 >= hi4) { copy_part(dst, src, lo, hi, part, nparts); return; }
+    copy_part(reinterpret_cast<int4 *>(dst), reinterpret_cast<const int4 *>(src), lo4 >> 2, hi4 >> 2, part, nparts);
+    if (part == 0) {
+        for (int i = lo + threadIdx.x; i < lo4; i += blockDim.x) dst[i] = src[i];
+        for (int i = hi4 + threadIdx.x; i < hi; i += blockDim.x) dst[i] = src[i];
+    }
 }
 // grid = K * 2 * nparts CTAs: CTA (k, side, part) copies every nparts-th 256-element block of each range of batch k
 __global__ void __launch_bounds__(256) plan_pull_body_kernel(const PullArgs a, int nparts) {
@@ -350,11 +369,11 @@ __global__ void __launch_bounds__(256) plan_pull_body_kernel(const PullArgs a, i
     // offsets come from the local copy (written by the head kernel, one launch earlier on the same stream)
     const int g0 = D.b_seg[k] + D.b_own[k * W + r], g1 = D.b_seg[k] + D.b_own[k * W + r + 1];
     if (g1 > g0) {
-        copy_part(D.seg_id, S.seg_id, g0, g1, part, nparts);
-        copy_part(D.seg_prev, S.seg_prev, g0, g1, part, nparts);
-        copy_part(D.seg_push, S.seg_push, g0, g1, part, nparts);
-        copy_part(D.seg_long, S.seg_long, g0, g1, part, nparts);
-        copy_part(D.seg_start, S.seg_start, g0, g1 + 1, part, nparts);
+        copy_part32(D.seg_id, S.seg_id, g0, g1, part, nparts);
+        copy_part32(D.seg_prev, S.seg_prev, g0, g1, part, nparts);
+        copy_part32(D.seg_push, S.seg_push, g0, g1, part, nparts);
+        copy_part32(D.seg_long, S.seg_long, g0, g1, part, nparts);
+        copy_part32(D.seg_start, S.seg_start, g0, g1 + 1, part, nparts);
         const int q0 = S.seg_start[g0], q1 = S.seg_start[g1];
         copy_part(D.rec, S.rec, q0, q1, part, nparts);
     }
@@ -363,8 +382,8 @@ __global__ void __launch_bounds__(256) plan_pull_body_kernel(const PullArgs a, i
     // request lists: the rows shard r needs (from every owner), and the rows every other shard needs from owner r
     const int32_t *off = D.need_off + (int64_t)k * kMaxShards * W;
     for (int q = 0; q < a.n_shards; ++q) {
-        if (q == r) copy_part(D.need_pos, S.need_pos, off[r * W], off[r * W + a.n_shards], part, nparts);
-        else copy_part(D.need_pos, S.need_pos, off[q * W + r], off[q * W + r + 1], part, nparts);
+        if (q == r) copy_part32(D.need_pos, S.need_pos, off[r * W], off[r * W + a.n_shards], part, nparts);
+        else copy_part32(D.need_pos, S.need_pos, off[q * W + r], off[q * W + r + 1], part, nparts);
     }
 }
 

@@ -86,7 +86,7 @@ struct StepWs {
     float *own_scal;          // [4] this rank's loss sums of the current step (one-call sharded step)
     size_t bytes;
 };
-static inline int64_t snapshot_rows(int32_t B) { return (int64_t)B + B / 4 + 64; }  // room for padded shard blocks
+__host__ __device__ static inline int64_t snapshot_rows(int32_t B) { return (int64_t)B + B / 4 + 64; }  // room for padded shard blocks
 static inline int64_t max_parts_per_batch(int32_t B) { return 2 * (int64_t)B / kItemMax + 2; }
 static StepWs step_ws_view(void *base, int32_t B, int32_t d) {
     StepWs w;
@@ -163,6 +163,12 @@ __device__ __forceinline__ bool batch_index(const StepParams &p, int &k, int &st
     if (p.hdr->magic != kPlanMagic || k < 0 || k >= p.hdr->K || p.hdr->B != p.B ||
         (p.opt == GLOVE_OPT_ADAM && step >= p.alpha_len)) {
         if (threadIdx.x == 0 && blockIdx.x == 0) p.sc->error = 1;
+        return false;
+    }
+    // row-sharded tables: the padded owner blocks of this batch must fit the snapshot (a batch whose ids pile up on one owner
+    // does not); checked here, by every kernel of the step, so that the host need not read the block sizes back per chunk
+    if (p.n_shards > 1 && (int64_t)p.n_shards * max(p.side[0].b_upad[k], p.side[1].b_upad[k]) > snapshot_rows(p.B)) {
+        if (threadIdx.x == 0 && blockIdx.x == 0) p.sc->error = 3;
         return false;
     }
     return true;

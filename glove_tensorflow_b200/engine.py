@@ -273,7 +273,8 @@ class GloveEngine:
         out["g"] = np.float32(sc["g"])
         out["step"] = sc["step"]
         if sc["error"]:
-            raise _lib.GloveError("device-side error flag set (plan / step mismatch)")
+            raise _lib.GloveError("device-side error flag %d set (1: plan / step mismatch, 2: non-finite loss, 3: shard blocks "
+                                  "too unbalanced for the snapshot buffer)" % sc["error"])
         return out
 
     def row_embeddings(self) -> torch.Tensor:
@@ -610,10 +611,6 @@ class GloveEngine:
         if (s % self.K or s + self.K > self.max_steps or (self.dp_world > 1 and not shard_ok) or self._plan_override is not None
                 or self.adam_mode in ("replay_exact", "dense")):
             return 0
-        if shard_ok:      # the host-side check of the padded block sizes, once per chunk instead of once per step
-            for t in range(s, s + self.K):
-                if self.dp_world * max(self._shard_info(t)[1]) > lib.glove_step_snapshot_rows(self.B):
-                    raise _lib.GloveError("shard blocks too unbalanced for the snapshot buffer")
         if self.sample_idx is not None and s + self.K - self.sample_idx_first > self.sample_idx.shape[0]:
             return 0
         which = self._plan_for(s)
@@ -791,11 +788,10 @@ class GloveEngine:
         if self.shard_exchange in ("peer-sync", "peer-push"):
             # the whole step is device work: stage -> announce -> pull (waits owner by owner) -> update -> announce + wait +
             # finish, with flags and loss sums exchanged through the peer-mapped workspaces
+            # (padded owner blocks that do not fit the snapshot are refused by the kernels themselves -- error flag 3, the step
+            # counter stops -- so the host does not read the block sizes back, which would drain the stream once per chunk)
             which = self._plan_for(self.host_step)
             self._before_step(which)
-            own, upad = self._shard_info(self.host_step)
-            if self.dp_world * max(upad) > lib.glove_step_snapshot_rows(self.B):
-                raise _lib.GloveError("shard blocks too unbalanced for the snapshot buffer (%d x %d rows)" % (self.dp_world, max(upad)))
             check(lib.glove_shard_train_step(ctypes.byref(self._args[which]), _stream()), "glove_shard_train_step")
             self._after_step()
             self.host_step += 1
