@@ -69,6 +69,8 @@ struct StepParams {
     int64_t sync_off, scal_off;  // byte offsets of the two areas inside a workspace (same layout on every rank)
     int32_t dev_sync;
     float *const *push_snap;     // peer_gather == 4: [2][kMaxShards] snapshot bases of the peers the stage pushes rows to
+    int32_t fused_sync;          // peer_gather == 4: the stage kernel announces its block itself, the update kernel waits for the owners
+    int32_t *stage_ticket;       // CTAs of the stage kernel that have finished (self-resetting)
 };
 
 struct StepWs {
@@ -101,7 +103,7 @@ static StepWs step_ws_view(void *base, int32_t B, int32_t d) {
     w.peer_tab = (const float **)take(sizeof(float *) * 2 * kMaxShards);
     for (int s = 0; s < 2; ++s) w.gap[s] = (int32_t *)take(sizeof(int32_t) * (size_t)snapshot_rows(B));
     w.loss_acc = (unsigned long long *)take(sizeof(unsigned long long) * 6);
-    w.item_ctr = (int32_t *)take(sizeof(int32_t) * 2);
+    w.item_ctr = (int32_t *)take(sizeof(int32_t) * 4);   // [2] = ticket of the stage kernel (fused announcement)
     w.sync = (int32_t *)take(sizeof(int32_t) * 32);
     w.peer_scal = (float *)take(sizeof(float) * 4 * kMaxShards);
     w.peer_base = (char **)take(sizeof(char *) * kMaxShards);
@@ -189,6 +191,20 @@ __device__ __forceinline__ void head_eval(int head, float z, float a, float b, f
         l = a * softplus_f(-z) + nf * (b * softplus_f(z));
         e = (a * (sg - 1.0f) + nf * b * sg) * invB;
     }
+}
+
+// device-side synchronisation over peer memory (see sync_staged_kernel / finish_sync_kernel below)
+enum { SYNC_STAGED = 0, SYNC_UPDATED = 8, SYNC_EPOCH = 16 };
+__device__ __forceinline__ int ld_acquire_sys(const int32_t *p) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(int32_t *p, int v) {
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int32_t *peer_sync(const StepParams &p, int q) {
+    return reinterpret_cast<int32_t *>(p.peer_base[q] + p.sync_off);
 }
 
 // ---- K1: stage -----------------------------------------------------------------------------------------------------
@@ -341,7 +357,8 @@ __global__ void __launch_bounds__(256, 2) stage_closed_kernel(const StepParams p
     int k, step;
     const bool ok = batch_index(p, k, step);
     replay_tables_init(tabs, p.b1, p.b2);
-    if (!ok) return;
+    if (!ok && !p.fused_sync) return;
+    if (!ok) k = 0;     // fused announcement: a refused step stages nothing (total = 0 below) but still announces, or the peers would wait for ever
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     const int S4 = p.S >> 2;
@@ -351,7 +368,7 @@ __global__ void __launch_bounds__(256, 2) stage_closed_kernel(const StepParams p
     const int g_r = p.side[0].b_seg[k] + own_r, g_c = p.side[1].b_seg[k] + own_c;         // first owned segment of each side
     const int pos_r = p.shard * p.side[0].b_upad[k], pos_c = p.shard * p.side[1].b_upad[k]; // first snapshot row of the block
     const int64_t id0 = (int64_t)p.shard * p.v_loc;
-    const int total = U0 + U1;
+    const int total = ok ? U0 + U1 : 0;
     const uint64_t pol_stream = p.l2_hints ? l2_policy_evict_first() : l2_policy_evict_normal();
     const uint64_t pol_keep = p.l2_hints ? l2_policy_evict_last() : l2_policy_evict_normal();
     float4 xn[NV], mn[NV], vn[NV];
@@ -426,6 +443,20 @@ __global__ void __launch_bounds__(256, 2) stage_closed_kernel(const StepParams p
         }
     }
     if (p.push_snap && lane == 0) bulk_wait_all();   // every pushed row has left before the kernel (and its announcement) ends
+    if (p.fused_sync) {
+        // fused announcement (instead of the sync_staged_kernel launch): the last CTA to finish tells every peer that this
+        // rank's block -- and every row it pushed -- of the current step is complete
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            if (atomicAdd(p.stage_ticket, 1) == (int)gridDim.x - 1) {
+                *p.stage_ticket = 0;
+                __threadfence_system();
+                const int epoch = p.sync[SYNC_EPOCH];
+                for (int q = 0; q < p.n_shards; ++q) st_release_sys(peer_sync(p, q) + SYNC_STAGED + p.shard, epoch + 1);
+            }
+        }
+    }
 }
 
 // second half of the catch-up: mark the pre-replayed rows current (same predicate as stage_kernel<true>)
@@ -662,6 +693,16 @@ template <int NV, int HEAD, bool DP>
 __global__ void __launch_bounds__(128, (NV <= 3 ? 4 : 3)) update_kernel(const StepParams p) {
     int k, step;
     if (!batch_index(p, k, step)) return;
+    if (p.fused_sync) {
+        // fused wait (instead of the wait_staged_kernel launch): the rows this CTA gathers were pushed by their owners' stage
+        // kernels; one thread polls the owners' announcements in this rank's own memory, the CTA waits at the barrier
+        if (threadIdx.x == 0) {
+            const int epoch = p.sync[SYNC_EPOCH];
+            for (int q = 0; q < p.n_shards; ++q)
+                while (ld_acquire_sys(p.sync + SYNC_STAGED + q) < epoch + 1) __nanosleep(64);
+        }
+        __syncthreads();
+    }
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     const int S4 = p.S >> 2;
@@ -883,20 +924,6 @@ __global__ void __launch_bounds__(256) exchange_kernel(const StepParams p, float
     }
 }
 
-// device-side synchronisation over peer memory (see sync_staged_kernel / finish_sync_kernel below)
-enum { SYNC_STAGED = 0, SYNC_UPDATED = 8, SYNC_EPOCH = 16 };
-__device__ __forceinline__ int ld_acquire_sys(const int32_t *p) {
-    int v;
-    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(int32_t *p, int v) {
-    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ int32_t *peer_sync(const StepParams &p, int q) {
-    return reinterpret_cast<int32_t *>(p.peer_base[q] + p.sync_off);
-}
-
 // PULL (peer-mapped workspaces): every row this shard's work items need from another owner is read ONCE from that owner's
 // snapshot over NVLink and written to the same position of the local snapshot -- pack + all-to-all + unpack in one launch,
 // with no send / receive buffers.  One warp per row, two rows in flight per warp.
@@ -1060,11 +1087,13 @@ __global__ void apply_finish_kernel(const StepParams p, const float *reduced) {
 // measurement switch, read once from the environment (default = the shipped configuration)
 struct Tuning {
     int l2_hints;        // GLOVE_L2_HINTS (default 1): L2 eviction-priority hints on table / snapshot traffic
+    int fused_sync;      // GLOVE_FUSED_SYNC (default 0): peer-push announcement / wait inside the stage / update kernels
 };
 static const Tuning &tuning() {
     static const Tuning t = [] {
-        Tuning v{1};
+        Tuning v{1, 0};
         if (const char *e = getenv("GLOVE_L2_HINTS")) v.l2_hints = atoi(e) != 0;
+        if (const char *e = getenv("GLOVE_FUSED_SYNC")) v.fused_sync = atoi(e) != 0;
         return v;
     }();
     return t;
@@ -1100,6 +1129,8 @@ static int fill_params(const glove_step_args *a, StepParams &p, int mode) {
     p.sync_off = (char *)w.sync - (char *)a->workspace; p.scal_off = (char *)w.peer_scal - (char *)a->workspace;
     p.dev_sync = (a->peer_gather >= 3 && a->n_shards > 1) ? 1 : 0;
     p.push_snap = (a->peer_gather == 4 && a->n_shards > 1) ? (float *const *)w.peer_tab : nullptr;
+    p.fused_sync = 0;               // set by glove_shard_train_step only: callers that drive the phases themselves keep the launches
+    p.stage_ticket = w.item_ctr + 2;
     p.l2b1 = replay_log2(a->beta1); p.l2b2 = replay_log2(a->beta2);
     p.l2_hints = tuning().l2_hints;
     p.grad_scalars = nullptr;
@@ -1348,15 +1379,16 @@ int glove_grad_step(const glove_step_args *args, float *grad_rows, float *grad_c
     return dispatch(p, (cudaStream_t)stream);
 }
 
-int glove_shard_stage_step(const glove_step_args *args, void *stream) {
+// fused: the peer-push announcement / wait happen inside the stage / update kernels (one-call step only)
+static int shard_stage(const glove_step_args *args, void *stream, int fused) {
     StepParams p;
     int rc = fill_params(args, p, MODE_SHARD);
     if (rc != GLOVE_OK) return rc;
     p.run_update = 0;
+    p.fused_sync = fused;
     return dispatch(p, (cudaStream_t)stream);
 }
-
-int glove_shard_update_step(const glove_step_args *args, float *loss_scalars, void *stream) {
+static int shard_update(const glove_step_args *args, float *loss_scalars, void *stream, int fused) {
     StepParams p;
     int rc = fill_params(args, p, MODE_SHARD);
     if (rc != GLOVE_OK) return rc;
@@ -1364,7 +1396,12 @@ int glove_shard_update_step(const glove_step_args *args, float *loss_scalars, vo
     p.grad_scalars = loss_scalars;
     p.dp_world = 1;           // ownership is by segment, not by triple
     p.run_stage = 0;
+    p.fused_sync = fused;
     return dispatch(p, (cudaStream_t)stream);
+}
+int glove_shard_stage_step(const glove_step_args *args, void *stream) { return shard_stage(args, stream, 0); }
+int glove_shard_update_step(const glove_step_args *args, float *loss_scalars, void *stream) {
+    return shard_update(args, loss_scalars, stream, 0);
 }
 
 int glove_shard_pack_step(const glove_step_args *args, float *send_buf, void *stream) {
@@ -1426,10 +1463,13 @@ int glove_shard_finish_sync(const glove_step_args *args, const float *loss_scala
 int glove_shard_train_step(const glove_step_args *args, void *stream) {
     GLOVE_REQUIRE(args && args->workspace, "glove_shard_train_step: null args");
     float *scal = step_ws_view(args->workspace, args->B, args->d).own_scal;
-    int rc = glove_shard_stage_step(args, stream);
-    if (rc == GLOVE_OK) rc = glove_shard_signal_staged(args, stream);
-    if (rc == GLOVE_OK) rc = args->peer_gather == 4 ? glove_shard_wait_staged(args, stream) : glove_shard_pull_step(args, stream);
-    if (rc == GLOVE_OK) rc = glove_shard_update_step(args, scal, stream);
+    // peer-push with the closed-form Adam stage: announcement and wait can live inside the two big kernels (3 launches per step)
+    const int fused = tuning().fused_sync && args->peer_gather == 4 && args->n_shards > 1 && args->optimizer == GLOVE_OPT_ADAM &&
+                      args->adam_mode == GLOVE_ADAM_REPLAY;
+    int rc = shard_stage(args, stream, fused);
+    if (rc == GLOVE_OK && !fused) rc = glove_shard_signal_staged(args, stream);
+    if (rc == GLOVE_OK && !fused) rc = args->peer_gather == 4 ? glove_shard_wait_staged(args, stream) : glove_shard_pull_step(args, stream);
+    if (rc == GLOVE_OK) rc = shard_update(args, scal, stream, fused);
     if (rc == GLOVE_OK) rc = glove_shard_finish_sync(args, scal, stream);
     return rc;
 }

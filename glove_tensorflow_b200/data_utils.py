@@ -64,7 +64,37 @@ def read_header(train_csv, limit=1 << 20):
     return names, min(end + 1, len(head))
 
 
-def make_schema(names, row_name, col_name, value_names):
+def read_sample_records(train_csv, offset, n=100, limit=1 << 20):
+    """The first ``n`` data records (lists of fields) after byte ``offset`` -- what make_csv_dataset's
+    num_rows_for_inference=100 looks at to decide a column's dtype [ref src/models/data_utils.py:19]."""
+    import csv
+    import io
+    with open(train_csv, "rb") as f:
+        f.seek(offset)
+        text = f.read(limit).decode("utf8", errors="replace")
+    out = []
+    try:
+        for rec in csv.reader(io.StringIO(text, newline="")):
+            if rec:
+                out.append(rec)
+            if len(out) > n:
+                break
+    except csv.Error:
+        pass
+    return out[:n] if len(out) > n or len(text) < limit else out[:-1]   # a record cut by the read limit is dropped
+
+
+def _int_like(field):
+    import re
+    return re.fullmatch(r"[+-]?[0-9]+", field.strip()) is not None
+
+
+def make_schema(names, row_name, col_name, value_names, sample=None):
+    """Column positions and kinds.  A key column (row / col) is a TOKEN column -- resolved through vocab.txt like the
+    reference's string_id_table.lookup [ref src/models/estimator.py:27-28] -- unless its values are integers, in which case
+    they are taken as ids directly.  Like make_csv_dataset the kind is inferred from the data (``sample`` = the first
+    records, see read_sample_records): a string column called 'user_id' is still a token column.  Without a sample the
+    name decides ('*_id' = integer ids)."""
     from . import _lib
     sc = _lib.CsvSchema()
     sc.n_cols = len(names)
@@ -72,7 +102,13 @@ def make_schema(names, row_name, col_name, value_names):
         if name not in names:
             raise ValueError("column %r not in the csv header %r" % (name, names))
         sc.column[c] = names.index(name)
-        sc.kind[c] = _lib.CSV_FLOAT if c >= 2 else (_lib.CSV_INT if name.endswith("_id") else _lib.CSV_TOKEN)
+        if c >= 2:
+            sc.kind[c] = _lib.CSV_FLOAT
+        elif sample:
+            col = sc.column[c]
+            sc.kind[c] = _lib.CSV_INT if all(len(r) > col and _int_like(r[col]) for r in sample) else _lib.CSV_TOKEN
+        else:
+            sc.kind[c] = _lib.CSV_INT if name.endswith("_id") else _lib.CSV_TOKEN
     return sc
 
 
@@ -136,7 +172,7 @@ def ingest_csv(train_csv, vocab_txt, row_name="row_token", col_name="col_token",
         raise ValueError("exactly two value columns are read (target, weight) / (pos, neg)")
     dev = torch.device(device)
     names, data_off = read_header(train_csv)
-    schema = make_schema(names, row_name, col_name, value_names)
+    schema = make_schema(names, row_name, col_name, value_names, sample=read_sample_records(train_csv, data_off))
     size = os.path.getsize(train_csv) - data_off
     parts = {k: [] for k in ("row", "col", "a", "b")}
     with torch.cuda.device(dev):

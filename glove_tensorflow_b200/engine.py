@@ -466,6 +466,17 @@ class GloveEngine:
         if self.overlap:
             self._ev_step_done[self.host_step & 1].record(torch.cuda.current_stream())
 
+    def _dense_flush(self):
+        """adam_mode == 'dense' (the literal dense sweep): bring every row up to date after the step that has just been
+        counted.  The sweep rewrites rows that the catch-up of a later step may replay, so the step's completion event --
+        what that catch-up waits for -- is recorded again BEHIND the sweep (a host that runs ahead of the device would
+        otherwise let the two overlap)."""
+        if self.adam_mode != "dense":
+            return
+        self.flush()
+        if self.overlap:
+            self._ev_step_done[(self.host_step - 1) & 1].record(torch.cuda.current_stream())
+
     # ---- shared plan construction (row-sharded tables over peer memory) ------------------------------------------------
     # Every rank of a row-sharded job needs the plan of the GLOBAL batch but dereferences only the ~1/world of it that
     # describes its own segments, and building it (two radix sorts + ~30 passes over K * B_global elements) costs as much as
@@ -597,8 +608,7 @@ class GloveEngine:
         check(lib.glove_train_step(ctypes.byref(self._args[which]), _stream()), "glove_train_step")
         self._after_step()
         self.host_step += 1
-        if self.adam_mode == "dense":
-            self.flush()
+        self._dense_flush()
 
     def step_chunk_graph(self) -> int:
         """The K steps of the plan chunk that starts at the current step as ONE CUDA graph launch (captured once per plan
@@ -652,8 +662,7 @@ class GloveEngine:
         check(lib.glove_apply_step(ctypes.byref(self._args[which]), _ptr(gr), _ptr(gc), _ptr(gs), _stream()), "glove_apply_step")
         self._after_step()
         self.host_step += 1
-        if self.adam_mode == "dense":
-            self.flush()
+        self._dense_flush()
 
     # ---- row-sharded data parallel (cfg4): owner-computes ------------------------------------------------------------
     def _shard_info(self, step):
@@ -748,8 +757,7 @@ class GloveEngine:
         check(lib.glove_shard_finish_step(ctypes.byref(self._args[which]), _ptr(self._shard_scalars()), _stream()), "glove_shard_finish_step")
         self._after_step()
         self.host_step += 1
-        if self.adam_mode == "dense":
-            self.flush()
+        self._dense_flush()
 
     def _need_counts(self, step):
         """(rows to send to each peer, rows to receive from each owner) of the request-only exchange of `step`."""
@@ -846,9 +854,9 @@ class GloveEngine:
         which = self._plan_for(self.host_step)
         ms = (ctypes.c_float * 3)()
         check(lib.glove_train_step_profiled(ctypes.byref(self._args[which]), _stream(), ms), "glove_train_step_profiled")
+        self._after_step()
         self.host_step += 1
-        if self.adam_mode == "dense":
-            self.flush()
+        self._dense_flush()
         return tuple(ms)
 
     def train_steps_host(self, host_row, host_col, host_a, host_b, host_losses):
@@ -871,6 +879,9 @@ class GloveEngine:
                                          _ptr(host_losses), _stream()), "glove_train_steps_host")
         self.host_step += steps
         self.plan_first = [None, None]
+        if self.overlap:   # both completion slots (see step_chunk_graph): a later catch-up waits on a current event
+            self._ev_step_done[0].record(torch.cuda.current_stream())
+            self._ev_step_done[1].record(torch.cuda.current_stream())
 
     def train_chunk_from_host(self, host_row, host_col, host_a, host_b):
         """One chunk of K*B explicit triples from pinned HOST tensors (see train_chunks_from_host)."""

@@ -8,11 +8,14 @@ from . import config_utils, data_utils, train_utils
 HEAD = "glove"
 
 
-def build_engine(params, head=HEAD, value_names=None):
+def build_engine(params, head=HEAD, value_names=None, load_coo=True):
+    """``load_coo=False``: tables only (PREDICT needs the checkpoint and vocab.txt, not interaction.csv)."""
     from .engine import GloveEngine
     value_names = value_names or (params["target_name"], params["weight_name"])
-    coo = data_utils.load_interaction_csv(params["train_csv"], params["vocab_txt"], params["row_name"],
-                                          params["col_name"], value_names, device=params.get("device", "cuda:0"))
+    coo = None
+    if load_coo:
+        coo = data_utils.load_interaction_csv(params["train_csv"], params["vocab_txt"], params["row_name"],
+                                              params["col_name"], value_names, device=params.get("device", "cuda:0"))
     vocab_size = data_utils.file_lines(params["vocab_txt"])
     reg_scale = params.get("reg_scale")
     if reg_scale is None:
@@ -23,7 +26,8 @@ def build_engine(params, head=HEAD, value_names=None):
                       batch_size=params["batch_size"], plan_steps=params.get("plan_steps", 16),
                       max_steps=params["train_steps"] + 1, device=params.get("device", "cuda:0"))
     eng.init_uniform(params.get("seed", 0))
-    eng.set_coo(coo["row"], coo["col"], coo[value_names[0]], coo[value_names[1]], shuffle_key=params.get("seed", 0))
+    if coo is not None:
+        eng.set_coo(coo["row"], coo["col"], coo[value_names[0]], coo[value_names[1]], shuffle_key=params.get("seed", 0))
     return eng
 
 
@@ -41,7 +45,7 @@ def estimator_predict(params, input_ids=None):
     """ref estimator_predict (src/models/estimator.py:59-76): PREDICT over every vocab line from the latest checkpoint."""
     import numpy as np
     from .model_utils import get_predictions
-    eng = build_engine(params)
+    eng = build_engine(params, load_coo=False)
     ckpt = train_utils.latest_checkpoint(params["job_dir"])
     if ckpt is None:
         raise FileNotFoundError("no checkpoint in %s" % params["job_dir"])

@@ -80,12 +80,16 @@ def parse_interaction_csv(data: bytes, vocab, row_name, col_name, value_names):
     cols = [header.index(n) for n in (row_name, col_name) + tuple(value_names)]
     out_ids = [[], []]
     out_val = [[], []]
+    # a key column holds ids when its first 100 values are integers (make_csv_dataset's num_rows_for_inference=100
+    # [ref src/models/data_utils.py:19]), tokens otherwise -- whatever the column is called
+    import re
+    is_id = [all(len(r) > cols[s] and re.fullmatch(r"[+-]?[0-9]+", r[cols[s]].strip()) for r in rows[1:101]) for s in range(2)]
     for r in rows[1:]:
         if len(r) != len(header):
             raise ValueError("expected %d fields, got %d" % (len(header), len(r)))
         for s, name in enumerate((row_name, col_name)):
             field = r[cols[s]].encode("latin-1")
-            if name.endswith("_id"):
+            if is_id[s]:
                 v = int(field)
                 if not 0 <= v < len(vocab):
                     raise ValueError("id out of range")

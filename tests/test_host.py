@@ -111,6 +111,17 @@ def test_ingest_host_helpers(tmp_path):
     assert sc.n_cols == 9 and list(sc.column) == [4, 1, 8, 7] and list(sc.kind) == [_lib.CSV_TOKEN, _lib.CSV_INT, _lib.CSV_FLOAT, _lib.CSV_FLOAT]
     with pytest.raises(ValueError):
         data_utils.make_schema(names, "row_token", "nope", ("glove_value", "glove_weight"))
+    # the kind of a key column comes from the data, as in make_csv_dataset: the golden file's id columns hold integers, its
+    # token columns strings; a STRING column that happens to be called '*_id' is a token column
+    sample = data_utils.read_sample_records(csv, off)
+    assert len(sample) == 100 and len(sample[0]) == 9
+    sc = data_utils.make_schema(names, "row_token", "col_token_id", ("glove_value", "glove_weight"), sample=sample)
+    assert list(sc.kind) == [_lib.CSV_TOKEN, _lib.CSV_INT, _lib.CSV_FLOAT, _lib.CSV_FLOAT]
+    u = tmp_path / "u.csv"
+    u.write_text("user_id,item_id,v,w\nalice,7,1.0,1.0\nbob,-3,2.0,1.0\n")
+    un, uoff = data_utils.read_header(str(u))
+    usc = data_utils.make_schema(un, "user_id", "item_id", ("v", "w"), sample=data_utils.read_sample_records(str(u), uoff))
+    assert list(usc.kind)[:2] == [_lib.CSV_TOKEN, _lib.CSV_INT]
     blob, offs = data_utils.vocab_blob(voc)
     vocab = data_utils.read_vocab(voc)
     assert data_utils.file_lines(voc) == len(vocab) == len(offs) - 1 == 61

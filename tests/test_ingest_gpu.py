@@ -112,9 +112,16 @@ def test_malformed_records_fail_loudly(tmp_path):
     csv.write_bytes(b"row_token_id,col_token_id,glove_value,glove_weight\n0,1,1,1\n2,3,1,1\n")
     with pytest.raises(GloveError, match="record 1: id outside"):
         _ingest(csv, voc, "row_token_id", "col_token_id")
-    csv.write_bytes(b"row_token_id,col_token_id,glove_value,glove_weight\n0,1,1,1\n2,1x,1,1\n")
-    with pytest.raises(GloveError, match="record 1: not an integer"):
+    # a key column is an id column when its first 100 values are integers (the rule make_csv_dataset infers dtypes by); a
+    # value that is not an integer further down is an error, never a silent 0
+    csv.write_bytes(b"row_token_id,col_token_id,glove_value,glove_weight\n" + b"0,1,1,1\n" * 100 + b"2,1x,1,1\n")
+    with pytest.raises(GloveError, match="record 100: not an integer"):
         _ingest(csv, voc, "row_token_id", "col_token_id")
+    # ... and a column with a non-integer among its first values is a token column whatever it is called: resolved through
+    # vocab.txt, unknown tokens -> id 0 (the reference's string_id_table default)
+    csv.write_bytes(b"row_token_id,col_token_id,glove_value,glove_weight\nb,a,1,1\na,1x,1,1\n")
+    got = _ingest(csv, voc, "row_token_id", "col_token_id")
+    assert got["row"].tolist() == [2, 1] and got["col"].tolist() == [1, 0]
     csv.write_bytes(head + b"a,b,1,1\n")
     with pytest.raises(ValueError, match="not in the csv header"):
         _ingest(csv, voc, "row_token", "nope")
