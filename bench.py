@@ -16,7 +16,8 @@ shape (V=2.2M; row-sharded tables at N>1); ``topk`` is configs[4] alone (cosine 
 N = 1: whole plan chunks (16 steps) go out as one CUDA-graph launch each (``--no-graph``: step by step); the timed region
 starts after 2,048 real TRAIN steps.  N > 1: row-sharded tables with a frequency-balanced owner map, exchange fused into
 the stage kernel over NVLink peer memory and device-side synchronisation (``--shard-exchange peer-push``; no NCCL on the
-step path); the e2e leg feeds every rank 1/N of each batch from pinned host memory.
+step path), plans built by one rank per chunk and shared over peer memory (``--no-plan-sharing``: every rank builds every
+plan); the e2e leg feeds every rank 1/N of each batch from pinned host memory.
 
 One JSON line is printed by rank 0 (see DESIGN.md "Measurement" for every key).
 """
