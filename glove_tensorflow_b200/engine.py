@@ -588,8 +588,10 @@ class GloveEngine:
     def _ring_pull_chunk(self, c, which):
         """device-resident COO: chunk c = steps [c*K, (c+1)*K) of the keyed shuffle / the injected batch order"""
         # plan buffer `which` belonged to chunk c-2, whose steps were all enqueued before this call
+        from .parallel import shared_plan_slot
         self._ring["pull_stream"].wait_stream(torch.cuda.current_stream())
-        self._ring_pull(c // self.dp_world, c % self.dp_world, which, c * self.K)
+        R, builder, _ = shared_plan_slot(c, self.dp_world)
+        self._ring_pull(R, builder, which, c * self.K)
 
     # ---- train ---------------------------------------------------------------------------------------------------
     def step(self):

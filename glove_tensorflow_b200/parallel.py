@@ -97,3 +97,20 @@ def assemble_chunk(gathered, world, n_steps, b_local):
     order).  Works on torch tensors and numpy arrays alike."""
     g = gathered.reshape(world, 4, n_steps, b_local)
     return g.permute(1, 2, 0, 3) if hasattr(g, "permute") else g.transpose(1, 2, 0, 3)
+
+
+# ---- shared plan construction (GloveEngine.enable_plan_sharing) ----------------------------------------------------------
+def shared_plan_slot(chunk, world):
+    """(round, builder rank, build buffer) of plan chunk ``chunk``: the chunks are dealt round-robin, rank ``chunk % world``
+    builds the plan of chunk ``chunk`` into its build buffer ``round & 1`` while the previous round is being trained on."""
+    r = int(chunk) // int(world)
+    return r, int(chunk) % int(world), r & 1
+
+
+def round_send_buffer(shares, world):
+    """Host-fed rounds: ``shares[q]`` = this rank's share of chunk q of the round, 4 arrays of ``m`` 32-bit words each.
+    Returns the all-to-all send buffer [dest rank q][array][m]: after ``all_to_all_single`` rank q holds
+    [src rank][array][m] -- every rank's share of ITS chunk, the layout ``assemble_chunk`` takes.  numpy in, numpy out
+    (the engine writes the same layout straight into a device buffer)."""
+    assert len(shares) == world and all(len(s) == 4 for s in shares)
+    return np.stack([np.stack([np.asarray(a).view(np.int32).reshape(-1) for a in s]) for s in shares])

@@ -221,6 +221,46 @@ def test_sliced_host_chunks_assemble_to_the_global_batch(tmp_path):
     assert np.array_equal(a, b)
 
 
+def _round_worker(rank, world, port, tmp):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from glove_tensorflow_b200 import parallel
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    K, Bl = 3, 5
+    B, m = Bl * world, K * Bl
+    # chunk q of the round, array j, step k, in-batch position p -> 10000 q + 1000 j + 100 k + p
+    full = np.array([[[[10000 * q + 1000 * j + 100 * k + p for p in range(B)] for k in range(K)] for j in range(4)]
+                     for q in range(world)], np.int32)
+    shares = [[full[q, j].reshape(K, world, Bl)[:, rank, :].reshape(-1) for j in range(4)] for q in range(world)]
+    send = torch.from_numpy(parallel.round_send_buffer(shares, world)).reshape(-1)
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send)                       # rank q receives every rank's share of chunk q
+    got = parallel.assemble_chunk(recv, world, K, Bl).reshape(4, K, B)
+    assert np.array_equal(got.numpy(), full[rank]), rank
+    np.save(os.path.join(tmp, "round%d.npy" % rank), got.numpy())
+    dist.destroy_process_group()
+
+
+def test_shared_plan_round_exchange_hands_every_rank_its_chunk(tmp_path):
+    """Shared plan construction, host-fed path: of a round of `world` chunks every rank holds 1/world of each batch; ONE
+    all-to-all must leave rank q with the whole of chunk q in batch order (world_size 2, gloo).  Plus the round-robin
+    deal itself: consecutive rounds alternate build buffers, a round's chunks have distinct builders."""
+    import torch.multiprocessing as mp
+    sys.path.insert(0, ROOT)
+    from glove_tensorflow_b200 import parallel
+    port = 29500 + (os.getpid() % 2000) + 11
+    mp.spawn(_round_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a, b = np.load(tmp_path / "round0.npy"), np.load(tmp_path / "round1.npy")
+    assert a[0, 0, 0] == 0 and b[0, 0, 0] == 10000           # rank 0 got chunk 0, rank 1 chunk 1
+    for world in (2, 3, 4, 8):
+        slots = [parallel.shared_plan_slot(c, world) for c in range(4 * world)]
+        for R in range(4):
+            rnd = [s for s in slots if s[0] == R]
+            assert sorted(s[1] for s in rnd) == list(range(world)) and {s[2] for s in rnd} == {R & 1}
+
+
 def test_balanced_owner_labels():
     """balance_owners: a permutation of the vocabulary that keeps every owner's row count, keeps id order inside an owner
     and evens out a Zipf head that puts 1.5x the mean work on owner 0 under id % world."""
