@@ -550,13 +550,19 @@ class GloveEngine:
             ev = torch.cuda.Event()
             ev.record(bs)
         ring["built"][R] = ev
-        ring["built"].pop(R - 2, None)
+        for r in [r for r in ring["built"] if r != R and (r & 1) == (R & 1)]:   # the buffer held another round: gone
+            del ring["built"][r]
+            ring["opened"].discard(r)
 
     def _ring_open(self, R):
         ring = self._ring
         if R in ring["opened"]:
             return
-        self._ring_build(R)                      # cold start (or after a reset); otherwise built one round ago
+        if R not in ring["built"]:
+            # cold start, or a round out of order (a plan of earlier steps asked for again): its build overwrites a buffer
+            # that a peer may still be copying a later chunk from -- start over behind a barrier
+            self._ring_reset()
+        self._ring_build(R)                      # normally a no-op: built one round ago
         ps = ring["pull_stream"]
         ps.wait_event(ring["built"][R])
         with torch.cuda.stream(ps):
