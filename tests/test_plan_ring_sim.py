@@ -34,10 +34,10 @@ class Sim:
         self.by_id = {}
         self.records = itertools.count(1)
         self.done = set()
-        self.mem = {}              # device address -> chunk whose complete plan it holds
+        self.mem = {}              # device address -> first step of the complete plan it holds
         self.current = None        # engine whose host code is running
         self.stack = []            # torch.cuda.stream(...) contexts
-        self.executed = {"build": 0, "pull": 0, "step": 0, "read": 0, "barrier": 0}
+        self.executed = {"build": 0, "pull": 0, "step": 0, "read": 0, "barrier": 0, "a2a": 0}
 
     def current_stream(self):
         return self.stack[-1] if self.stack else self.current._main
@@ -106,7 +106,7 @@ def make_world(monkeypatch, world, K, first_step, max_steps):
         return sim.by_id[stream_arg.value]
 
     def prepare(dst, ws, wsb, row, col, ca, cb, nnz, sidx, first_sample, key, first, K_, B, V, n, stream):
-        on(stream).ops.append(("build", dst.value, first // K_))
+        on(stream).ops.append(("build", dst.value, first))
         return 0
 
     def pull(dst, src, K_, B, n, rank, stream):
@@ -122,7 +122,7 @@ def make_world(monkeypatch, world, K, first_step, max_steps):
     def batch_counts(plan, K_, B, k, out, stream):
         eng = sim.current
         which = plan.value - local_ptr(eng.dp_rank, 0)
-        on(stream).ops.append(("read", plan.value, eng.plan_first[which] // K_))
+        on(stream).ops.append(("read", plan.value, eng.plan_first[which]))
         return 0
 
     monkeypatch.setattr(E, "lib", types.SimpleNamespace(glove_prepare_batches_sharded=prepare, glove_plan_pull_slice=pull,
@@ -131,7 +131,7 @@ def make_world(monkeypatch, world, K, first_step, max_steps):
     real_pull = E.GloveEngine._ring_pull
 
     def ring_pull(self, R, j, which, first, after=None):
-        self._expect = first // self.K                  # what the pull about to be issued must find
+        self._expect = first                            # first step of the plan the pull about to be issued must find
         return real_pull(self, R, j, which, first, after)
 
     monkeypatch.setattr(E.GloveEngine, "_ring_pull", ring_pull)
@@ -187,8 +187,8 @@ def execute(sim, rng, bias, limit=None):
             if op[0] == "wait":
                 if op[1] is None or op[1] in sim.done:
                     runnable.append((s, None))
-            elif op[0] in ("barrier", "step"):      # collectives: the ranks' matching calls, all at the head of their queues
-                kind = "pull" if op[0] == "barrier" else "main"
+            elif op[0] in ("barrier", "step", "a2a"):   # collectives: the ranks' matching calls, all at the head of their queues
+                kind = {"barrier": "pull", "step": "main", "a2a": "build"}[op[0]]
                 peers = [t for t in sim.streams if t.kind == kind and t.ops and t.ops[0][0] == op[0] and t.ops[0][-1] == op[-1]]
                 if len(peers) == sim.world:
                     runnable.append((s, peers))
@@ -205,12 +205,13 @@ def execute(sim, rng, bias, limit=None):
             elif op[0] == "build":
                 sim.mem[op[1]] = op[2]
             elif op[0] == "pull":
-                assert sim.mem.get(op[2]) == op[3], "rank %d pulled chunk %r where chunk %r was expected" % (t.rank, sim.mem.get(op[2]), op[3])
+                assert sim.mem.get(op[2]) == op[3], "rank %d pulled the plan of steps %r.. where %r.. was expected" % (t.rank, sim.mem.get(op[2]), op[3])
                 sim.mem[op[1]] = op[3]
             elif op[0] == "step":
-                assert sim.mem.get(op[1]) == op[2] // sim.K, "rank %d ran step %d on the plan of chunk %r" % (t.rank, op[2], sim.mem.get(op[1]))
+                first = sim.mem.get(op[1])
+                assert first is not None and first <= op[2] < first + sim.K, "rank %d ran step %d on the plan of steps %r.." % (t.rank, op[2], first)
             elif op[0] == "read":
-                assert sim.mem.get(op[1]) == op[2], "rank %d read the plan of chunk %r for chunk %r" % (t.rank, sim.mem.get(op[1]), op[2])
+                assert sim.mem.get(op[1]) == op[2], "rank %d read the plan of steps %r.. for %r.." % (t.rank, sim.mem.get(op[1]), op[2])
             if op[0] in sim.executed:
                 sim.executed[op[0]] += 1
         n += 1
@@ -253,3 +254,69 @@ def test_shared_plan_ring_protocol(monkeypatch, world, K, first_step):
         rounds = n_steps / (K * world)
         per_rank = sim.executed["build"] / world
         assert per_rank <= rounds + 4 + (3 if seed % 3 == 1 else 0) + (rounds + 6 if seed % 3 == 2 else 0), (per_rank, rounds, sim.executed)
+
+
+class Anything:
+    """Stand-in for a tensor whose contents do not matter here: every method returns the object itself."""
+    ptrs = itertools.count(500)
+
+    def __init__(self, n=0, is_cuda=True):
+        self.n, self.is_cuda, self.ptr = n, is_cuda, next(Anything.ptrs)
+
+    def numel(self):
+        return self.n
+
+    def data_ptr(self):
+        return self.ptr
+
+    def __getitem__(self, k):
+        return self
+
+    def __mod__(self, k):
+        return self
+
+    def __getattr__(self, name):
+        return lambda *a, **k: self
+
+
+@pytest.mark.parametrize("world,K", [(2, 4), (4, 2), (8, 2)])
+def test_shared_plan_rounds_of_host_fed_chunks(monkeypatch, world, K):
+    """train_chunks_from_host(sliced=True) with shared plans: rounds of `world` chunks -- H2D of the shares, one all-to-all,
+    rank q plans chunk q, slices pulled as the steps reach them -- between stretches of steps on the resident COO (the ring
+    is reset on the way in and out).  Same checks as above, plus matching all-to-all sequences."""
+    import torch.distributed as dist
+    from glove_tensorflow_b200 import engine as E
+    for seed, bias in enumerate(BIASES * 2):
+        rng = random.Random(77 * world + seed)
+        first_step = K * world * rng.randrange(0, 3)
+        sim, engs = make_world(monkeypatch, world, K, first_step, 10 ** 6)
+        sim.K = K
+        monkeypatch.setattr(E.torch, "empty", lambda n, *a, **k: Anything(n if isinstance(n, int) else 0))
+        monkeypatch.setattr(E.torch, "arange", lambda *a, **k: Anything())
+        monkeypatch.setattr(dist, "get_backend", lambda *a, **k: "gloo")
+
+        def a2a(recv, send, group=None):
+            e = sim.current
+            sim.current_stream().ops.append(("a2a", e._a2a))
+            e._a2a += 1
+
+        monkeypatch.setattr(dist, "all_to_all_single", a2a)
+        m = K * 64                                         # a rank's share of a chunk: K steps x B / world triples
+        for e in engs:
+            e._ring["hdl"] = object()
+            e._a2a, e._label, e.loss_cap, e.loss_out = 0, None, 4096, Anything()
+        n_resident = 0
+        for phase in range(3):
+            for _ in range(rng.randrange(0, 2 * K * world)):   # steps on the resident COO
+                for e in engs:
+                    host(sim, e, e._step_sharded)
+                n_resident += 1
+                assert execute(sim, rng, bias, rng.choice([0, 5, 50]))
+            n_chunks = world * rng.randrange(1, 4)
+            chunks = [tuple(Anything(m, is_cuda=False) for _ in range(4)) for _ in range(n_chunks)]
+            for e in engs:                                  # every rank enqueues its whole call; the final loss read drains
+                host(sim, e, e.train_chunks_from_host, chunks, True)
+            assert execute(sim, rng, bias), "deadlock"
+            assert all(e.host_step == engs[0].host_step for e in engs)
+        assert len({e._barriers for e in engs}) == 1 and len({e._a2a for e in engs}) == 1 and engs[0]._a2a > 0
+        assert sim.executed["step"] == world * (engs[0].host_step - first_step)
