@@ -261,6 +261,90 @@ def test_shared_plan_round_exchange_hands_every_rank_its_chunk(tmp_path):
             assert sorted(s[1] for s in rnd) == list(range(world)) and {s[2] for s in rnd} == {R & 1}
 
 
+def _hostfed_worker(rank, world, port, tmp):
+    """The engine's own host-fed path with shared plans (train_chunks_from_host(sliced=True) ->
+    _train_chunks_shared_plans) on CPU tensors over gloo: streams / events / C entry points are stubs, the tensors, the
+    all-to-all and the assembly are real.  What reaches glove_prepare_batches_sharded on rank q in round R must be the
+    whole of chunk R * world + q in batch order."""
+    sys.path.insert(0, ROOT)
+    import contextlib
+    import ctypes
+    import types
+    import torch
+    import torch.distributed as dist
+    from glove_tensorflow_b200 import engine as E
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    class Stream:
+        cuda_stream = 1
+        def wait_event(self, ev): pass
+        def wait_stream(self, other): pass
+
+    class Event:
+        def __init__(self, *a, **k): pass
+        def record(self, stream=None): pass
+
+    E.torch.cuda.Event = Event
+    E.torch.cuda.stream = lambda s: contextlib.nullcontext()
+    E.torch.cuda.current_stream = lambda *a, **k: Stream()
+    K, Bl, rounds = 3, 5, 2
+    B, m = Bl * world, K * Bl
+    seen = {}
+
+    def prepare(dst, ws, wsb, row, col, ca, cb, nnz, sidx, first_sample, key, first, K_, B_, V, n, stream):
+        coo = next(c for c in eng._ring_coo if c[0].data_ptr() == row.value)
+        assert [t.data_ptr() for t in coo] == [row.value, col.value, ca.value, cb.value] and nnz == K * B
+        seen[first] = [t.clone() for t in coo]
+        return 0
+
+    E.lib = types.SimpleNamespace(glove_prepare_batches_sharded=prepare, glove_plan_pull_slice=lambda *a: 0,
+                                  glove_shard_train_step=lambda *a: 0)
+    E.check = lambda rc, what="": None
+    eng = object.__new__(E.GloveEngine)
+    eng.dp_rank, eng.dp_world, eng.sharded, eng.K, eng.B, eng.V_global = rank, world, True, K, B, 1000
+    eng.max_steps, eng.host_step, eng.device = 10 ** 6, 7, torch.device("cpu")
+    eng.optimizer, eng.adam_mode, eng.shard_exchange, eng.overlap = "Adam", "replay", "peer-push", True
+    eng._side, eng._prep_stream = Stream(), Stream()
+    eng.plans = [torch.zeros(8, dtype=torch.uint8), torch.zeros(8, dtype=torch.uint8)]
+    eng.plan_bytes = 64
+    eng.plan_first, eng._plan_counts, eng._plan_shards, eng._plan_need = [None, None], [None, None], [None, None], [None, None]
+    eng._ev_plan, eng._keep, eng._plan_override, eng._ev_catchup = [None, None], [None, None], None, None
+    eng._ev_step_done = [Event(), Event()]
+    eng.prep_ws, eng._ev_coo, eng._label = torch.zeros(8, dtype=torch.uint8), None, None
+    eng.loss_cap, eng.loss_out = 64, torch.zeros(64)
+    eng._args = [ctypes.c_int(0), ctypes.c_int(1)]
+    eng._ring = dict(buf=torch.zeros(128, dtype=torch.uint8), hdl=object(), ptrs=[0] * world, barrier=lambda: None, built={},
+                     opened=set(), ev_barrier=None, keep={}, build_stream=Stream(), pull_stream=Stream(),
+                     builder=eng._ring_build_resident)
+    # chunk c, array j, step k, in-batch position p -> an int pattern for the id arrays, a float pattern for the value arrays
+    def full(c, j):
+        v = np.array([[100000 * c + 10000 * j + 100 * k + p for p in range(B)] for k in range(K)])
+        return v.astype(np.int32) if j < 2 else (v / 7.0).astype(np.float32)
+    chunks = [tuple(torch.from_numpy(np.ascontiguousarray(full(c, j).reshape(K, world, Bl)[:, rank, :]).reshape(-1)) for j in range(4))
+              for c in range(rounds * world)]
+    assert all(t.numel() == m for t in chunks[0])
+    eng.train_chunks_from_host(chunks, sliced=True)
+    assert eng.host_step == 7 + rounds * world * K
+    mine = sorted(seen)                                   # the plans this rank built: chunk R * world + rank of every round
+    assert mine == [7 + (R * world + rank) * K for R in range(rounds)], mine
+    for R in range(rounds):
+        got = seen[7 + (R * world + rank) * K]
+        for j in range(4):
+            exp = full(R * world + rank, j).reshape(-1)
+            assert got[j].dtype == (torch.int32 if j < 2 else torch.float32)
+            assert np.array_equal(got[j].numpy().view(np.int32), exp.view(np.int32)), (R, j)
+    np.save(os.path.join(tmp, "hostfed%d.npy" % rank), np.array(mine))
+    dist.destroy_process_group()
+
+
+def test_shared_plan_host_fed_path_plans_the_whole_chunk(tmp_path):
+    import torch.multiprocessing as mp
+    port = 29500 + (os.getpid() % 2000) + 13
+    mp.spawn(_hostfed_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert np.load(tmp_path / "hostfed0.npy").tolist() == [7, 13] and np.load(tmp_path / "hostfed1.npy").tolist() == [10, 16]
+
+
 def test_balanced_owner_labels():
     """balance_owners: a permutation of the vocabulary that keeps every owner's row count, keeps id order inside an owner
     and evens out a Zipf head that puts 1.5x the mean work on owner 0 under id % world."""
