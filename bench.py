@@ -559,7 +559,17 @@ def main():
             t = torch.tensor([dt], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
+        # the e2e steps are real steps: the device step counter must have followed the host's and no kernel may have refused
+        # its plan (error flag), on any rank -- reported as e2e.steps_verified
+        sc2 = eng.read_scalars()
+        e2e_ok = torch.tensor([1.0 if (sc2["error"] == 0 and sc2["step"] == eng.host_step) else 0.0], device=dev)
+        if world > 1:
+            dist.all_reduce(e2e_ok, op=dist.ReduceOp.MIN)
+        if not bool(e2e_ok.item()):
+            print("bench: e2e leg INVALID on rank %d or a peer (device step %d, host %d, error flag %d)"
+                  % (rank, sc2["step"], eng.host_step, sc2["error"]), file=sys.stderr)
         e2e = {"value": n_chunks * KC * B / dt, "unit": "updates/s", "h2d_bytes_per_step": B * 16,
+               "steps_verified": bool(e2e_ok.item()),    # device step counter == host's and no error flag, on every rank
                "d2h_bytes_per_step": 4 + 4.0 / KC, "steps": n_chunks * KC,
                "path": ("glove_train_steps_host, %d steps per call: pinned host COO -> H2D -> plans -> steps -> D2H losses; inside a "
                         "call the copy + plan of chunk c+1 overlap the steps of chunk c" % KC if N == 1 else
