@@ -320,3 +320,48 @@ def test_shared_plan_rounds_of_host_fed_chunks(monkeypatch, world, K):
             assert all(e.host_step == engs[0].host_step for e in engs)
         assert len({e._barriers for e in engs}) == 1 and len({e._a2a for e in engs}) == 1 and engs[0]._a2a > 0
         assert sim.executed["step"] == world * (engs[0].host_step - first_step)
+
+
+def test_plan_reads_with_host_synchronisation_do_not_deadlock(monkeypatch):
+    """bench.py at N > 1 reads the segment counts of the timed steps back (GloveEngine.batch_counts): plans of EARLIER
+    chunks, asked for out of order, and every call synchronises the caller's step stream on the host.  A rank blocked in
+    that synchronisation depends on barriers its peers have not even enqueued yet; the ranks' hosts run the same loop
+    independently.  Modelled here with one coroutine per rank that may only proceed past a call once its step stream has
+    drained: the loop must complete on every rank, for every world size and schedule."""
+    for world, K, first_step, n_steps in [(2, 16, 2048, 25), (2, 4, 0, 30), (4, 4, 8, 40), (8, 2, 32, 40), (3, 4, 20, 30)]:
+        for seed, bias in enumerate(BIASES):
+            rng = random.Random(31 * world + seed)
+            sim, engs = make_world(monkeypatch, world, K, first_step, 10 ** 6)
+            sim.K = K
+            for s in range(n_steps):
+                for e in engs:
+                    host(sim, e, e._step_sharded)
+                assert execute(sim, rng, bias, rng.choice([0, 10, 100]))
+            assert execute(sim, rng, bias)                       # torch.cuda.synchronize() + barrier after the timed region
+
+            def reader(e):
+                for t in range(first_step, first_step + min(n_steps, 32)):
+                    host(sim, e, e.batch_counts, t)
+                    while e._main.ops:                           # cudaStreamSynchronize inside glove_plan_batch_counts
+                        before = sum(sim.executed.values())
+                        execute(sim, rng, bias, 50)
+                        if e._main.ops and sum(sim.executed.values()) == before:
+                            yield                                # blocked on something a peer's host has yet to enqueue
+                for _ in range(2 * K):                           # ... and training goes on afterwards
+                    host(sim, e, e._step_sharded)
+
+            runs = [reader(e) for e in engs]
+            idle = 0
+            while runs and idle < 4 * world:
+                for g in list(runs):
+                    before = sum(sim.executed.values()) + sum(len(st.ops) for st in sim.streams)
+                    try:
+                        next(g)
+                    except StopIteration:
+                        runs.remove(g)
+                        idle = 0
+                        continue
+                    idle = 0 if sum(sim.executed.values()) + sum(len(st.ops) for st in sim.streams) != before else idle + 1
+            assert not runs, "world %d: the ranks' hosts block one another" % world
+            assert execute(sim, rng, bias), "deadlock"
+            assert len({e._barriers for e in engs}) == 1 and sim.executed["read"] == world * min(n_steps, 32)
