@@ -117,6 +117,19 @@ def test_ingest_host_helpers(tmp_path):
     assert len(sample) == 100 and len(sample[0]) == 9
     sc = data_utils.make_schema(names, "row_token", "col_token_id", ("glove_value", "glove_weight"), sample=sample)
     assert list(sc.kind) == [_lib.CSV_TOKEN, _lib.CSV_INT, _lib.CSV_FLOAT, _lib.CSV_FLOAT]
+    # fewer records than the sample size, quoted fields with embedded newlines / commas, blank lines, \r\n
+    r = tmp_path / "r.csv"
+    r.write_bytes(b'a,b,c\r\n"x,1","y\nz",3\r\n\r\n7,8,9\r\n')
+    rn, roff = data_utils.read_header(str(r))
+    assert data_utils.read_sample_records(str(r), roff) == [["x,1", "y\nz", "3"], ["7", "8", "9"]]
+    # a record cut by the read limit is not part of the sample
+    big = tmp_path / "big.csv"
+    big.write_bytes(b"a,b\n" + b"12345,67890\n" * 50)
+    bn, boff = data_utils.read_header(str(big))
+    cut = data_utils.read_sample_records(str(big), boff, n=100, limit=12 * 10 + 5)
+    assert cut == [["12345", "67890"]] * 10
+    assert [data_utils._int_like(x) for x in ("7", "-3", "+12", " 5 ", "", "1.0", "1e3", "a1", "--1")] == \
+        [True, True, True, True, False, False, False, False, False]
     u = tmp_path / "u.csv"
     u.write_text("user_id,item_id,v,w\nalice,7,1.0,1.0\nbob,-3,2.0,1.0\n")
     un, uoff = data_utils.read_header(str(u))
