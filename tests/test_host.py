@@ -6,6 +6,7 @@ import numpy as np
 import pytest
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden", "text8_small")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_cli_flags_and_defaults_match_the_reference():
@@ -256,3 +257,29 @@ def test_tensorboard_event_files_round_trip(tmp_path):
     z = ev[1]["histograms"]["mf/col_biases"]
     assert z["num"] == 7 and z["bucket"].sum() == 7 and z["min"] == z["max"] == 0.0
     assert ev[2]["scalars"] == {"loss": 1.0}
+
+
+def test_bench_reference_arm_line_and_rank_gating():
+    """bench.py --impl reference (the arm the driver runs beside the GPU arm): one JSON line with the contract's keys on the
+    host cores; under torchrun only rank 0 works and prints, the other ranks exit 0 without output."""
+    import json
+    import subprocess
+    import sys
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "text8", "--steps", "4", "--warmup", "3"]
+    env = dict(os.environ, RANK="0", WORLD_SIZE="1")
+    out = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and j["metric"] == "co-occurrence updates/sec" and j["unit"] == "updates/s"
+    assert j["higher_is_better"] is True and j["scaling"] == "weak" and j["vs_baseline"] is None and j["dtype"] == "f32"
+    assert j["steps"] == 4 and j["warmup"] == 3 and j["value"] > 0 and abs(j["value"] - 65536 / (j["ms_per_step"] * 1e-3)) < 1e-3 * j["value"]
+    assert j["config"]["workload"].startswith("text8:") and j["config"]["global_batch"] == 65536
+    cb = j["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == j["value"] and "TRAIN steps" in cb["sample"]
+    assert j["e2e"] == {"value": j["value"], "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # rank 1 of a 2-rank launch: exits 0 without work or output
+    out = subprocess.run(cmd + ["--gpus", "2"], capture_output=True, text=True, env=dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1"),
+                         timeout=60)
+    assert out.returncode == 0 and out.stdout.strip() == ""
