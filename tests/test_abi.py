@@ -102,6 +102,12 @@ def test_argument_errors_are_reported_without_a_gpu():
     assert rc == _lib.EINVAL
     args = _lib.StepArgs()
     assert _lib.lib.glove_train_step(ctypes.byref(args), None) == _lib.EINVAL
+    # shared plan construction: null plans, a world of one, a shard outside the world
+    pull = _lib.lib.glove_plan_pull_slice
+    assert pull(None, None, 4, 64, 2, 0, None) == _lib.EINVAL and b"glove_plan_pull_slice" in _lib.lib.glove_last_error()
+    one = ctypes.c_void_p(256)
+    assert pull(one, one, 4, 64, 1, 0, None) == _lib.EINVAL and pull(one, one, 4, 64, 4, 4, None) == _lib.EINVAL
+    assert pull(one, one, 0, 64, 2, 0, None) == _lib.EINVAL and pull(one, one, 4, 64, 9, 0, None) == _lib.EINVAL
     with pytest.raises(_lib.GloveError):
         _lib.check(rc, "probe")
 
