@@ -310,6 +310,11 @@ class GloveEngine:
         for side, t in enumerate((self.row_table, self.col_table)):
             check(fn(_ptr(t), self.V, self.d, self.opt_id, side, _ptr(self.alpha), self.max_steps,
                      self.host_step, ADAM_BETA1, ADAM_BETA2, KERAS_EPSILON, _stream()), "glove_flush_lazy_state")
+        if self.overlap and self.adam_mode in ("replay_exact", "dense"):
+            # the sweep rewrites rows that the look-ahead catch-up of a later step replays too: that catch-up waits for the
+            # completion event of an earlier step, so both slots are moved BEHIND the sweep
+            for ev in self._ev_step_done:
+                ev.record(torch.cuda.current_stream())
 
     # ---- input ---------------------------------------------------------------------------------------------------
     def set_coo(self, row, col, col_a, col_b, shuffle_key: int = 0):
